@@ -1,0 +1,452 @@
+// Persistent, warp-specialised TMA + tcgen05/TMEM GEMM for sm_100a.
+//
+//   C[M,N] = A[M,K] * W[N,K]^T (+ fused epilogue), bf16 operands, fp32 accumulation in TMEM.
+//
+// Replaces every nn.Linear / 1x1 Conv2d of the reference forward (see include/duoformer_sm100.h
+// for the file:line map).  Structure (one CTA per SM, static round-robin tile scheduler, N
+// fastest so concurrently running CTAs share one A row-panel in L2):
+//
+//   warp 0      TMA producer: A tile 128x64 and W tile BLOCK_Nx64 (both K-major, SWIZZLE_128B)
+//               into a kStages-deep shared-memory ring, completion on `full` mbarriers.
+//   warp 1      MMA issuer: one elected lane issues tcgen05.mma (UMMA 128 x BLOCK_N x 16),
+//               accumulating into one of two TMEM accumulator buffers; tcgen05.commit releases
+//               ring slots (`empty`) and publishes finished accumulators (`tmem_full`).
+//   warps 2..5  epilogue: tcgen05.ld the accumulator (one TMEM lane quarter per warp, one output
+//               row per thread), fuse bias / GELU(erf) / LayerScale+residual / token scatter /
+//               hi-lo split, store to global, then hand the buffer back (`tmem_empty`).
+//               Double-buffered TMEM lets the epilogue of tile i overlap the MMAs of tile i+1.
+//
+// split3 mode (fp32-accuracy path): A and W hold bf16 hi|lo halves; the K loop runs three
+// segments (Ah*Wh, Ah*Wl, Al*Wh) into the same accumulator.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace duo {
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kNumThreads = 192;
+constexpr int kNumEpilogueThreads = 128;
+
+template <int BLOCK_N>
+struct Cfg {
+  static constexpr int kStages = BLOCK_N == 256 ? 4 : 6;
+  static constexpr uint32_t kABytes = kBlockM * kBlockK * 2;   // 16 KB
+  static constexpr uint32_t kBBytes = BLOCK_N * kBlockK * 2;   // 32 / 16 KB
+  static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  static constexpr uint32_t kTmemCols = 2 * BLOCK_N;           // two accumulator buffers
+  static constexpr uint32_t kBarrierBytes = (2 * kStages + 4) * 8 + 8;
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kBarrierBytes + 1024;
+};
+
+struct GemmParams {
+  const float* bias;
+  void* out;
+  const float* gamma;
+  const int32_t* row_map;
+  const float* pos;
+  int64_t M;
+  int64_t ldo;
+  int32_t N, K;
+  int32_t split3;
+  int32_t rows_per_group, dest_rows_per_group, pos_period;
+  int32_t num_m_blocks, num_n_blocks;
+};
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_store(const GemmParams& p, int64_t row, int col,
+                                               uint32_t (&v)[32]) {
+  // v holds 32 consecutive fp32 accumulator columns [col, col+32) of output row `row`.
+  float f[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+  if (p.bias != nullptr) {
+    const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 b = __ldg(b4 + j);
+      f[4 * j + 0] += b.x;
+      f[4 * j + 1] += b.y;
+      f[4 * j + 2] += b.z;
+      f[4 * j + 3] += b.w;
+    }
+  }
+  if constexpr (EPI == DUO_EPI_GELU_BF16 || EPI == DUO_EPI_GELU_SPLIT_BF16) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+  }
+
+  if constexpr (EPI == DUO_EPI_BF16 || EPI == DUO_EPI_GELU_BF16) {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + col;
+    uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 w;
+      w.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+      w.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+      w.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+      w.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+      o4[j] = w;
+    }
+  } else if constexpr (EPI == DUO_EPI_SPLIT_BF16 || EPI == DUO_EPI_GELU_SPLIT_BF16) {
+    __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + col;
+    __nv_bfloat16* ol = oh + p.N;
+    uint4* h4 = reinterpret_cast<uint4*>(oh);
+    uint4* l4 = reinterpret_cast<uint4*>(ol);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 h, l;
+      pack_split2(f[8 * j + 0], f[8 * j + 1], h.x, l.x);
+      pack_split2(f[8 * j + 2], f[8 * j + 3], h.y, l.y);
+      pack_split2(f[8 * j + 4], f[8 * j + 5], h.z, l.z);
+      pack_split2(f[8 * j + 6], f[8 * j + 7], h.w, l.w);
+      h4[j] = h;
+      l4[j] = l;
+    }
+  } else if constexpr (EPI == DUO_EPI_F32) {
+    float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + row * p.ldo + col);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      o4[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+  } else if constexpr (EPI == DUO_EPI_RESIDUAL_F32) {
+    float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + row * p.ldo + col);
+    float4 r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = o4[j];
+    if (p.gamma != nullptr) {
+      const float4* g4 = reinterpret_cast<const float4*>(p.gamma + col);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 g = __ldg(g4 + j);
+        r[j].x = fmaf(g.x, f[4 * j + 0], r[j].x);
+        r[j].y = fmaf(g.y, f[4 * j + 1], r[j].y);
+        r[j].z = fmaf(g.z, f[4 * j + 2], r[j].z);
+        r[j].w = fmaf(g.w, f[4 * j + 3], r[j].w);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        r[j].x += f[4 * j + 0];
+        r[j].y += f[4 * j + 1];
+        r[j].z += f[4 * j + 2];
+        r[j].w += f[4 * j + 3];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o4[j] = r[j];
+  } else if constexpr (EPI == DUO_EPI_SCATTER_F32) {
+    const int64_t grp = row / p.rows_per_group;
+    const int32_t in_grp = static_cast<int32_t>(row - grp * p.rows_per_group);
+    const int32_t dst_in_grp = __ldg(p.row_map + in_grp);
+    const int64_t dst = grp * p.dest_rows_per_group + dst_in_grp;
+    if (p.pos != nullptr) {
+      const int32_t s = dst_in_grp % p.pos_period;
+      const float4* q4 = reinterpret_cast<const float4*>(p.pos + static_cast<int64_t>(s) * p.N + col);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 q = __ldg(q4 + j);
+        f[4 * j + 0] += q.x;
+        f[4 * j + 1] += q.y;
+        f[4 * j + 2] += q.z;
+        f[4 * j + 3] += q.w;
+      }
+    }
+    float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + dst * p.ldo + col);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      o4[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+  }
+}
+
+template <int BLOCK_N, int EPI>
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                    const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+  using C = Cfg<BLOCK_N>;
+  constexpr int kStages = C::kStages;
+
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024 B alignment.
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + kStages * C::kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
+  auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
+  const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * kStages + 4);
+  uint32_t* tmem_ptr_generic =
+      reinterpret_cast<uint32_t*>(smem_raw + (tmem_ptr_smem - ptx::smem_u32(smem_raw)));
+
+  const int warp_idx = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+
+  if (warp_idx == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_a);
+    ptx::prefetch_tmap(&tmap_b);
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) {
+      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), 1);
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(tmem_full_bar(a), 1);
+      ptx::mbar_init(tmem_empty_bar(a), kNumEpilogueThreads);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp_idx == 1) {
+    ptx::tmem_alloc<C::kTmemCols>(tmem_ptr_smem);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_generic;
+
+  const int kseg_blocks = p.K / kBlockK;
+  const int num_k_blocks = p.split3 ? 3 * kseg_blocks : kseg_blocks;
+  const int64_t num_tiles = static_cast<int64_t>(p.num_m_blocks) * p.num_n_blocks;
+
+  if (warp_idx == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = static_cast<int>(tile / p.num_n_blocks);
+        const int n_blk = static_cast<int>(tile - static_cast<int64_t>(m_blk) * p.num_n_blocks);
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          int a_k, b_k;
+          if (p.split3) {
+            const int seg = kb / kseg_blocks;
+            const int r = kb - seg * kseg_blocks;
+            a_k = (seg == 2 ? p.K : 0) + r * kBlockK;
+            b_k = (seg == 1 ? p.K : 0) + r * kBlockK;
+          } else {
+            a_k = b_k = kb * kBlockK;
+          }
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_base + stage * C::kStageBytes;
+          const uint32_t sb = sa + C::kABytes;
+          ptx::mbar_arrive_expect_tx(full_bar(stage), C::kStageBytes);
+          ptx::tma_load_2d(sa, &tmap_a, full_bar(stage), a_k, m_blk * kBlockM);
+          ptx::tma_load_2d(sb, &tmap_b, full_bar(stage), b_k, n_blk * BLOCK_N);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(kBlockM, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          ptx::mbar_wait(full_bar(stage), phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = smem_base + stage * C::kStageBytes;
+          const uint32_t sb = sa + C::kABytes;
+          const uint64_t desc_a = ptx::make_smem_desc_sw128(sa);
+          const uint64_t desc_b = ptx::make_smem_desc_sw128(sb);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (>>4) address field
+            ptx::umma_bf16(tmem_d, desc_a + static_cast<uint64_t>(2 * k),
+                           desc_b + static_cast<uint64_t>(2 * k), idesc,
+                           (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          ptx::umma_commit(empty_bar(stage));  // ring slot free once these MMAs retire
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        ptx::umma_commit(tmem_full_bar(acc));  // accumulator complete
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..5) =====================
+    const int quarter = warp_idx & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = static_cast<int>(tile / p.num_n_blocks);
+      const int n_blk = static_cast<int>(tile - static_cast<int64_t>(m_blk) * p.num_n_blocks);
+      const int64_t row = static_cast<int64_t>(m_blk) * kBlockM + quarter * 32 + lane;
+      const bool valid = row < p.M;
+      ptx::mbar_wait(tmem_full_bar(acc), acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t taddr =
+          tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(taddr + static_cast<uint32_t>(c), v);
+        ptx::tmem_ld_wait();
+        if (valid) epilogue_store<EPI>(p, row, n_blk * BLOCK_N + c, v);
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(tmem_empty_bar(acc));
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<C::kTmemCols>(tmem_base);
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess) return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  }
+  return fn;
+}
+
+// bf16 [rows, cols] row-major (leading dim ld elements); box = box_rows x 64 cols, 128B swizzle.
+int make_tmap_bf16(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld,
+                   int box_rows) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return DUO_ERR_CUDA;
+  }
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed: CUresult %d (rows=%lld cols=%lld ld=%lld)", (int)r,
+              (long long)rows, (long long)cols, (long long)ld);
+    return DUO_ERR_CUDA;
+  }
+  return DUO_OK;
+}
+
+template <int BLOCK_N, int EPI>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+  using C = Cfg<BLOCK_N>;
+  static bool configured = false;
+  auto kfn = gemm_tcgen05_kernel<BLOCK_N, EPI>;
+  if (!configured) {
+    DUO_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(C::kSmemBytes)));
+    configured = true;
+  }
+  const int64_t tiles = static_cast<int64_t>(p.num_m_blocks) * p.num_n_blocks;
+  const int sms = device_sm_count();
+  const int grid = static_cast<int>(tiles < sms ? tiles : sms);
+  kfn<<<grid, kNumThreads, C::kSmemBytes, st>>>(ta, tb, p);
+  DUO_LAUNCH_CHECK("gemm_tcgen05_kernel");
+  return DUO_OK;
+}
+
+template <int BLOCK_N>
+int dispatch_epi(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int epi,
+                 cudaStream_t st) {
+  switch (epi) {
+    case DUO_EPI_BF16: return launch<BLOCK_N, DUO_EPI_BF16>(ta, tb, p, st);
+    case DUO_EPI_GELU_BF16: return launch<BLOCK_N, DUO_EPI_GELU_BF16>(ta, tb, p, st);
+    case DUO_EPI_RESIDUAL_F32: return launch<BLOCK_N, DUO_EPI_RESIDUAL_F32>(ta, tb, p, st);
+    case DUO_EPI_SCATTER_F32: return launch<BLOCK_N, DUO_EPI_SCATTER_F32>(ta, tb, p, st);
+    case DUO_EPI_F32: return launch<BLOCK_N, DUO_EPI_F32>(ta, tb, p, st);
+    case DUO_EPI_SPLIT_BF16: return launch<BLOCK_N, DUO_EPI_SPLIT_BF16>(ta, tb, p, st);
+    case DUO_EPI_GELU_SPLIT_BF16: return launch<BLOCK_N, DUO_EPI_GELU_SPLIT_BF16>(ta, tb, p, st);
+    default: set_error("duo_gemm: unknown epilogue %d", epi); return DUO_ERR_INVALID;
+  }
+}
+
+}  // namespace
+}  // namespace duo
+
+extern "C" int duo_gemm(const duo_gemm_args* a, duo_stream_t stream) {
+  using namespace duo;
+  DUO_CHECK_ARG(a != nullptr, "duo_gemm: args is NULL");
+  DUO_CHECK_ARG(a->A && a->W && a->out, "duo_gemm: NULL operand");
+  DUO_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0, "duo_gemm: empty problem M=%lld N=%d K=%d",
+                (long long)a->M, a->N, a->K);
+  DUO_CHECK_ARG(a->N % 128 == 0, "duo_gemm: N=%d must be a multiple of 128", a->N);
+  DUO_CHECK_ARG(a->K % kBlockK == 0, "duo_gemm: K=%d must be a multiple of 64", a->K);
+  const int kcols = a->split3 ? 2 * a->K : a->K;
+  DUO_CHECK_ARG(a->lda >= kcols && a->ldw >= kcols && a->lda % 8 == 0 && a->ldw % 8 == 0,
+                "duo_gemm: bad leading dims lda=%lld ldw=%lld", (long long)a->lda, (long long)a->ldw);
+  DUO_CHECK_ARG((reinterpret_cast<uintptr_t>(a->A) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(a->W) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(a->out) & 15) == 0,
+                "duo_gemm: operands must be 16-byte aligned");
+  DUO_CHECK_ARG(a->ldo % 8 == 0, "duo_gemm: ldo=%lld must be a multiple of 8", (long long)a->ldo);
+  if (a->epilogue == DUO_EPI_SCATTER_F32) {
+    DUO_CHECK_ARG(a->row_map && a->rows_per_group > 0 && a->dest_rows_per_group > 0,
+                  "duo_gemm: scatter epilogue needs row_map / group sizes");
+    DUO_CHECK_ARG(a->pos == nullptr || a->pos_period > 0, "duo_gemm: pos_period must be > 0");
+  }
+  DUO_CHECK_ARG(a->M < (int64_t(1) << 31) - 256, "duo_gemm: M too large for a 32-bit TMA coordinate");
+
+  // BLOCK_N: 256 when it divides N and there are enough tiles to fill the machine, else 128.
+  const int64_t m_blocks = (a->M + kBlockM - 1) / kBlockM;
+  int block_n = 128;
+  if (a->N % 256 == 0 && m_blocks * (a->N / 256) >= 2 * device_sm_count()) block_n = 256;
+
+  CUtensorMap ta, tb;
+  int rc = make_tmap_bf16(&ta, a->A, a->M, kcols, a->lda, kBlockM);
+  if (rc != DUO_OK) return rc;
+  rc = make_tmap_bf16(&tb, a->W, a->N, kcols, a->ldw, block_n);
+  if (rc != DUO_OK) return rc;
+
+  GemmParams p;
+  p.bias = a->bias;
+  p.out = a->out;
+  p.gamma = a->gamma;
+  p.row_map = a->row_map;
+  p.pos = a->pos;
+  p.M = a->M;
+  p.ldo = a->ldo;
+  p.N = a->N;
+  p.K = a->K;
+  p.split3 = a->split3 ? 1 : 0;
+  p.rows_per_group = a->rows_per_group;
+  p.dest_rows_per_group = a->dest_rows_per_group;
+  p.pos_period = a->pos_period;
+  p.num_m_blocks = static_cast<int32_t>(m_blocks);
+  p.num_n_blocks = a->N / block_n;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (block_n == 256) return dispatch_epi<256>(ta, tb, p, a->epilogue, st);
+  return dispatch_epi<128>(ta, tb, p, a->epilogue, st);
+}

@@ -1,0 +1,464 @@
+// Grouped multi-head attention over S consecutive rows of a fused qkv matrix (head_dim 64).
+//
+//   scale attention : group = one patch, S = 6 / 22 / 86 scale tokens
+//                     (scale_attention.py:28-45, multiscale_attn.py:149-166)
+//   patch attention : group = one image, S = P+1 tokens
+//                     (scale_attention.py:195-207, multiscale_attn.py:205-216)
+//
+// Two kernels:
+//   algo 1  warp-per-(group, head) register/shuffle kernel: K and V of the head live in shared
+//           memory, each lane owns ceil(S/32) keys, softmax statistics via warp shuffles, all
+//           arithmetic fp32 FMA.  Exact enough for the fp32 mode; HBM-bound for small S.
+//   algo 2  warp-level tensor-core kernel (mma.sync m16n8k16 bf16, fp32 accumulate) for
+//           16 < S <= 96: one CTA of two warps per (group, head), Q/K/V staged once in
+//           XOR-swizzled shared memory via cp.async, scores/probabilities stay in registers
+//           (the accumulator fragment of QK^T is re-used as the A fragment of PV).
+#include "common.cuh"
+
+namespace duo {
+namespace {
+
+constexpr int kHeadDim = 64;
+
+// =============================== algo 1: FMA ===============================================
+template <typename T>
+struct ElemTraits;
+template <>
+struct ElemTraits<__nv_bfloat16> {
+  static constexpr int kWordsPerRow = 32;  // 64 bf16
+};
+template <>
+struct ElemTraits<float> {
+  static constexpr int kWordsPerRow = 64;
+};
+
+template <typename Tin>
+__host__ __device__ constexpr int fma_smem_words_per_warp(int S, int kpl) {
+  // V rows dense, q row, p row, then K rows padded by one word (conflict-free column reads);
+  // rounded up so every warp's region stays 16-byte aligned.
+  const int words =
+      S * ElemTraits<Tin>::kWordsPerRow + 64 + kpl * 32 + S * (ElemTraits<Tin>::kWordsPerRow + 1);
+  return (words + 3) & ~3;
+}
+
+template <typename Tin, int OUT_KIND, int KPL>
+__global__ void group_attention_fma_kernel(const Tin* __restrict__ qkv, void* __restrict__ out,
+                                           int64_t num_problems, int S, int H, float scale) {
+  constexpr int WPR = ElemTraits<Tin>::kWordsPerRow;
+  constexpr int VPR = WPR / 4;          // 16-byte vectors per row
+  constexpr int RPP = 32 / VPR;         // rows loaded per warp pass
+  constexpr bool kIsBf16 = (WPR == 32);
+  extern __shared__ uint32_t smem_words[];
+
+  const int warps_per_cta = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t prob = static_cast<int64_t>(blockIdx.x) * warps_per_cta + warp;
+  if (prob >= num_problems) return;
+  const int64_t g = prob / H;
+  const int h = static_cast<int>(prob - g * H);
+  const int D = H * kHeadDim;
+  const int64_t ld = 3 * static_cast<int64_t>(D);
+
+  uint32_t* Vs = smem_words + static_cast<size_t>(warp) * fma_smem_words_per_warp<Tin>(S, KPL);
+  float* qs = reinterpret_cast<float*>(Vs + S * WPR);
+  float* ps = qs + 64;
+  uint32_t* Ks = reinterpret_cast<uint32_t*>(ps + KPL * 32);
+
+  const Tin* base = qkv + (g * S) * ld + h * kHeadDim;
+  // ---- stage K and V of this head ----
+  for (int r0 = 0; r0 < S; r0 += RPP) {
+    const int r = r0 + lane / VPR;
+    const int vec = lane % VPR;
+    if (r < S) {
+      const uint4 kv = __ldg(reinterpret_cast<const uint4*>(base + r * ld + D) + vec);
+      const uint4 vv = __ldg(reinterpret_cast<const uint4*>(base + r * ld + 2 * D) + vec);
+      uint32_t* kd = Ks + r * (WPR + 1) + vec * 4;
+      kd[0] = kv.x; kd[1] = kv.y; kd[2] = kv.z; kd[3] = kv.w;
+      uint32_t* vd = Vs + r * WPR + vec * 4;
+      vd[0] = vv.x; vd[1] = vv.y; vd[2] = vv.z; vd[3] = vv.w;
+    }
+  }
+  __syncwarp();
+
+  int krow[KPL];
+#pragma unroll
+  for (int kk = 0; kk < KPL; ++kk) {
+    const int j = lane + 32 * kk;
+    krow[kk] = (j < S ? j : S - 1) * (WPR + 1);
+  }
+
+  for (int i = 0; i < S; ++i) {
+    // q row -> shared (fp32)
+    {
+      const Tin* qp = base + i * ld + 2 * lane;
+      float q0, q1;
+      if constexpr (kIsBf16) {
+        const __nv_bfloat162 q2 = *reinterpret_cast<const __nv_bfloat162*>(qp);
+        q0 = __bfloat162float(q2.x);
+        q1 = __bfloat162float(q2.y);
+      } else {
+        const float2 q2 = *reinterpret_cast<const float2*>(qp);
+        q0 = q2.x;
+        q1 = q2.y;
+      }
+      qs[2 * lane] = q0;
+      qs[2 * lane + 1] = q1;
+    }
+    __syncwarp();
+
+    float acc[KPL];
+#pragma unroll
+    for (int kk = 0; kk < KPL; ++kk) acc[kk] = 0.f;
+    if constexpr (kIsBf16) {
+#pragma unroll 8
+      for (int w = 0; w < 32; w += 2) {
+        const float4 q4 = *reinterpret_cast<const float4*>(qs + 2 * w);
+#pragma unroll
+        for (int kk = 0; kk < KPL; ++kk) {
+          const uint32_t k01 = Ks[krow[kk] + w];
+          const uint32_t k23 = Ks[krow[kk] + w + 1];
+          acc[kk] = fmaf(q4.x, __uint_as_float(k01 << 16), acc[kk]);
+          acc[kk] = fmaf(q4.y, __uint_as_float(k01 & 0xffff0000u), acc[kk]);
+          acc[kk] = fmaf(q4.z, __uint_as_float(k23 << 16), acc[kk]);
+          acc[kk] = fmaf(q4.w, __uint_as_float(k23 & 0xffff0000u), acc[kk]);
+        }
+      }
+    } else {
+#pragma unroll 8
+      for (int w = 0; w < 64; w += 4) {
+        const float4 q4 = *reinterpret_cast<const float4*>(qs + w);
+#pragma unroll
+        for (int kk = 0; kk < KPL; ++kk) {
+          const float* kr = reinterpret_cast<const float*>(Ks) + krow[kk] + w;
+          acc[kk] = fmaf(q4.x, kr[0], acc[kk]);
+          acc[kk] = fmaf(q4.y, kr[1], acc[kk]);
+          acc[kk] = fmaf(q4.z, kr[2], acc[kk]);
+          acc[kk] = fmaf(q4.w, kr[3], acc[kk]);
+        }
+      }
+    }
+
+    float m = -INFINITY;
+#pragma unroll
+    for (int kk = 0; kk < KPL; ++kk) {
+      acc[kk] = (lane + 32 * kk < S) ? acc[kk] * scale : -INFINITY;
+      m = fmaxf(m, acc[kk]);
+    }
+    m = warp_max(m);
+    float sum = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < KPL; ++kk) {
+      acc[kk] = (lane + 32 * kk < S) ? __expf(acc[kk] - m) : 0.f;
+      sum += acc[kk];
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int kk = 0; kk < KPL; ++kk) ps[lane + 32 * kk] = acc[kk] * inv;
+    __syncwarp();
+
+    float o0 = 0.f, o1 = 0.f;
+    for (int j = 0; j < S; ++j) {
+      const float pj = ps[j];
+      if constexpr (kIsBf16) {
+        const uint32_t v01 = Vs[j * WPR + lane];
+        o0 = fmaf(pj, __uint_as_float(v01 << 16), o0);
+        o1 = fmaf(pj, __uint_as_float(v01 & 0xffff0000u), o1);
+      } else {
+        const float2 v01 = *reinterpret_cast<const float2*>(Vs + j * WPR + 2 * lane);
+        o0 = fmaf(pj, v01.x, o0);
+        o1 = fmaf(pj, v01.y, o1);
+      }
+    }
+
+    const int64_t orow = g * S + i;
+    const int ocol = h * kHeadDim + 2 * lane;
+    if constexpr (OUT_KIND == DUO_ACT_BF16) {
+      reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(out) + orow * D + ocol)[0] =
+          pack_bf16x2(o0, o1);
+    } else if constexpr (OUT_KIND == DUO_ACT_SPLIT) {
+      uint32_t hi, lo;
+      pack_split2(o0, o1, hi, lo);
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + orow * (2 * D) + ocol;
+      reinterpret_cast<uint32_t*>(o)[0] = hi;
+      reinterpret_cast<uint32_t*>(o + D)[0] = lo;
+    } else {
+      reinterpret_cast<float2*>(reinterpret_cast<float*>(out) + orow * D + ocol)[0] =
+          make_float2(o0, o1);
+    }
+    __syncwarp();
+  }
+}
+
+template <typename Tin, int OUT_KIND, int KPL>
+int launch_fma(const void* qkv, void* out, int64_t groups, int S, int H, float scale,
+               cudaStream_t st) {
+  const size_t per_warp = static_cast<size_t>(fma_smem_words_per_warp<Tin>(S, KPL)) * 4;
+  int warps = 4;
+  while (warps > 1 && per_warp * warps > 100 * 1024) warps >>= 1;
+  const size_t smem = per_warp * warps;
+  if (smem > 220 * 1024) {
+    set_error("duo_group_attention: S=%d needs %zu B of shared memory", S, smem);
+    return DUO_ERR_INVALID;
+  }
+  auto kfn = group_attention_fma_kernel<Tin, OUT_KIND, KPL>;
+  DUO_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(smem)));
+  const int64_t problems = groups * H;
+  const int64_t grid = (problems + warps - 1) / warps;
+  if (grid >= (int64_t(1) << 31)) {
+    set_error("duo_group_attention: too many groups");
+    return DUO_ERR_INVALID;
+  }
+  kfn<<<static_cast<unsigned>(grid), warps * 32, smem, st>>>(reinterpret_cast<const Tin*>(qkv), out,
+                                                            problems, S, H, scale);
+  DUO_LAUNCH_CHECK("group_attention_fma_kernel");
+  return DUO_OK;
+}
+
+template <typename Tin, int OUT_KIND>
+int dispatch_fma_kpl(const void* qkv, void* out, int64_t groups, int S, int H, float scale,
+                     cudaStream_t st) {
+  const int kpl = (S + 31) / 32;
+  switch (kpl) {
+    case 1: return launch_fma<Tin, OUT_KIND, 1>(qkv, out, groups, S, H, scale, st);
+    case 2: return launch_fma<Tin, OUT_KIND, 2>(qkv, out, groups, S, H, scale, st);
+    case 3: return launch_fma<Tin, OUT_KIND, 3>(qkv, out, groups, S, H, scale, st);
+    case 4: return launch_fma<Tin, OUT_KIND, 4>(qkv, out, groups, S, H, scale, st);
+    case 5: return launch_fma<Tin, OUT_KIND, 5>(qkv, out, groups, S, H, scale, st);
+    default: set_error("duo_group_attention: S=%d > 160 unsupported", S); return DUO_ERR_INVALID;
+  }
+}
+
+// =============================== algo 2: mma.sync ==========================================
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1,
+                                            uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1,
+                                                  uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0,
+                                               uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, "
+      "{%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+// Byte offset of 16-byte chunk `c` (0..7) of row `r` in a [rows][128 B] XOR-swizzled tile.
+__device__ __forceinline__ uint32_t swz(int r, int c) {
+  return static_cast<uint32_t>(r * 128 + ((c ^ (r & 7)) << 4));
+}
+
+constexpr int kMmaWarps = 2;
+
+template <int S_PAD>
+__global__ void __launch_bounds__(kMmaWarps * 32)
+group_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
+                           int S, int H, float scale_log2e) {
+  constexpr int MT = S_PAD / 16;  // query m-tiles (also 16-key steps)
+  constexpr int NT = S_PAD / 8;   // 8-key n-tiles
+  __shared__ __align__(128) uint8_t smem[3 * S_PAD * 128];
+  const uint32_t sQ = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+  const uint32_t sK = sQ + S_PAD * 128;
+  const uint32_t sV = sK + S_PAD * 128;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int64_t prob = blockIdx.x;
+  const int64_t g = prob / H;
+  const int h = static_cast<int>(prob - g * H);
+  const int D = H * kHeadDim;
+  const int64_t ld = 3 * static_cast<int64_t>(D);
+  const __nv_bfloat16* base = qkv + (g * S) * ld + h * kHeadDim;
+
+  // ---- stage Q, K, V (S rows x 128 B each) with cp.async; zero the padding rows ----
+  for (int idx = tid; idx < 3 * S_PAD * 8; idx += kMmaWarps * 32) {
+    const int which = idx / (S_PAD * 8);
+    const int rem = idx - which * (S_PAD * 8);
+    const int r = rem >> 3;
+    const int c = rem & 7;
+    const uint32_t dst = sQ + which * (S_PAD * 128) + swz(r, c);
+    if (r < S) {
+      cp_async_16(dst, base + r * ld + which * D + c * 8);
+    } else {
+      asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0u) : "memory");
+    }
+  }
+  cp_async_wait_all();
+  __syncthreads();
+
+  const int gq = lane >> 2;  // fragment row group
+  const int tq = lane & 3;   // fragment column pair
+
+  for (int mt = warp; mt < MT; mt += kMmaWarps) {
+    const int m0 = mt * 16;
+    if (m0 >= S) break;
+    // ---- Q fragments (A operand), 4 k-steps of 16 ----
+    uint32_t qa[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const int r = m0 + (lane & 7) + ((lane >> 3) & 1) * 8;
+      const int c = 2 * ks + (lane >> 4);
+      ldmatrix_x4(sQ + swz(r, c), qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3]);
+    }
+    // ---- scores = Q K^T ----
+    float sc[NT][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+#pragma unroll
+    for (int np = 0; np < MT; ++np) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t b0, b1, b2, b3;
+        const int r = np * 16 + (lane & 7) + ((lane >> 4) & 1) * 8;
+        const int c = 2 * ks + ((lane >> 3) & 1);
+        ldmatrix_x4(sK + swz(r, c), b0, b1, b2, b3);
+        mma_bf16_16816(sc[2 * np], qa[ks], b0, b1);
+        mma_bf16_16816(sc[2 * np + 1], qa[ks], b2, b3);
+      }
+    }
+    // ---- softmax over keys (rows gq and gq+8 of this m-tile) ----
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const int col = nt * 8 + 2 * tq;
+      if (col >= S) sc[nt][0] = sc[nt][2] = -INFINITY;
+      if (col + 1 >= S) sc[nt][1] = sc[nt][3] = -INFINITY;
+      mx0 = fmaxf(mx0, fmaxf(sc[nt][0], sc[nt][1]));
+      mx1 = fmaxf(mx1, fmaxf(sc[nt][2], sc[nt][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float off0 = mx0 * scale_log2e, off1 = mx1 * scale_log2e;
+    float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      sc[nt][0] = exp2f(fmaf(sc[nt][0], scale_log2e, -off0));
+      sc[nt][1] = exp2f(fmaf(sc[nt][1], scale_log2e, -off0));
+      sc[nt][2] = exp2f(fmaf(sc[nt][2], scale_log2e, -off1));
+      sc[nt][3] = exp2f(fmaf(sc[nt][3], scale_log2e, -off1));
+      sum0 += sc[nt][0] + sc[nt][1];
+      sum1 += sc[nt][2] + sc[nt][3];
+    }
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+
+    // ---- O = P V ----
+    float o[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < MT; ++kk) {
+      uint32_t pa[4];
+      pa[0] = pack_bf16x2(sc[2 * kk][0], sc[2 * kk][1]);
+      pa[1] = pack_bf16x2(sc[2 * kk][2], sc[2 * kk][3]);
+      pa[2] = pack_bf16x2(sc[2 * kk + 1][0], sc[2 * kk + 1][1]);
+      pa[3] = pack_bf16x2(sc[2 * kk + 1][2], sc[2 * kk + 1][3]);
+#pragma unroll
+      for (int dp = 0; dp < 4; ++dp) {
+        uint32_t b0, b1, b2, b3;
+        const int r = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int c = 2 * dp + (lane >> 4);
+        ldmatrix_x4_trans(sV + swz(r, c), b0, b1, b2, b3);
+        mma_bf16_16816(o[2 * dp], pa, b0, b1);
+        mma_bf16_16816(o[2 * dp + 1], pa, b2, b3);
+      }
+    }
+    // ---- normalise and store (heads merged: column h*64 + d) ----
+    const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+    const int r0 = m0 + gq, r1 = m0 + gq + 8;
+    __nv_bfloat16* obase = out + (g * S) * D + h * kHeadDim + 2 * tq;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      if (r0 < S)
+        *reinterpret_cast<uint32_t*>(obase + static_cast<int64_t>(r0) * D + nt * 8) =
+            pack_bf16x2(o[nt][0] * inv0, o[nt][1] * inv0);
+      if (r1 < S)
+        *reinterpret_cast<uint32_t*>(obase + static_cast<int64_t>(r1) * D + nt * 8) =
+            pack_bf16x2(o[nt][2] * inv1, o[nt][3] * inv1);
+    }
+  }
+}
+
+template <int S_PAD>
+int launch_mma(const void* qkv, void* out, int64_t groups, int S, int H, float scale,
+               cudaStream_t st) {
+  const int64_t problems = groups * H;
+  if (problems >= (int64_t(1) << 31)) {
+    set_error("duo_group_attention: too many groups");
+    return DUO_ERR_INVALID;
+  }
+  group_attention_mma_kernel<S_PAD><<<static_cast<unsigned>(problems), kMmaWarps * 32, 0, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), S, H,
+      scale * 1.4426950408889634f);
+  DUO_LAUNCH_CHECK("group_attention_mma_kernel");
+  return DUO_OK;
+}
+
+}  // namespace
+}  // namespace duo
+
+extern "C" int duo_group_attention(const void* qkv, int32_t in_kind, void* out, int32_t out_kind,
+                                   int64_t num_groups, int32_t S, int32_t num_heads, float scale,
+                                   int32_t algo, duo_stream_t stream) {
+  using namespace duo;
+  DUO_CHECK_ARG(qkv && out, "duo_group_attention: NULL pointer");
+  DUO_CHECK_ARG(num_groups > 0 && S > 0 && num_heads > 0, "duo_group_attention: empty problem");
+  DUO_CHECK_ARG(in_kind == DUO_ACT_BF16 || in_kind == DUO_ACT_F32,
+                "duo_group_attention: in_kind=%d", in_kind);
+  DUO_CHECK_ARG(out_kind == DUO_ACT_BF16 || out_kind == DUO_ACT_SPLIT || out_kind == DUO_ACT_F32,
+                "duo_group_attention: out_kind=%d", out_kind);
+  DUO_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                "duo_group_attention: pointers must be 16-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool mma_ok = in_kind == DUO_ACT_BF16 && out_kind == DUO_ACT_BF16 && S > 16 && S <= 96;
+  if (algo == 0) algo = mma_ok ? 2 : 1;
+  if (algo == 2) {
+    DUO_CHECK_ARG(mma_ok, "duo_group_attention: algo 2 needs bf16 in/out and 16 < S <= 96 (S=%d)", S);
+    if (S <= 32) return launch_mma<32>(qkv, out, num_groups, S, num_heads, scale, st);
+    if (S <= 48) return launch_mma<48>(qkv, out, num_groups, S, num_heads, scale, st);
+    if (S <= 64) return launch_mma<64>(qkv, out, num_groups, S, num_heads, scale, st);
+    if (S <= 80) return launch_mma<80>(qkv, out, num_groups, S, num_heads, scale, st);
+    return launch_mma<96>(qkv, out, num_groups, S, num_heads, scale, st);
+  }
+  DUO_CHECK_ARG(algo == 1, "duo_group_attention: algo=%d", algo);
+  if (in_kind == DUO_ACT_BF16) {
+    switch (out_kind) {
+      case DUO_ACT_BF16:
+        return dispatch_fma_kpl<__nv_bfloat16, DUO_ACT_BF16>(qkv, out, num_groups, S, num_heads, scale, st);
+      case DUO_ACT_SPLIT:
+        return dispatch_fma_kpl<__nv_bfloat16, DUO_ACT_SPLIT>(qkv, out, num_groups, S, num_heads, scale, st);
+      default:
+        return dispatch_fma_kpl<__nv_bfloat16, DUO_ACT_F32>(qkv, out, num_groups, S, num_heads, scale, st);
+    }
+  }
+  switch (out_kind) {
+    case DUO_ACT_BF16:
+      return dispatch_fma_kpl<float, DUO_ACT_BF16>(qkv, out, num_groups, S, num_heads, scale, st);
+    case DUO_ACT_SPLIT:
+      return dispatch_fma_kpl<float, DUO_ACT_SPLIT>(qkv, out, num_groups, S, num_heads, scale, st);
+    default:
+      return dispatch_fma_kpl<float, DUO_ACT_F32>(qkv, out, num_groups, S, num_heads, scale, st);
+  }
+}

@@ -1,0 +1,114 @@
+// Fused LayerNorm (fp32 statistics, two-pass in registers), fp32 residual stream in,
+// bf16 (or split hi|lo bf16) GEMM operand out.  HBM-bound: one warp per row, float4 loads,
+// the row never leaves registers.  Replaces nn.LayerNorm(eps=1e-6) of
+// scale_attention.py:65,78,91-92 / multiscale_attn.py:282-285.
+#include "common.cuh"
+
+namespace duo {
+namespace {
+
+constexpr int kWarpsPerCta = 8;
+
+__device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+
+// NV = dim / 128 float4 vectors per lane.
+template <int NV, int OUT_KIND>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, void* __restrict__ out, int64_t rows, float eps) {
+  constexpr int D = NV * 128;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * kWarpsPerCta + (threadIdx.x >> 5);
+  if (row >= rows) return;
+
+  const float4* xr = reinterpret_cast<const float4*>(x + row * D);
+  float4 v[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = ld_stream_f4(xr + lane + 32 * i);
+
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const float mean = warp_sum(s) * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c4 = lane + 32 * i;  // float4 index inside the row
+    const float4 g = __ldg(g4 + c4);
+    const float4 b = __ldg(b4 + c4);
+    const float y0 = (v[i].x - mean) * rstd * g.x + b.x;
+    const float y1 = (v[i].y - mean) * rstd * g.y + b.y;
+    const float y2 = (v[i].z - mean) * rstd * g.z + b.z;
+    const float y3 = (v[i].w - mean) * rstd * g.w + b.w;
+    if constexpr (OUT_KIND == DUO_ACT_BF16) {
+      uint2 w;
+      w.x = pack_bf16x2(y0, y1);
+      w.y = pack_bf16x2(y2, y3);
+      reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + row * D)[c4] = w;
+    } else {
+      uint2 h, l;
+      pack_split2(y0, y1, h.x, l.x);
+      pack_split2(y2, y3, h.y, l.y);
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + row * (2 * D);
+      reinterpret_cast<uint2*>(o)[c4] = h;
+      reinterpret_cast<uint2*>(o + D)[c4] = l;
+    }
+  }
+}
+
+template <int NV>
+int launch_ln(const float* x, const float* g, const float* b, void* out, int out_kind,
+              int64_t rows, float eps, cudaStream_t st) {
+  const int64_t grid = (rows + kWarpsPerCta - 1) / kWarpsPerCta;
+  if (out_kind == DUO_ACT_BF16)
+    layernorm_kernel<NV, DUO_ACT_BF16><<<static_cast<unsigned>(grid), kWarpsPerCta * 32, 0, st>>>(
+        x, g, b, out, rows, eps);
+  else
+    layernorm_kernel<NV, DUO_ACT_SPLIT><<<static_cast<unsigned>(grid), kWarpsPerCta * 32, 0, st>>>(
+        x, g, b, out, rows, eps);
+  DUO_LAUNCH_CHECK("layernorm_kernel");
+  return DUO_OK;
+}
+
+}  // namespace
+}  // namespace duo
+
+extern "C" int duo_layernorm(const float* x, const float* gamma, const float* beta, void* out,
+                             int32_t out_kind, int64_t rows, int32_t dim, float eps,
+                             duo_stream_t stream) {
+  using namespace duo;
+  DUO_CHECK_ARG(x && gamma && beta && out, "duo_layernorm: NULL pointer");
+  DUO_CHECK_ARG(rows > 0, "duo_layernorm: rows=%lld", (long long)rows);
+  DUO_CHECK_ARG(dim % 128 == 0 && dim >= 128 && dim <= 1024,
+                "duo_layernorm: dim=%d must be a multiple of 128 in [128,1024]", dim);
+  DUO_CHECK_ARG(out_kind == DUO_ACT_BF16 || out_kind == DUO_ACT_SPLIT,
+                "duo_layernorm: out_kind=%d", out_kind);
+  DUO_CHECK_ARG((rows + kWarpsPerCta - 1) / kWarpsPerCta < (int64_t(1) << 31),
+                "duo_layernorm: too many rows");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (dim / 128) {
+    case 1: return launch_ln<1>(x, gamma, beta, out, out_kind, rows, eps, st);
+    case 2: return launch_ln<2>(x, gamma, beta, out, out_kind, rows, eps, st);
+    case 3: return launch_ln<3>(x, gamma, beta, out, out_kind, rows, eps, st);
+    case 4: return launch_ln<4>(x, gamma, beta, out, out_kind, rows, eps, st);
+    case 5: return launch_ln<5>(x, gamma, beta, out, out_kind, rows, eps, st);
+    case 6: return launch_ln<6>(x, gamma, beta, out, out_kind, rows, eps, st);
+    case 7: return launch_ln<7>(x, gamma, beta, out, out_kind, rows, eps, st);
+    default: return launch_ln<8>(x, gamma, beta, out, out_kind, rows, eps, st);
+  }
+}

@@ -1,0 +1,195 @@
+"""Thin torch-tensor front-ends of the C ABI (one function per entry point).
+
+PyTorch is used for device memory and streams only; every function enqueues hand-written
+sm_100a kernels on ``torch.cuda.current_stream()``.  No CPU / eager fallback exists: a
+non-CUDA tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import (  # noqa: F401  (re-exported)
+    ACT_BF16,
+    ACT_F32,
+    ACT_SPLIT,
+    EPI_BF16,
+    EPI_F32,
+    EPI_GELU_BF16,
+    EPI_GELU_SPLIT_BF16,
+    EPI_RESIDUAL_F32,
+    EPI_SCATTER_F32,
+    EPI_SPLIT_BF16,
+)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("duoformer_tcga_b200 ops need CUDA tensors (no CPU fallback)")
+    return t.data_ptr()
+
+
+def _act_kind(t: torch.Tensor, cols: int) -> int:
+    if t.dtype == torch.float32:
+        return ACT_F32
+    if t.dtype != torch.bfloat16:
+        raise RuntimeError(f"unsupported activation dtype {t.dtype}")
+    return ACT_SPLIT if t.shape[-1] == 2 * cols else ACT_BF16
+
+
+def gemm(
+    A: torch.Tensor,
+    W: torch.Tensor,
+    bias: Optional[torch.Tensor],
+    out: torch.Tensor,
+    epilogue: int,
+    *,
+    split3: bool = False,
+    gamma: Optional[torch.Tensor] = None,
+    row_map: Optional[torch.Tensor] = None,
+    rows_per_group: int = 0,
+    dest_rows_per_group: int = 0,
+    pos: Optional[torch.Tensor] = None,
+    pos_period: int = 0,
+) -> torch.Tensor:
+    """out = epilogue(A @ W.T + bias).  A [M,K] / W [N,K] bf16 (or [.,2K] split when split3)."""
+    assert A.dim() == 2 and W.dim() == 2 and A.dtype == torch.bfloat16 and W.dtype == torch.bfloat16
+    assert A.stride(1) == 1 and W.stride(1) == 1 and out.stride(-1) == 1
+    M = A.shape[0]
+    N = W.shape[0]
+    K = W.shape[1] // 2 if split3 else W.shape[1]
+    assert A.shape[1] == W.shape[1], (A.shape, W.shape)
+    a = _lib.GemmArgs()
+    a.A, a.W, a.bias, a.out = _ptr(A), _ptr(W), _ptr(bias), _ptr(out)
+    a.gamma, a.row_map, a.pos = _ptr(gamma), _ptr(row_map), _ptr(pos)
+    a.M, a.N, a.K = M, N, K
+    a.lda, a.ldw = A.stride(0), W.stride(0)
+    a.ldo = out.stride(-2) if out.dim() >= 2 else out.shape[-1]
+    a.split3 = 1 if split3 else 0
+    a.epilogue = epilogue
+    a.rows_per_group, a.dest_rows_per_group, a.pos_period = rows_per_group, dest_rows_per_group, pos_period
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == N
+    if row_map is not None:
+        assert row_map.dtype == torch.int32
+    _lib.check(_lib.load().duo_gemm(ctypes.byref(a), _stream()), "duo_gemm")
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out: torch.Tensor, eps: float) -> torch.Tensor:
+    """out (bf16 [rows,D] or split bf16 [rows,2D]) = LayerNorm(x fp32 [rows,D])."""
+    D = x.shape[-1]
+    assert x.dtype == torch.float32 and x.is_contiguous() and out.is_contiguous()
+    rows = x.numel() // D
+    kind = _act_kind(out, D)
+    assert kind in (ACT_BF16, ACT_SPLIT)
+    _lib.check(
+        _lib.load().duo_layernorm(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(out), kind, rows, D, float(eps), _stream()),
+        "duo_layernorm",
+    )
+    return out
+
+
+def group_attention(
+    qkv: torch.Tensor, out: torch.Tensor, S: int, num_heads: int, scale: float, algo: int = 0
+) -> torch.Tensor:
+    """softmax(q k^T * scale) v per (group of S rows, head); qkv [rows, 3*D], out [rows, D | 2D]."""
+    assert qkv.is_contiguous() and out.is_contiguous()
+    D = qkv.shape[-1] // 3
+    rows = qkv.numel() // (3 * D)
+    assert rows % S == 0 and D == 64 * num_heads
+    in_kind = ACT_F32 if qkv.dtype == torch.float32 else ACT_BF16
+    out_kind = _act_kind(out, D)
+    _lib.check(
+        _lib.load().duo_group_attention(
+            _ptr(qkv), in_kind, _ptr(out), out_kind, rows // S, S, num_heads, float(scale), algo, _stream()
+        ),
+        "duo_group_attention",
+    )
+    return out
+
+
+def fill_scale_token(X: torch.Tensor, tok: torch.Tensor, pos0: torch.Tensor) -> torch.Tensor:
+    """X[b,p,0,:] = tok[b,p,:] + pos0.  X fp32 [B,P,S,D]; tok [D] (broadcast) or [B,P,D]."""
+    B, P, S, D = X.shape
+    assert X.dtype == torch.float32 and X.is_contiguous() and tok.dtype == torch.float32
+    if tok.numel() == D:
+        sb, sp = 0, 0
+    else:
+        assert tok.shape == (B, P, D) and tok.stride(2) == 1
+        sb, sp = tok.stride(0), tok.stride(1)
+    _lib.check(
+        _lib.load().duo_fill_scale_token(_ptr(X), _ptr(tok), sb, sp, _ptr(pos0), B, P, S, D, _stream()),
+        "duo_fill_scale_token",
+    )
+    return X
+
+
+def assemble_patch_tokens(X: torch.Tensor, cls: torch.Tensor, pos: torch.Tensor, Z: torch.Tensor) -> torch.Tensor:
+    """Z[b,0]=cls+pos[0]; Z[b,1+p]=X[b,p,0]+pos[1+p].  Z bf16 [B,P+1,D] or split [B,P+1,2D]."""
+    B, P, S, D = X.shape
+    assert X.is_contiguous() and Z.is_contiguous() and pos.is_contiguous()
+    kind = _act_kind(Z, D)
+    _lib.check(
+        _lib.load().duo_assemble_patch_tokens(_ptr(X), _ptr(cls), _ptr(pos), _ptr(Z), kind, B, P, S, D, _stream()),
+        "duo_assemble_patch_tokens",
+    )
+    return Z
+
+
+def head(
+    inp: torch.Tensor,
+    row_stride: int,
+    W: torch.Tensor,
+    bias: Optional[torch.Tensor],
+    logits: torch.Tensor,
+    ln_gamma: Optional[torch.Tensor] = None,
+    ln_beta: Optional[torch.Tensor] = None,
+    eps: float = 1e-6,
+) -> torch.Tensor:
+    B, ncls = logits.shape
+    D = W.shape[1]
+    assert inp.dtype == torch.float32 and W.dtype == torch.float32 and W.is_contiguous()
+    _lib.check(
+        _lib.load().duo_head(
+            _ptr(inp), row_stride, _ptr(ln_gamma), _ptr(ln_beta), float(eps), _ptr(W), _ptr(bias), _ptr(logits),
+            B, D, ncls, _stream(),
+        ),
+        "duo_head",
+    )
+    return logits
+
+
+def convert(inp: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """fp32 [rows, cols] -> bf16 [rows, cols] or split bf16 [rows, 2*cols]."""
+    assert inp.dtype == torch.float32 and inp.dim() == 2 and inp.stride(1) == 1 and out.is_contiguous()
+    rows, cols = inp.shape
+    kind = _act_kind(out, cols)
+    _lib.check(
+        _lib.load().duo_convert(_ptr(inp), inp.stride(0), _ptr(out), kind, rows, cols, _stream()), "duo_convert"
+    )
+    return out
+
+
+def launch_count() -> int:
+    return int(_lib.load().duo_launch_count())
+
+
+def launch_count_reset() -> None:
+    _lib.load().duo_launch_count_reset()
+
+
+def split_weight(w: torch.Tensor) -> torch.Tensor:
+    """fp32 [N,K] -> split bf16 [N,2K] (hi | lo).  Host-side weight packing helper (any device)."""
+    hi = w.to(torch.bfloat16)
+    lo = (w - hi.to(torch.float32)).to(torch.bfloat16)
+    return torch.cat([hi, lo], dim=1).contiguous()

@@ -1,0 +1,156 @@
+/*
+ * duoformer_sm100.h — C ABI of libduoformer_sm100.so
+ *
+ * B200 (sm_100a) kernels for the DuoFormer multi-scale transformer forward path.
+ * The reference (AliSerwat/duoformer_TCGA) is pure PyTorch and has no FFI of its own; the
+ * boundary it exposes is the Python module API of models/model.py and
+ * models/model_wo_extra_params.py.  This C ABI sits directly beneath that API: every entry
+ * point below replaces one group of ATen calls of the reference forward, cited per function
+ * as <reference file>:<lines>.  The Python classes in duoformer_tcga_b200/ keep the
+ * reference's constructor signatures / state_dict schema and call these functions through
+ * ctypes (see INTEGRATION.md for the binding).
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers owned by the caller (PyTorch caching allocator).  The
+ *     library never allocates, frees or retains device memory.
+ *   - Every call only ENQUEUES work on `stream` (a cudaStream_t); no host synchronisation, so
+ *     calls are CUDA-graph capturable.
+ *   - Return value: 0 = ok, negative = error (DUO_ERR_*); duo_last_error() returns a
+ *     thread-local message.  No C++ exception crosses the ABI.
+ *   - "bf16" = __nv_bfloat16 storage.  "split bf16" = a [rows, 2*cols] bf16 matrix holding
+ *     hi = bf16(x) in columns [0, cols) and lo = bf16(x - hi) in [cols, 2*cols): the operand
+ *     format of the 3-pass (hi*hi + hi*lo + lo*hi) tensor-core GEMM used for the fp32-accuracy
+ *     mode (north-star tolerance 1e-3).
+ *   - There is NO CPU fallback.
+ */
+#ifndef DUOFORMER_SM100_H_
+#define DUOFORMER_SM100_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* duo_stream_t; /* cudaStream_t */
+
+enum {
+  DUO_OK = 0,
+  DUO_ERR_INVALID = -1,     /* bad argument / unsupported shape */
+  DUO_ERR_CUDA = -2,        /* CUDA runtime / driver error (message has the code) */
+  DUO_ERR_UNSUPPORTED = -3  /* device is not sm_100 */
+};
+
+/* GEMM epilogues (duo_gemm_args.epilogue) */
+enum {
+  DUO_EPI_BF16 = 0,            /* out bf16 [M,N]      = acc + bias                         */
+  DUO_EPI_GELU_BF16 = 1,       /* out bf16 [M,N]      = gelu_erf(acc + bias)               */
+  DUO_EPI_RESIDUAL_F32 = 2,    /* out f32  [M,N]     += gamma[n] * (acc + bias)  (in place) */
+  DUO_EPI_SCATTER_F32 = 3,     /* out f32  [*,N]: row r -> dest(r); = acc + bias + pos     */
+  DUO_EPI_F32 = 4,             /* out f32  [M,N]      = acc + bias                         */
+  DUO_EPI_SPLIT_BF16 = 5,      /* out split bf16 [M,2N] of (acc + bias)                    */
+  DUO_EPI_GELU_SPLIT_BF16 = 6  /* out split bf16 [M,2N] of gelu_erf(acc + bias)            */
+};
+
+/* Element kinds of activation tensors */
+enum {
+  DUO_ACT_BF16 = 0,  /* bf16 [rows, cols]        */
+  DUO_ACT_SPLIT = 1, /* split bf16 [rows, 2*cols] */
+  DUO_ACT_F32 = 2    /* float [rows, cols]       */
+};
+
+const char* duo_last_error(void);
+int duo_abi_version(void);
+/* Number of kernels launched by this library in the calling thread since the last reset
+ * (bench.py's "gpu_launches"). */
+int64_t duo_launch_count(void);
+void duo_launch_count_reset(void);
+
+/*
+ * Dense contraction  C[M,N] = A[M,K] * W[N,K]^T  (+ epilogue), bf16 operands, fp32 accumulate
+ * in TMEM, TMA-fed tcgen05.mma.  Replaces every nn.Linear / 1x1 Conv2d on the path:
+ *   qkv / proj            scale_attention.py:31,42 ; multiscale_attn.py:144-146,151,164
+ *   fc1 / GELU / fc2      timm Mlp, instantiated scale_attention.py:79-84
+ *   1x1 conv projection   projection_head.py:134-149 (+ gather/cat/permute
+ *                         model_wo_extra_params.py:252-299 via DUO_EPI_SCATTER_F32)
+ *   residual / LayerScale scale_attention.py:91-92 ; multiscale_attn.py:282-285
+ * Requirements: N % 128 == 0, K % 64 == 0, A/W 16-byte aligned, lda/ldw multiples of 8.
+ * split3 != 0: A is split bf16 [M,2K], W is split bf16 [N,2K]; computes Ah*Wh + Ah*Wl + Al*Wh.
+ */
+typedef struct duo_gemm_args {
+  const void* A;       /* bf16 [M, K] (or [M, 2K] when split3) row-major, leading dim lda */
+  const void* W;       /* bf16 [N, K] (or [N, 2K] when split3) row-major, leading dim ldw */
+  const float* bias;   /* [N] or NULL */
+  void* out;           /* see epilogue; leading dim ldo (elements of the out type)        */
+  const float* gamma;  /* RESIDUAL: LayerScale [N] or NULL (== 1)                          */
+  const int32_t* row_map; /* SCATTER: [rows_per_group] dest row inside the group           */
+  const float* pos;    /* SCATTER: [pos_period, N] added by (dest_row % pos_period) or NULL */
+  int64_t M;
+  int64_t lda, ldw, ldo;
+  int32_t N, K;
+  int32_t split3;
+  int32_t epilogue;
+  int32_t rows_per_group;      /* SCATTER: source rows per image (h*w of the stage)        */
+  int32_t dest_rows_per_group; /* SCATTER: token rows per image (P*S)                      */
+  int32_t pos_period;          /* SCATTER: S                                               */
+  int32_t reserved;
+} duo_gemm_args;
+int duo_gemm(const duo_gemm_args* args, duo_stream_t stream);
+
+/*
+ * LayerNorm over the last dim (fp32 statistics, two-pass), fp32 in -> bf16 / split bf16 out.
+ * Replaces nn.LayerNorm(eps=1e-6): scale_attention.py:65,78,91-92; multiscale_attn.py:282-285.
+ * dim % 128 == 0, dim <= 1024.
+ */
+int duo_layernorm(const float* x, const float* gamma, const float* beta, void* out,
+                  int32_t out_kind, int64_t rows, int32_t dim, float eps, duo_stream_t stream);
+
+/*
+ * Grouped multi-head attention over S consecutive rows of a fused qkv matrix:
+ *   for every group g (S rows) and head h: out = softmax(q k^T * scale) v, heads merged.
+ * qkv row layout [3][H][64] (which*D + h*64 + d), exactly the reference's
+ * reshape(..., 3, H, dh): scale_attention.py:30-41 (scale attention, group = one patch,
+ * S = 6/22/86), scale_attention.py:195-207 / multiscale_attn.py:205-216 (patch attention,
+ * group = one image, S = P+1).  head_dim must be 64.
+ * in_kind: DUO_ACT_BF16 or DUO_ACT_F32; out_kind: DUO_ACT_BF16 / DUO_ACT_SPLIT / DUO_ACT_F32.
+ * algo: 0 = auto, 1 = warp-per-(group,head) register/shuffle FMA kernel (any S <= 160),
+ *       2 = warp-level tensor-core (mma.sync) kernel (bf16 in, bf16 out, 16 < S <= 96).
+ */
+int duo_group_attention(const void* qkv, int32_t in_kind, void* out, int32_t out_kind,
+                        int64_t num_groups, int32_t S, int32_t num_heads, float scale,
+                        int32_t algo, duo_stream_t stream);
+
+/*
+ * Scale token row (s = 0) of the token tensor:  X[b,p,0,:] = tok[b,p,:] + pos0[:]
+ * (tok strides in elements; 0,0 broadcasts the learned channel_token).
+ * model_wo_extra_params.py:296-299 + scale_attention.py:331 ; model.py:322.
+ */
+int duo_fill_scale_token(float* X, const float* tok, int64_t tok_stride_b, int64_t tok_stride_p,
+                         const float* pos0, int32_t B, int32_t P, int32_t S, int32_t D,
+                         duo_stream_t stream);
+
+/*
+ * Patch-stage input:  Z[b,0,:] = cls + pos[0];  Z[b,1+p,:] = X[b,p,0,:] + pos[1+p]
+ * scale_attention.py:183-193 ; multiscale_attn.py:190-203.  out_kind BF16 or SPLIT.
+ */
+int duo_assemble_patch_tokens(const float* X, const float* cls, const float* pos, void* Z,
+                              int32_t out_kind, int32_t B, int32_t P, int32_t S, int32_t D,
+                              duo_stream_t stream);
+
+/*
+ * Classification head on one row per image: logits[b,:] = W * f(z_b) + bias, where
+ * z_b = in[b*row_stride : +D] and f = LayerNorm(ln_gamma, ln_beta, eps) if ln_gamma != NULL.
+ * scale_attention.py:341-344 (no norm) ; multi_vision_transformer.py:161-171 (norm, head).
+ */
+int duo_head(const float* in, int64_t row_stride, const float* ln_gamma, const float* ln_beta,
+             float eps, const float* W, const float* bias, float* logits, int32_t B, int32_t D,
+             int32_t num_classes, duo_stream_t stream);
+
+/* fp32 [rows, cols] (leading dim ld) -> bf16 / split bf16 (contiguous). */
+int duo_convert(const float* in, int64_t ld, void* out, int32_t out_kind, int64_t rows,
+                int32_t cols, duo_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DUOFORMER_SM100_H_ */

@@ -1,0 +1,192 @@
+"""Kernel-level parity (-m gpu): every C-ABI entry point against a plain PyTorch fp32 restatement
+of the same op on seeded inputs.  Tolerances: bf16 operands -> error of the fp32 result after
+rounding the INPUTS to bf16 is compared tightly (1e-2 rel of max for bf16 outputs, 2e-3 for fp32
+outputs); split3 (fp32-accuracy) GEMM: 2e-5."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from duoformer_tcga_b200 import ops  # noqa: E402
+
+
+def relerr(a, b):
+    return ((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-30)).item()
+
+
+def _gen(shape, seed, scale=1.0, device="cuda"):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(device)
+
+
+@pytest.mark.parametrize(
+    "M,N,K",
+    [(128, 256, 64), (128, 128, 64), (256, 768, 768), (294 * 2, 2304, 768), (1000, 768, 3072), (128 * 300, 768, 256), (98, 768, 2048)],
+)
+def test_gemm_bf16_epilogues(M, N, K):
+    A = _gen((M, K), 1).to(torch.bfloat16)
+    W = _gen((N, K), 2, 0.05).to(torch.bfloat16)
+    bias = _gen((N,), 3)
+    ref = A.float() @ W.float().t() + bias
+    out = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    ops.gemm(A, W, bias, out, ops.EPI_BF16)
+    assert relerr(out, ref) < 1e-2
+    out32 = torch.empty(M, N, dtype=torch.float32, device="cuda")
+    ops.gemm(A, W, bias, out32, ops.EPI_F32)
+    assert relerr(out32, ref) < 1e-4
+    ops.gemm(A, W, None, out32, ops.EPI_F32)
+    assert relerr(out32, ref - bias) < 1e-4
+    outg = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    ops.gemm(A, W, bias, outg, ops.EPI_GELU_BF16)
+    assert relerr(outg, torch.nn.functional.gelu(ref)) < 1e-2
+    # residual with LayerScale
+    X = _gen((M, N), 4, 3.0)
+    gamma = _gen((N,), 5)
+    Xr = X + gamma * ref
+    ops.gemm(A, W, bias, X, ops.EPI_RESIDUAL_F32, gamma=gamma)
+    assert relerr(X, Xr) < 1e-4
+    X2 = _gen((M, N), 6, 3.0)
+    X2r = X2 + ref
+    ops.gemm(A, W, bias, X2, ops.EPI_RESIDUAL_F32)
+    assert relerr(X2, X2r) < 1e-4
+
+
+def test_gemm_split3_fp32_accuracy():
+    M, N, K = 300, 768, 768
+    A = _gen((M, K), 11)
+    W = _gen((N, K), 12, 0.05)
+    bias = _gen((N,), 13)
+    ref = (A.double() @ W.double().t() + bias.double()).float()
+    As = torch.empty(M, 2 * K, dtype=torch.bfloat16, device="cuda")
+    ops.convert(A, As)
+    assert torch.equal(As, ops.split_weight(A))
+    Ws = ops.split_weight(W)
+    out = torch.empty(M, N, dtype=torch.float32, device="cuda")
+    ops.gemm(As, Ws, bias, out, ops.EPI_F32, split3=True)
+    assert relerr(out, ref) < 2e-5
+    outs = torch.empty(M, 2 * N, dtype=torch.bfloat16, device="cuda")
+    ops.gemm(As, Ws, bias, outs, ops.EPI_SPLIT_BF16, split3=True)
+    rec = outs[:, :N].float() + outs[:, N:].float()
+    assert relerr(rec, ref) < 3e-5
+    ops.gemm(As, Ws, bias, outs, ops.EPI_GELU_SPLIT_BF16, split3=True)
+    rec = outs[:, :N].float() + outs[:, N:].float()
+    assert relerr(rec, torch.nn.functional.gelu(ref)) < 3e-5
+
+
+def test_gemm_scatter_tokens():
+    # 2 images, stage with 8 source rows per image scattered into 5*4 token rows per image
+    B, hw, P, S, N, K = 3, 196, 49, 6, 768, 1024
+    A = _gen((B * hw, K), 21).to(torch.bfloat16)
+    W = _gen((N, K), 22, 0.05).to(torch.bfloat16)
+    bias = _gen((N,), 23)
+    pos = _gen((S, N), 24)
+    g = torch.Generator().manual_seed(5)
+    # random injective map of the 196 source rows into the 49*6 token rows, avoiding s == 0
+    cand = torch.tensor([p * S + s for p in range(P) for s in range(1, S)])
+    row_map = cand[torch.randperm(cand.numel(), generator=g)[:hw]].to(torch.int32).cuda()
+    X = torch.zeros(B * P * S, N, device="cuda")
+    ops.gemm(A, W, bias, X, ops.EPI_SCATTER_F32, row_map=row_map, rows_per_group=hw,
+             dest_rows_per_group=P * S, pos=pos, pos_period=S)
+    ref = A.float() @ W.float().t() + bias
+    Xr = torch.zeros_like(X)
+    for b in range(B):
+        dst = b * P * S + row_map.long()
+        Xr[dst] = ref[b * hw:(b + 1) * hw] + pos[(row_map.long() % S)]
+    assert relerr(X, Xr) < 1e-4
+
+
+@pytest.mark.parametrize("rows,D", [(1, 768), (1000, 768), (4214 * 3, 768), (77, 128), (33, 1024)])
+def test_layernorm(rows, D):
+    x = _gen((rows, D), 31, 50.0) + 10.0
+    g = _gen((D,), 32)
+    b = _gen((D,), 33)
+    ref = torch.nn.functional.layer_norm(x, (D,), g, b, 1e-6)
+    out = torch.empty(rows, D, dtype=torch.bfloat16, device="cuda")
+    ops.layernorm(x, g, b, out, 1e-6)
+    assert relerr(out, ref) < 6e-3
+    outs = torch.empty(rows, 2 * D, dtype=torch.bfloat16, device="cuda")
+    ops.layernorm(x, g, b, outs, 1e-6)
+    assert relerr(outs[:, :D].float() + outs[:, D:].float(), ref) < 2e-5
+
+
+def _attn_ref(qkv, S, H, scale):
+    rows, D3 = qkv.shape
+    D = D3 // 3
+    G = rows // S
+    t = qkv.float().reshape(G, S, 3, H, 64).permute(2, 0, 3, 1, 4)
+    q, k, v = t[0], t[1], t[2]
+    a = torch.softmax((q @ k.transpose(-2, -1)) * scale, dim=-1)
+    return (a @ v).transpose(1, 2).reshape(rows, D)
+
+
+@pytest.mark.parametrize("S,G,algo", [(6, 98, 1), (22, 50, 1), (22, 50, 2), (86, 49, 1), (86, 49, 2), (50, 7, 1), (50, 7, 2), (145, 3, 1), (17, 5, 2), (96, 4, 2)])
+def test_group_attention_bf16(S, G, algo):
+    H = 12
+    qkv = _gen((G * S, 3 * H * 64), 41 + S, 2.0).to(torch.bfloat16)
+    ref = _attn_ref(qkv, S, H, 0.125)
+    out = torch.empty(G * S, H * 64, dtype=torch.bfloat16, device="cuda")
+    ops.group_attention(qkv, out, S, H, 0.125, algo=algo)
+    assert relerr(out, ref) < (1.5e-2 if algo == 2 else 8e-3)
+
+
+@pytest.mark.parametrize("S,G", [(6, 98), (86, 10), (50, 4)])
+def test_group_attention_fp32(S, G):
+    H = 12
+    qkv = _gen((G * S, 3 * H * 64), 51 + S, 2.0)
+    ref = _attn_ref(qkv, S, H, 0.0721)
+    out = torch.empty(G * S, H * 64, dtype=torch.float32, device="cuda")
+    ops.group_attention(qkv, out, S, H, 0.0721)
+    assert relerr(out, ref) < 1e-5
+    outs = torch.empty(G * S, 2 * H * 64, dtype=torch.bfloat16, device="cuda")
+    ops.group_attention(qkv, outs, S, H, 0.0721)
+    assert relerr(outs[:, :768].float() + outs[:, 768:].float(), ref) < 2e-5
+
+
+def test_token_helpers_and_head():
+    B, P, S, D, ncls = 3, 49, 6, 768, 10
+    X = _gen((B, P, S, D), 61)
+    X0 = X.clone()
+    tok = _gen((D,), 62)
+    pos_s = _gen((S, D), 63)
+    ops.fill_scale_token(X, tok, pos_s[0].contiguous())
+    ref = X0.clone()
+    ref[:, :, 0, :] = tok + pos_s[0]
+    assert torch.equal(X, ref)
+    tokb = _gen((B, P, D), 64)
+    ops.fill_scale_token(X, tokb, pos_s[0].contiguous())
+    ref[:, :, 0, :] = tokb + pos_s[0]
+    assert torch.equal(X, ref)
+
+    cls = _gen((D,), 65)
+    pos = _gen((P + 1, D), 66)
+    Z = torch.empty(B, P + 1, D, dtype=torch.bfloat16, device="cuda")
+    ops.assemble_patch_tokens(X, cls, pos, Z)
+    Zr = torch.cat([cls.expand(B, 1, D), X[:, :, 0, :]], dim=1) + pos
+    assert torch.equal(Z, Zr.to(torch.bfloat16))
+    Zs = torch.empty(B, P + 1, 2 * D, dtype=torch.bfloat16, device="cuda")
+    ops.assemble_patch_tokens(X, cls, pos, Zs)
+    assert relerr(Zs[..., :D].float() + Zs[..., D:].float(), Zr) < 2e-5
+
+    Wh = _gen((ncls, D), 67, 0.05)
+    bh = _gen((ncls,), 68)
+    Zf = _gen((B, P + 1, D), 69)
+    logits = torch.empty(B, ncls, device="cuda")
+    ops.head(Zf, (P + 1) * D, Wh, bh, logits)
+    assert relerr(logits, Zf[:, 0] @ Wh.t() + bh) < 1e-5
+    g, b = _gen((D,), 70), _gen((D,), 71)
+    ops.head(Zf, (P + 1) * D, Wh, bh, logits, ln_gamma=g, ln_beta=b, eps=1e-6)
+    lr = torch.nn.functional.layer_norm(Zf[:, 0], (D,), g, b, 1e-6) @ Wh.t() + bh
+    assert relerr(logits, lr) < 1e-5
+
+
+def test_invalid_arguments_raise():
+    A = torch.zeros(128, 64, dtype=torch.bfloat16, device="cuda")
+    W = torch.zeros(100, 64, dtype=torch.bfloat16, device="cuda")
+    out = torch.zeros(128, 100, dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(RuntimeError, match="multiple of 128"):
+        ops.gemm(A, W, None, out, ops.EPI_BF16)
+    with pytest.raises(RuntimeError):
+        ops.layernorm(torch.zeros(4, 100, device="cuda"), torch.zeros(100, device="cuda"),
+                      torch.zeros(100, device="cuda"), torch.zeros(4, 100, dtype=torch.bfloat16, device="cuda"), 1e-6)
