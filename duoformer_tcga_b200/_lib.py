@@ -28,6 +28,7 @@ EXPORTED_SYMBOLS = (
     "duo_layernorm",
     "duo_group_attention",
     "duo_fill_scale_token",
+    "duo_add_pos",
     "duo_assemble_patch_tokens",
     "duo_head",
     "duo_convert",
@@ -97,6 +98,8 @@ def load() -> ctypes.CDLL:
     lib.duo_group_attention.argtypes = [c_void_p, c_int32, c_void_p, c_int32, c_int64, c_int32, c_int32, c_float, c_int32, c_void_p]
     lib.duo_fill_scale_token.restype = c_int32
     lib.duo_fill_scale_token.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]
+    lib.duo_add_pos.restype = c_int32
+    lib.duo_add_pos.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p]
     lib.duo_assemble_patch_tokens.restype = c_int32
     lib.duo_assemble_patch_tokens.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]
     lib.duo_head.restype = c_int32

@@ -62,6 +62,22 @@ __global__ void assemble_patch_tokens_kernel(const float* __restrict__ X,
   }
 }
 
+// out[r,:] = in[r,:] + pos[r % S, :]
+__global__ void add_pos_kernel(const float* __restrict__ in, const float* __restrict__ pos,
+                               float* __restrict__ out, int64_t rows, int S, int D) {
+  const int d4 = D >> 2;
+  const int64_t total = rows * d4;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % d4);
+    const int64_t r = i / d4;
+    const int s = static_cast<int>(r % S);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(in + r * D) + c);
+    const float4 q = __ldg(reinterpret_cast<const float4*>(pos + static_cast<int64_t>(s) * D) + c);
+    reinterpret_cast<float4*>(out + r * D)[c] = make_float4(v.x + q.x, v.y + q.y, v.z + q.z, v.w + q.w);
+  }
+}
+
 // One CTA (128 threads) per image: optional LayerNorm of the row, then ncls dot products.
 __global__ void __launch_bounds__(128)
 head_kernel(const float* __restrict__ in, int64_t row_stride, const float* __restrict__ ln_g,
@@ -150,6 +166,18 @@ extern "C" int duo_fill_scale_token(float* X, const float* tok, int64_t tok_stri
   fill_scale_token_kernel<<<elementwise_grid(total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       X, tok, tok_stride_b, tok_stride_p, pos0, B, P, S, D);
   DUO_LAUNCH_CHECK("fill_scale_token_kernel");
+  return DUO_OK;
+}
+
+extern "C" int duo_add_pos(const float* in, const float* pos, float* out, int64_t rows, int32_t S,
+                           int32_t D, duo_stream_t stream) {
+  using namespace duo;
+  DUO_CHECK_ARG(in && pos && out, "duo_add_pos: NULL pointer");
+  DUO_CHECK_ARG(rows > 0 && S > 0 && D > 0 && D % 4 == 0, "duo_add_pos: bad dims");
+  const int64_t total = rows * (D / 4);
+  add_pos_kernel<<<elementwise_grid(total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      in, pos, out, rows, S, D);
+  DUO_LAUNCH_CHECK("add_pos_kernel");
   return DUO_OK;
 }
 

@@ -1,0 +1,178 @@
+"""Host-side executor of the DuoFormer forward path: weight packing and kernel sequencing.
+
+This is orchestration only — every arithmetic step is a kernel of libduoformer_sm100.so
+(see ops.py).  Two precisions:
+
+  "bf16"  (default, the benchmarked path) bf16 GEMM operands, fp32 accumulation / residual
+          stream / LayerNorm statistics / softmax.
+  "fp32"  fp32-accuracy mode (north-star tolerance 1e-3): activations and weights are split into
+          bf16 hi|lo halves and every Linear runs as a 3-pass tensor-core GEMM (hi*hi+hi*lo+lo*hi).
+
+Stage-wise parity tests hook `capture` dicts (name -> tensor clone).
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import ops
+
+PRECISIONS = ("bf16", "fp32")
+
+
+def require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise NotImplementedError(
+            f"{what}: the B200 path has no CPU / eager fallback — move the model and inputs to a CUDA device"
+        )
+
+
+def param_signature(module: nn.Module, precision: str) -> tuple:
+    sig: List = [precision]
+    for p in list(module.parameters()) + list(module.buffers()):
+        sig.append((p.data_ptr(), p._version))
+    return tuple(sig)
+
+
+def pack_linear(weight: torch.Tensor, bias: Optional[torch.Tensor], precision: str) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """[N, K] fp32 master weight -> bf16 (or split hi|lo bf16) K-major TMA operand + fp32 bias."""
+    w = weight.detach().reshape(weight.shape[0], -1).to(torch.float32)
+    wp = ops.split_weight(w) if precision == "fp32" else w.to(torch.bfloat16).contiguous()
+    b = None if bias is None else bias.detach().to(torch.float32).contiguous()
+    return wp, b
+
+
+def _f32(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    return None if t is None else t.detach().to(torch.float32).contiguous()
+
+
+class Workspace:
+    """One reusable byte buffer carved into the per-chunk activation tensors."""
+
+    def __init__(self, device: torch.device):
+        self.device = device
+        self.buf: Optional[torch.Tensor] = None
+
+    def get(self, nbytes: int) -> torch.Tensor:
+        if self.buf is None or self.buf.numel() < nbytes:
+            self.buf = None
+            self.buf = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        return self.buf
+
+    @staticmethod
+    def view(buf: torch.Tensor, offset: int, shape: Tuple[int, ...], dtype: torch.dtype) -> torch.Tensor:
+        n = 1
+        for s in shape:
+            n *= s
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        return buf[offset : offset + nbytes].view(dtype).view(*shape)
+
+
+def _align(n: int, a: int = 1024) -> int:
+    return (n + a - 1) // a * a
+
+
+def scale_stage(
+    X: torch.Tensor,
+    blocks: List[Dict],
+    num_heads: int,
+    scale: float,
+    eps: float,
+    precision: str,
+    ws: Workspace,
+    capture: Optional[Dict[str, torch.Tensor]] = None,
+    attn_algo: int = 0,
+    max_chunk_tokens: int = 1 << 21,
+) -> torch.Tensor:
+    """L x { X += g1*Attn(LN1 X) ; X += g2*MLP(LN2 X) } in place on the fp32 token tensor
+    X [B, P, S, D]  (scale_attention.py:90-93 / multiscale_attn.py:282-285)."""
+    B, P, S, D = X.shape
+    if not blocks:
+        return X
+    fp32 = precision == "fp32"
+    kd = 2 if fp32 else 1
+    hidden = blocks[0]["fc1"][0].shape[0]
+    tokens_per_image = P * S
+    chunk_images = max(1, min(B, max_chunk_tokens // tokens_per_image))
+    if capture is not None:
+        chunk_images = B  # captures want whole-batch tensors after every block
+    Tc = chunk_images * tokens_per_image
+    # workspace: Hn | max(QKV, HID)
+    hn_bytes = _align(Tc * kd * D * 2)
+    qkv_bytes = Tc * 3 * D * (4 if fp32 else 2)
+    hid_bytes = Tc * kd * hidden * 2
+    buf = ws.get(hn_bytes + _align(max(qkv_bytes, hid_bytes)))
+    for b0 in range(0, B, chunk_images):
+        nb = min(chunk_images, B - b0)
+        T = nb * tokens_per_image
+        Xc = X[b0 : b0 + nb].view(T, D)
+        Hn = Workspace.view(buf, 0, (T, kd * D), torch.bfloat16)
+        QKV = Workspace.view(buf, hn_bytes, (T, 3 * D), torch.float32 if fp32 else torch.bfloat16)
+        HID = Workspace.view(buf, hn_bytes, (T, kd * hidden), torch.bfloat16)
+        for i, blk in enumerate(blocks):
+            ops.layernorm(Xc, blk["n1w"], blk["n1b"], Hn, eps)
+            ops.gemm(Hn, blk["qkv"][0], blk["qkv"][1], QKV, ops.EPI_F32 if fp32 else ops.EPI_BF16, split3=fp32)
+            ops.group_attention(QKV, Hn, S, num_heads, scale, algo=attn_algo)  # attention output re-uses Hn
+            ops.gemm(Hn, blk["proj"][0], blk["proj"][1], Xc, ops.EPI_RESIDUAL_F32, gamma=blk["g1"], split3=fp32)
+            ops.layernorm(Xc, blk["n2w"], blk["n2b"], Hn, eps)
+            ops.gemm(Hn, blk["fc1"][0], blk["fc1"][1], HID,
+                     ops.EPI_GELU_SPLIT_BF16 if fp32 else ops.EPI_GELU_BF16, split3=fp32)
+            ops.gemm(HID, blk["fc2"][0], blk["fc2"][1], Xc, ops.EPI_RESIDUAL_F32, gamma=blk["g2"], split3=fp32)
+            if capture is not None:
+                capture[f"scale_block_{i}"] = X.clone()
+    return X
+
+
+def region_attention(
+    Z: torch.Tensor,
+    blk: Dict,
+    N: int,
+    num_heads: int,
+    scale: float,
+    precision: str,
+    out_f32: bool,
+) -> torch.Tensor:
+    """One patch ("region") attention block without residual / norm / MLP:
+    Z <- proj(softmax(q k^T * scale) v)   (scale_attention.py:195-209, multiscale_attn.py:205-219).
+    Z: bf16 [B*N, D] (or split [B*N, 2D]); returns the same kind, or fp32 [B*N, D] if out_f32."""
+    fp32 = precision == "fp32"
+    kd = 2 if fp32 else 1
+    rows = Z.shape[0]
+    D = Z.shape[1] // kd
+    dev = Z.device
+    QKV = torch.empty(rows, 3 * D, dtype=torch.float32 if fp32 else torch.bfloat16, device=dev)
+    ops.gemm(Z, blk["qkv"][0], blk["qkv"][1], QKV, ops.EPI_F32 if fp32 else ops.EPI_BF16, split3=fp32)
+    AO = torch.empty(rows, kd * D, dtype=torch.bfloat16, device=dev)
+    ops.group_attention(QKV, AO, N, num_heads, scale)
+    if out_f32:
+        out = torch.empty(rows, D, dtype=torch.float32, device=dev)
+        ops.gemm(AO, blk["proj"][0], blk["proj"][1], out, ops.EPI_F32, split3=fp32)
+    else:
+        out = torch.empty(rows, kd * D, dtype=torch.bfloat16, device=dev)
+        ops.gemm(AO, blk["proj"][0], blk["proj"][1], out, ops.EPI_SPLIT_BF16 if fp32 else ops.EPI_BF16, split3=fp32)
+    return out
+
+
+def unsplit(t: torch.Tensor, precision: str) -> torch.Tensor:
+    """Debug/capture helper: fp32 view of a bf16 / split-bf16 activation."""
+    if precision == "fp32" and t.dtype == torch.bfloat16:
+        D = t.shape[-1] // 2
+        return t[..., :D].float() + t[..., D:].float()
+    return t.float()
+
+
+class PackCache:
+    """Mixin: lazily (re)build packed device weights when parameters or precision change."""
+
+    _packed = None
+    _packed_sig = None
+
+    def packed(self, build: Callable[[], Dict], module: nn.Module, precision: str) -> Dict:
+        sig = param_signature(module, precision)
+        if self._packed is None or self._packed_sig != sig:
+            with torch.no_grad():
+                self._packed = build()
+            self._packed_sig = sig
+        return self._packed

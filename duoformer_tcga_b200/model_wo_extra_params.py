@@ -1,0 +1,148 @@
+"""MyModel_no_extra_params — DuoFormer with the from-scratch MultiscaleFormer (primary target).
+
+Drop-in for models/model_wo_extra_params.py:29-302 of the reference: same constructor
+signature (plus the additive keyword `pretrained`, which build_model_no_extra_params already
+passes, `__init__.py:53,69`, App. A D2/D3), same attribute names = same state_dict keys.
+Forward: torch/cuDNN ResNet trunk -> fused projection/token-builder kernel -> MultiscaleFormer
+kernels.  CUDA + eval only; there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import torch
+import torchvision.models as models
+from torch import nn
+
+from . import engine
+from .projection_head import (Channel_Projector_All, Channel_Projector_layer1, Channel_Projector_layer2,
+                              Channel_Projector_layer3, Projection)
+from .resnet50ssl import resnet50FeatureExtractor
+from .scale_attention import MultiscaleFormer, _check_eval
+from .token_builder import TokenBuilder, TrunkRunner
+
+
+def _tv_resnet(name: str, pretrained: bool) -> nn.Module:
+    ctor = getattr(models, name)
+    if pretrained:
+        weights = {"resnet50": models.ResNet50_Weights.IMAGENET1K_V1, "resnet18": models.ResNet18_Weights.IMAGENET1K_V1}[name]
+        return ctor(weights=weights)  # == the reference's deprecated pretrained=True (needs network / cache)
+    return ctor(weights=None)
+
+
+class MyModel_no_extra_params(nn.Module):
+    def __init__(
+        self,
+        depth=None,
+        embed_dim=768,
+        num_heads=12,
+        init_values=1e-5,
+        num_classes=2,
+        num_layers=4,
+        num_patches=49,
+        mlp_ratio=4.0,
+        attn_drop_rate=0.0,
+        proj_drop_rate=0.0,
+        proj_dim=768,
+        freeze_backbone=True,
+        backbone="r50",
+        scale_token="random",
+        patch_attn=True,
+        pretrained=True,
+    ):
+        super().__init__()
+        if embed_dim != proj_dim:
+            raise ValueError(f"embed_dim ({embed_dim}) must equal proj_dim ({proj_dim})")
+        if depth is None:
+            raise TypeError("depth must be an int (the reference's default None cannot build a model)")
+        self.num_layers = num_layers
+        self.proj_dim = proj_dim
+        self.backbone = backbone
+        self.scale_token = scale_token
+        self.patch_attn = patch_attn
+        self.name = "scaleformer"
+        if backbone == "r50":
+            self.resnet_projector = nn.Sequential(*list(_tv_resnet("resnet50", pretrained).children())[:-2])
+        elif backbone == "r18":
+            self.resnet_projector = nn.Sequential(*list(_tv_resnet("resnet18", pretrained).children())[:-2])
+        elif backbone == "r50_Swav":
+            self.resnet_projector = resnet50FeatureExtractor(pretrained=pretrained, progress=False, key="SwAV")
+        else:
+            raise ValueError(f"unknown backbone {backbone!r}")
+        if freeze_backbone:
+            for param in self.resnet_projector.parameters():
+                param.requires_grad = False
+
+        if self.scale_token == "random":
+            self.channel_token = nn.Parameter(torch.randn(1, 1, 1, self.proj_dim))
+            nn.init.normal_(self.channel_token, std=0.036)
+        elif self.scale_token == "channel":
+            if backbone == "r18":
+                raise NotImplementedError("scale_token='channel' with r18 is broken in the reference")
+            self.chann_proj1 = Channel_Projector_layer1(backbone=backbone if backbone != "r50_Swav" else "r50")
+            self.chann_proj2 = Channel_Projector_layer2(backbone=backbone if backbone != "r50_Swav" else "r50")
+            self.chann_proj3 = Channel_Projector_layer3()
+            self.chann_proj_all = Channel_Projector_All(backbone=backbone if backbone != "r50_Swav" else "r50")
+        else:
+            raise ValueError(f"unknown scale_token {scale_token!r}")
+
+        self.projection = Projection(num_layers=self.num_layers, proj_dim=self.proj_dim,
+                                     backbone="r18" if backbone == "r18" else "r50")
+        self.vision_transformer = MultiscaleFormer(
+            depth=depth, scales=self.num_layers, num_heads=num_heads, embed_dim=embed_dim, mlp_ratio=mlp_ratio,
+            qkv_bias=True, qk_norm=False, proj_drop_rate=proj_drop_rate, attn_drop_rate=attn_drop_rate,
+            norm_layer=None, act_layer=None, init_values=None, num_classes=num_classes, num_patches=num_patches,
+            scale_token=scale_token, patch_attn=patch_attn,
+        )
+        # index tables are generated on device per patch grid (App. A D8, D15) — see index_tables.py
+        self._trunk_runner = TrunkRunner()
+        self._token_builder = TokenBuilder()
+        self._channel_runner = TrunkRunner()
+
+    # ---- precision switch (additive API) ---------------------------------------------------
+    @property
+    def precision(self) -> str:
+        return self.vision_transformer.precision
+
+    def set_precision(self, precision: str) -> "MyModel_no_extra_params":
+        """'bf16' (default, benchmarked path) or 'fp32' (3-pass split-bf16 GEMMs, 1e-3 accuracy)."""
+        if precision not in engine.PRECISIONS:
+            raise ValueError(f"precision must be one of {engine.PRECISIONS}")
+        self.vision_transformer.precision = precision
+        return self
+
+    # ---- reference API ------------------------------------------------------------------------
+    @torch.no_grad()
+    def get_features(self, x):
+        """Stage feature maps keyed '0'..'3' (model_wo_extra_params.py:214-224)."""
+        f = self._trunk_runner.features(self.resnet_projector, x, self.precision, self.backbone == "r50_Swav")
+        return {str(k): v for k, v in f.items()}
+
+    @torch.no_grad()
+    def channel_branch(self, feats) -> torch.Tensor:
+        """Channel token [B, P, D] fp32 from the four stage maps (model_wo_extra_params.py:236-248)."""
+        dt = torch.float32
+        with torch.autocast("cuda", enabled=False):
+            c0 = self.chann_proj1(feats[0].to(dt))
+            c1 = self.chann_proj2(feats[1].to(dt))
+            c2 = self.chann_proj3(feats[2].to(dt))
+            fused = torch.cat([c0, c1, c2, feats[3].to(dt)], dim=1)
+            tok = self.chann_proj_all(fused)  # [B, D, P]
+        return tok.permute(0, 2, 1).contiguous()
+
+    @torch.no_grad()
+    def build_tokens(self, x: torch.Tensor) -> torch.Tensor:
+        """Image batch -> fp32 tokens [B, P, S, D] including pos_embed_for_scale."""
+        feats = self._trunk_runner.features(self.resnet_projector, x, self.precision, self.backbone == "r50_Swav")
+        vt = self.vision_transformer
+        if self.scale_token == "channel":
+            tok = self.channel_branch(feats)
+        else:
+            tok = self.channel_token.detach().reshape(-1).to(torch.float32)
+        return self._token_builder.build(feats, self.projection, self.num_layers, tok, vt.pos_scale_table(),
+                                         self.precision)
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        _check_eval(self)
+        engine.require_cuda(x, "MyModel_no_extra_params.forward")
+        X = self.build_tokens(x)
+        return self.vision_transformer.forward_prepared(X)

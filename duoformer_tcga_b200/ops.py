@@ -134,6 +134,16 @@ def fill_scale_token(X: torch.Tensor, tok: torch.Tensor, pos0: torch.Tensor) -> 
     return X
 
 
+def add_pos(x: torch.Tensor, pos: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """out[..., s, :] = x[..., s, :] + pos[s, :]  (x fp32 [..., S, D] contiguous)."""
+    S, D = x.shape[-2], x.shape[-1]
+    assert x.dtype == torch.float32 and x.is_contiguous() and out.is_contiguous() and pos.is_contiguous()
+    _lib.check(
+        _lib.load().duo_add_pos(_ptr(x), _ptr(pos), _ptr(out), x.numel() // D, S, D, _stream()), "duo_add_pos"
+    )
+    return out
+
+
 def assemble_patch_tokens(X: torch.Tensor, cls: torch.Tensor, pos: torch.Tensor, Z: torch.Tensor) -> torch.Tensor:
     """Z[b,0]=cls+pos[0]; Z[b,1+p]=X[b,p,0]+pos[1+p].  Z bf16 [B,P+1,D] or split [B,P+1,2D]."""
     B, P, S, D = X.shape

@@ -1,0 +1,124 @@
+"""Multiscale token builder: stage features -> tokens [B, P, S, D] (fp32, + pos_embed_for_scale).
+
+Replaces, in ONE pass per stage, the reference sequence
+  Projection (1x1 conv)            projection_head.py:134-149
+  reshape + advanced-index gather  model_wo_extra_params.py:252-280 / model.py:300-306
+  cat + permute                    model_wo_extra_params.py:281     / model.py:307-309
+  scale-token concat               model_wo_extra_params.py:296-299 / model.py:322
+  x + pos_embed_for_scale          scale_attention.py:331 / multi_vision_transformer.py:142-144
+with a tcgen05 GEMM over the channels-last stage feature map whose epilogue adds bias and the
+scale position embedding and scatters each pixel row straight to its (patch, scale) token row.
+"""
+from __future__ import annotations
+
+import copy
+from typing import Dict, List, Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import engine, ops
+from .index_tables import num_scale_tokens, stages_used, token_row_maps
+
+
+class TrunkRunner:
+    """Runs the torch/cuDNN ResNet trunk in the precision of the path (bf16 channels-last copy
+    of the fp32 master weights, re-made when they change) and returns the tapped stage maps."""
+
+    def __init__(self):
+        self._sig = None
+        self._trunk: Optional[nn.Module] = None
+
+    def _packed_trunk(self, trunk: nn.Module, precision: str) -> nn.Module:
+        sig = engine.param_signature(trunk, precision)
+        if self._trunk is None or self._sig != sig:
+            t = copy.deepcopy(trunk).eval()
+            if precision == "bf16":
+                t = t.to(dtype=torch.bfloat16, memory_format=torch.channels_last)
+            else:
+                t = t.to(dtype=torch.float32, memory_format=torch.channels_last)
+            for p in t.parameters():
+                p.requires_grad_(False)
+            self._trunk, self._sig = t, sig
+        return self._trunk
+
+    @torch.no_grad()
+    def features(self, trunk: nn.Module, x: torch.Tensor, precision: str, by_scale: bool) -> Dict[int, torch.Tensor]:
+        t = self._packed_trunk(trunk, precision)
+        dt = torch.bfloat16 if precision == "bf16" else torch.float32
+        x = x.to(dtype=dt).contiguous(memory_format=torch.channels_last)
+        old_tf32 = torch.backends.cudnn.allow_tf32
+        if precision == "fp32":
+            torch.backends.cudnn.allow_tf32 = False
+        try:
+            if by_scale:  # ResNetTrunkByScale returns [layer1..layer4]  (resnet50ssl.py:35-45)
+                outs = t(x)
+                return {i: o for i, o in enumerate(outs)}
+            feats: Dict[int, torch.Tensor] = {}
+            # nn.Sequential(conv1,bn1,relu,maxpool,layer1..4): children '4'..'7' are the stage taps
+            # (model_wo_extra_params.py:214-224, model.py:213-223)
+            for name, module in t.named_children():
+                x = module(x)
+                if name in ("4", "5", "6", "7"):
+                    feats[int(name) - 4] = x
+            return feats
+        finally:
+            torch.backends.cudnn.allow_tf32 = old_tf32
+
+
+class TokenBuilder(engine.PackCache):
+    def __init__(self):
+        self._maps: Dict[Tuple[int, int, str], Dict[int, torch.Tensor]] = {}
+
+    def row_maps(self, num_layers: int, g: int, device: torch.device) -> Dict[int, torch.Tensor]:
+        key = (num_layers, g, str(device))
+        if key not in self._maps:
+            self._maps[key] = {k: m.to(device) for k, m in token_row_maps(num_layers, g).items()}
+        return self._maps[key]
+
+    def pack(self, projection: nn.Module, num_layers: int, precision: str) -> Dict[int, Tuple]:
+        def build():
+            return {k: engine.pack_linear(projection.head(k).weight, projection.head(k).bias, precision)
+                    for k in stages_used(num_layers)}
+
+        return self.packed(build, projection, precision)
+
+    @torch.no_grad()
+    def build(
+        self,
+        feats: Dict[int, torch.Tensor],
+        projection: nn.Module,
+        num_layers: int,
+        scale_tok: torch.Tensor,
+        pos_scale: torch.Tensor,
+        precision: str,
+    ) -> torch.Tensor:
+        """feats[k]: [B, C_k, g*w, g*w] (any memory format; channels-last is free).
+        scale_tok: [D] learned channel_token, or [B, P, D] channel-branch output (fp32).
+        pos_scale: [S, D] fp32.  Returns X fp32 [B, P, S, D]."""
+        B, _, h3, w3 = feats[3].shape
+        assert h3 == w3, "square inputs only"
+        g = h3
+        P = g * g
+        S = num_scale_tokens(num_layers)
+        D = pos_scale.shape[1]
+        dev = feats[3].device
+        X = torch.empty(B, P, S, D, dtype=torch.float32, device=dev)
+        ops.fill_scale_token(X, scale_tok, pos_scale[0])
+        maps = self.row_maps(num_layers, g, dev)
+        packs = self.pack(projection, num_layers, precision)
+        for k in stages_used(num_layers):
+            f = feats[k]
+            Bk, C, H, W = f.shape
+            assert H == g * 2 ** (3 - k) and W == H, f"stage {k}: expected {g * 2 ** (3 - k)}^2, got {H}x{W}"
+            rows = f.permute(0, 2, 3, 1)  # NHWC view; contiguous when f is channels-last
+            if precision == "bf16":
+                A = rows.to(torch.bfloat16).contiguous().view(Bk * H * W, C)
+            else:
+                a32 = rows.to(torch.float32).contiguous().view(Bk * H * W, C)
+                A = torch.empty(Bk * H * W, 2 * C, dtype=torch.bfloat16, device=dev)
+                ops.convert(a32, A)
+            w, b = packs[k]
+            ops.gemm(A, w, b, X.view(B * P * S, D), ops.EPI_SCATTER_F32, split3=(precision == "fp32"),
+                     row_map=maps[k], rows_per_group=H * W, dest_rows_per_group=P * S, pos=pos_scale, pos_period=S)
+        return X

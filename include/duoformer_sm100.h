@@ -130,6 +130,14 @@ int duo_fill_scale_token(float* X, const float* tok, int64_t tok_stride_b, int64
                          duo_stream_t stream);
 
 /*
+ * out[r,:] = in[r,:] + pos[r % S,:]  — `x + pos_embed_for_scale` for callers that hand a
+ * ready-made token tensor to MultiscaleFormer / MultiscaleTransformer
+ * (scale_attention.py:331 ; multi_vision_transformer.py:142-144).  in == out allowed.
+ */
+int duo_add_pos(const float* in, const float* pos, float* out, int64_t rows, int32_t S, int32_t D,
+                duo_stream_t stream);
+
+/*
  * Patch-stage input:  Z[b,0,:] = cls + pos[0];  Z[b,1+p,:] = X[b,p,0,:] + pos[1+p]
  * scale_attention.py:183-193 ; multiscale_attn.py:190-203.  out_kind BF16 or SPLIT.
  */

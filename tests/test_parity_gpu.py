@@ -1,0 +1,104 @@
+"""End-to-end and stage-wise parity (-m gpu): product model (CUDA kernels through the C ABI)
+against (a) the golden logits produced by the REAL reference and (b) the fp32 oracle's
+intermediates on identical seeded weights and inputs.
+
+Tolerances (BASELINE.json north_star): relative max-norm error  ||y - y_ref||_inf / ||y_ref||_inf
+  bf16 mode <= 2e-2, fp32 mode <= 1e-3, identical argmax."""
+import os
+
+import pytest
+import torch
+
+from common import build_product, load_golden, oracle_forward, relerr
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"bf16": 2e-2, "fp32": 1e-3}
+
+
+def _run(name, precision, capture=False):
+    gold = load_golden(name)
+    case = gold["case"]
+    model = build_product(case)
+    sd = synth.synth_state_dict(model.state_dict(), seed=gold["weight_seed"])
+    model.load_state_dict(sd)
+    model = model.cuda().eval().set_precision(precision)
+    x = synth.synth_images(case["batch"], seed=gold["input_seed"])
+    cap = {} if capture else None
+    model.vision_transformer._capture = cap
+    with torch.no_grad():
+        y = model(x.cuda())
+    torch.cuda.synchronize()
+    return gold, case, sd, x, y.float().cpu(), cap
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+@pytest.mark.parametrize("name", ["wo2_d12", "wo4_d2", "wo3_d2", "wo2_channel_d2", "wo2_swav_d2", "mm2_d12", "mm2_d1", "mm2_d2_b1"])
+def test_logits_match_reference(name, precision):
+    gold, case, sd, x, y, _ = _run(name, precision)
+    ref = gold["logits"]
+    assert tuple(y.shape) == tuple(ref.shape)
+    err = relerr(y, ref)
+    assert err < TOL[precision], f"{name} {precision}: rel err {err:.3e}"
+    assert torch.equal(y.reshape(-1, 10).argmax(-1), ref.reshape(-1, 10).argmax(-1))
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+@pytest.mark.parametrize("name", ["wo2_d12", "wo4_d2", "mm2_d12"])
+def test_stagewise_against_oracle(name, precision):
+    torch.set_num_threads(os.cpu_count() or 1)
+    gold, case, sd, x, y, cap = _run(name, precision, capture=True)
+    ocap = {}
+    with torch.no_grad():
+        yo = oracle_forward(case, x, sd, capture=ocap)
+    tol = TOL[precision]
+    worst = {}
+    for key, t in cap.items():
+        assert key in ocap, key
+        e = relerr(t, ocap[key])
+        worst[key] = e
+        assert e < tol, f"{name} {precision} {key}: rel err {e:.3e}"
+    assert relerr(y, yo) < tol
+    assert "tokens" in worst and any(k.startswith("scale_block") for k in worst)
+
+
+def test_forward_from_tokens_entry_point():
+    """MultiscaleFormer.forward(tokens) — the reference's own entry point (tokens without
+    pos_embed_for_scale) — equals the fused path."""
+    gold, case, sd, x, y, cap = _run("wo4_d2", "bf16", capture=True)
+    model = build_product(case)
+    model.load_state_dict(sd)
+    model = model.cuda().eval()
+    vt = model.vision_transformer
+    tokens = cap["tokens"] - vt.pos_embed_for_scale
+    with torch.no_grad():
+        y2 = vt(tokens.clone()).float().cpu()
+    assert relerr(y2, y) < 2e-3
+
+
+def test_batch_split_and_permutation_invariance():
+    gold = load_golden("wo4_d2")
+    case = gold["case"]
+    model = build_product(case)
+    model.load_state_dict(synth.synth_state_dict(model.state_dict(), seed=0))
+    model = model.cuda().eval()
+    x = synth.synth_images(6, seed=7).cuda()
+    with torch.no_grad():
+        y = model(x)
+        perm = torch.tensor([3, 0, 5, 1, 4, 2], device="cuda")
+        yp = model(x[perm])
+        ys = torch.cat([model(x[:2]), model(x[2:])], dim=0)
+    assert relerr(yp, y[perm]) < 5e-3
+    assert relerr(ys, y) < 5e-3
+
+
+def test_cpu_input_and_training_mode_raise():
+    gold = load_golden("mm2_d1")
+    model = build_product(gold["case"]).cuda().eval()
+    with pytest.raises(NotImplementedError):
+        model(torch.zeros(1, 3, 224, 224))
+    model.train()
+    with torch.enable_grad():
+        with pytest.raises(NotImplementedError):
+            model(torch.zeros(1, 3, 224, 224, device="cuda"))
