@@ -26,6 +26,11 @@ from ._lib import (  # noqa: F401  (re-exported)
 )
 
 
+# Optional per-launch CUDA-event timing of the GEMM kernel (bench.py's live roofline): when a
+# list is installed here, every gemm() appends (start_event, end_event, flops, tag).
+GEMM_PROFILE = None
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -81,7 +86,14 @@ def gemm(
         assert bias.dtype == torch.float32 and bias.numel() == N
     if row_map is not None:
         assert row_map.dtype == torch.int32
+    prof = GEMM_PROFILE
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     _lib.check(_lib.load().duo_gemm(ctypes.byref(a), _stream()), "duo_gemm")
+    if prof is not None:
+        e1.record()
+        prof.append((e0, e1, 2.0 * M * N * K * (3 if split3 else 1), f"{N}x{K}:epi{epilogue}"))
     return out
 
 

@@ -19,10 +19,9 @@ from .vit_layout import AttentionParams, LayerScale, Mlp, named_apply_vit_init, 
 
 
 def _check_eval(module: nn.Module) -> None:
-    if module.training and torch.is_grad_enabled():
+    if module.training:
         raise NotImplementedError(
-            "duoformer_tcga_b200 implements the inference forward only: call model.eval() "
-            "and run under torch.no_grad()"
+            "duoformer_tcga_b200 implements the inference (eval-mode) forward only: call model.eval()"
         )
 
 
