@@ -45,6 +45,91 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
 
+// GELU(erf) with erf evaluated by the fp32 rational minimax approximation x*P(x^2)/Q(x^2) on
+// [-4, 4] (coefficients of the widely used Eigen/XLA float erf; max abs error 4.2e-7 vs erf,
+// measured in numpy) — ~18 FMA-pipe ops + 1 MUFU.RCP per element instead of libdevice erff.
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  float t = fminf(fmaxf(x * 0.70710678118654752440f, -4.0f), 4.0f);
+  const float t2 = t * t;
+  float p = -2.72614225801306e-10f;
+  p = fmaf(p, t2, 2.77068142495902e-08f);
+  p = fmaf(p, t2, -2.10102402082508e-06f);
+  p = fmaf(p, t2, -5.69250639462346e-05f);
+  p = fmaf(p, t2, -7.34990630326855e-04f);
+  p = fmaf(p, t2, -2.95459980854025e-03f);
+  p = fmaf(p, t2, -1.60960333262415e-02f);
+  p *= t;
+  float q = -1.45660718464996e-05f;
+  q = fmaf(q, t2, -2.13374055278905e-04f);
+  q = fmaf(q, t2, -1.68282697438203e-03f);
+  q = fmaf(q, t2, -7.37332916720468e-03f);
+  q = fmaf(q, t2, -1.42647390514189e-02f);
+  const float e = __fdividef(p, q);
+  const float hx = 0.5f * x;
+  return fmaf(hx, e, hx);
+}
+
+// ---- packed fp32x2 arithmetic (Blackwell FFMA2/FMUL2/FADD2: two fp32 lanes per issue slot) ----
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// gelu_erf_fast on two values at once: the Horner chains run as FFMA2.
+__device__ __forceinline__ void gelu_erf_fast_x2(float& a, float& b) {
+#define DUO_C2(v) pack2((v), (v))
+  const uint64_t x = pack2(a, b);
+  float ta, tb;
+  unpack2(mul2(x, DUO_C2(0.70710678118654752440f)), ta, tb);
+  ta = fminf(fmaxf(ta, -4.0f), 4.0f);
+  tb = fminf(fmaxf(tb, -4.0f), 4.0f);
+  const uint64_t t = pack2(ta, tb);
+  const uint64_t t2 = mul2(t, t);
+  uint64_t p = fma2(DUO_C2(-2.72614225801306e-10f), t2, DUO_C2(2.77068142495902e-08f));
+  p = fma2(p, t2, DUO_C2(-2.10102402082508e-06f));
+  p = fma2(p, t2, DUO_C2(-5.69250639462346e-05f));
+  p = fma2(p, t2, DUO_C2(-7.34990630326855e-04f));
+  p = fma2(p, t2, DUO_C2(-2.95459980854025e-03f));
+  p = fma2(p, t2, DUO_C2(-1.60960333262415e-02f));
+  p = mul2(p, t);
+  uint64_t q = fma2(DUO_C2(-1.45660718464996e-05f), t2, DUO_C2(-2.13374055278905e-04f));
+  q = fma2(q, t2, DUO_C2(-1.68282697438203e-03f));
+  q = fma2(q, t2, DUO_C2(-7.37332916720468e-03f));
+  q = fma2(q, t2, DUO_C2(-1.42647390514189e-02f));
+  float qa, qb;
+  unpack2(q, qa, qb);
+  const uint64_t rq = pack2(rcp_approx(qa), rcp_approx(qb));
+  const uint64_t e = mul2(p, rq);
+  const uint64_t hx = mul2(x, DUO_C2(0.5f));
+  unpack2(fma2(hx, e, hx), a, b);
+#undef DUO_C2
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);  // .x = a (low 16 bits), .y = b
   return *reinterpret_cast<uint32_t*>(&v);

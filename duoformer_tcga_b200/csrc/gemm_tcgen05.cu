@@ -12,13 +12,18 @@
 //               accumulating into one of two TMEM accumulator buffers; tcgen05.commit releases
 //               ring slots (`empty`) and publishes finished accumulators (`tmem_full`).
 //   warps 2..5  epilogue: tcgen05.ld the accumulator (one TMEM lane quarter per warp, one output
-//               row per thread), fuse bias / GELU(erf) / LayerScale+residual / token scatter /
-//               hi-lo split, store to global, then hand the buffer back (`tmem_empty`).
+//               row per thread), fuse bias / GELU(erf) / LayerScale, then
+//                 * bf16 outputs: rows staged in a per-warp double-buffered 128B-swizzled
+//                   shared-memory tile and written with TMA stores (full-line, coalesced);
+//                 * residual (X += ...): staged fp32 tile + TMA reduce-add into the fp32 residual
+//                   stream (the read-modify-write happens in L2, no SM-side loads);
+//                 * token scatter / fp32 / hi-lo split outputs: direct 16-byte global stores.
 //               Double-buffered TMEM lets the epilogue of tile i overlap the MMAs of tile i+1.
 //
 // split3 mode (fp32-accuracy path): A and W hold bf16 hi|lo halves; the K loop runs three
 // segments (Ah*Wh, Ah*Wl, Al*Wh) into the same accumulator.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -31,6 +36,17 @@ constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int kUmmaK = 16;
 constexpr int kNumThreads = 192;
 constexpr int kNumEpilogueThreads = 128;
+constexpr uint32_t kStagingBytesPerWarp = 2 * 32 * 128;  // two 32-row x 128 B buffers
+
+// Internal epilogue variants (superset of the ABI's DUO_EPI_*): staged TMA paths.
+constexpr int kEpiResidualTma = 100;  // DUO_EPI_RESIDUAL_F32 through TMA reduce-add
+
+template <int EPI>
+struct EpiTraits {
+  static constexpr bool kStagedBf16 = (EPI == DUO_EPI_BF16 || EPI == DUO_EPI_GELU_BF16);
+  static constexpr bool kStagedF32 = (EPI == kEpiResidualTma);
+  static constexpr bool kStaged = kStagedBf16 || kStagedF32;
+};
 
 template <int BLOCK_N>
 struct Cfg {
@@ -39,8 +55,9 @@ struct Cfg {
   static constexpr uint32_t kBBytes = BLOCK_N * kBlockK * 2;   // 32 / 16 KB
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
   static constexpr uint32_t kTmemCols = 2 * BLOCK_N;           // two accumulator buffers
+  static constexpr uint32_t kStagingBytes = 4 * kStagingBytesPerWarp;  // 32 KB
   static constexpr uint32_t kBarrierBytes = (2 * kStages + 4) * 8 + 8;
-  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kBarrierBytes + 1024;
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kStagingBytes + kBarrierBytes + 1024;
 };
 
 struct GemmParams {
@@ -57,42 +74,51 @@ struct GemmParams {
   int32_t num_m_blocks, num_n_blocks;
 };
 
+// acc[32] (fp32 bits) -> f[32] = acc + bias (optionally GELU'd / scaled by LayerScale gamma)
 template <int EPI>
-__device__ __forceinline__ void epilogue_store(const GemmParams& p, int64_t row, int col,
-                                               uint32_t (&v)[32]) {
-  // v holds 32 consecutive fp32 accumulator columns [col, col+32) of output row `row`.
-  float f[32];
+__device__ __forceinline__ void epilogue_math(const GemmParams& p, int col, const uint32_t (&v)[32],
+                                              float (&f)[32]) {
 #pragma unroll
   for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
   if (p.bias != nullptr) {
     const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float4 b = __ldg(b4 + j);
+      const float4 b = __ldg(b4 + j);
       f[4 * j + 0] += b.x;
       f[4 * j + 1] += b.y;
       f[4 * j + 2] += b.z;
       f[4 * j + 3] += b.w;
     }
   }
-  if constexpr (EPI == DUO_EPI_GELU_BF16 || EPI == DUO_EPI_GELU_SPLIT_BF16) {
+  if constexpr (EPI == DUO_EPI_GELU_BF16) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) gelu_erf_fast_x2(f[j], f[j + 1]);
+  }
+  if constexpr (EPI == DUO_EPI_GELU_SPLIT_BF16) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
   }
-
-  if constexpr (EPI == DUO_EPI_BF16 || EPI == DUO_EPI_GELU_BF16) {
-    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + col;
-    uint4* o4 = reinterpret_cast<uint4*>(o);
+  if constexpr (EPI == kEpiResidualTma) {
+    if (p.gamma != nullptr) {
+      const float4* g4 = reinterpret_cast<const float4*>(p.gamma + col);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      uint4 w;
-      w.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
-      w.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-      w.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
-      w.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-      o4[j] = w;
+      for (int j = 0; j < 8; ++j) {
+        const float4 g = __ldg(g4 + j);
+        f[4 * j + 0] *= g.x;
+        f[4 * j + 1] *= g.y;
+        f[4 * j + 2] *= g.z;
+        f[4 * j + 3] *= g.w;
+      }
     }
-  } else if constexpr (EPI == DUO_EPI_SPLIT_BF16 || EPI == DUO_EPI_GELU_SPLIT_BF16) {
+  }
+}
+
+// Direct (non-staged) stores: one output row per thread, 32 consecutive columns.
+template <int EPI>
+__device__ __forceinline__ void epilogue_store_direct(const GemmParams& p, int64_t row, int col,
+                                                      float (&f)[32]) {
+  if constexpr (EPI == DUO_EPI_SPLIT_BF16 || EPI == DUO_EPI_GELU_SPLIT_BF16) {
     __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + col;
     __nv_bfloat16* ol = oh + p.N;
     uint4* h4 = reinterpret_cast<uint4*>(oh);
@@ -121,7 +147,7 @@ __device__ __forceinline__ void epilogue_store(const GemmParams& p, int64_t row,
       const float4* g4 = reinterpret_cast<const float4*>(p.gamma + col);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float4 g = __ldg(g4 + j);
+        const float4 g = __ldg(g4 + j);
         r[j].x = fmaf(g.x, f[4 * j + 0], r[j].x);
         r[j].y = fmaf(g.y, f[4 * j + 1], r[j].y);
         r[j].z = fmaf(g.z, f[4 * j + 2], r[j].z);
@@ -148,7 +174,7 @@ __device__ __forceinline__ void epilogue_store(const GemmParams& p, int64_t row,
       const float4* q4 = reinterpret_cast<const float4*>(p.pos + static_cast<int64_t>(s) * p.N + col);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float4 q = __ldg(q4 + j);
+        const float4 q = __ldg(q4 + j);
         f[4 * j + 0] += q.x;
         f[4 * j + 1] += q.y;
         f[4 * j + 2] += q.z;
@@ -162,17 +188,26 @@ __device__ __forceinline__ void epilogue_store(const GemmParams& p, int64_t row,
   }
 }
 
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c,
+                                             uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d)
+               : "memory");
+}
+
 template <int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
-                    const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+                    const __grid_constant__ CUtensorMap tmap_b,
+                    const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
   using C = Cfg<BLOCK_N>;
+  using ET = EpiTraits<EPI>;
   constexpr int kStages = C::kStages;
 
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024 B alignment.
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + kStages * C::kStageBytes;
+  const uint32_t staging_base = smem_base + kStages * C::kStageBytes;  // 1024-aligned
+  const uint32_t bar_base = staging_base + C::kStagingBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
   auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
@@ -187,6 +222,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   if (warp_idx == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_a);
     ptx::prefetch_tmap(&tmap_b);
+    if constexpr (ET::kStaged) ptx::prefetch_tmap(&tmap_out);
 #pragma unroll
     for (int s = 0; s < kStages; ++s) {
       ptx::mbar_init(full_bar(s), 1);
@@ -284,30 +320,111 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   } else {
     // ===================== epilogue warps (2..5) =====================
     const int quarter = warp_idx & 3;  // TMEM lane quarter this warp may access
+    const uint32_t stg = staging_base + static_cast<uint32_t>(quarter) * kStagingBytesPerWarp;
+    const uint32_t my_row_off = static_cast<uint32_t>(lane) * 128u;
+    uint32_t stg_buf = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = static_cast<int>(tile / p.num_n_blocks);
       const int n_blk = static_cast<int>(tile - static_cast<int64_t>(m_blk) * p.num_n_blocks);
-      const int64_t row = static_cast<int64_t>(m_blk) * kBlockM + quarter * 32 + lane;
+      const int row0 = m_blk * kBlockM + quarter * 32;  // first row of this warp's slab
+      const int64_t row = static_cast<int64_t>(row0) + lane;
       const bool valid = row < p.M;
+      const int n0 = n_blk * BLOCK_N;
       ptx::mbar_wait(tmem_full_bar(acc), acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr =
           tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
+
+      if constexpr (ET::kStagedBf16) {
+        // 64 output columns (= 128 B of bf16) per staged chunk
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 32) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(taddr + static_cast<uint32_t>(c), v);
-        ptx::tmem_ld_wait();
-        if (valid) epilogue_store<EPI>(p, row, n_blk * BLOCK_N + c, v);
+        for (int c = 0; c < BLOCK_N; c += 64) {
+          uint32_t v0[32], v1[32];
+          ptx::tmem_ld_32x32(taddr + static_cast<uint32_t>(c), v0);
+          ptx::tmem_ld_32x32(taddr + static_cast<uint32_t>(c + 32), v1);
+          ptx::tmem_ld_wait();
+          if (c + 64 >= BLOCK_N) {  // accumulator fully read: hand the TMEM buffer back early
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(tmem_empty_bar(acc));
+          }
+          float f0[32], f1[32];
+          epilogue_math<EPI>(p, n0 + c, v0, f0);
+          epilogue_math<EPI>(p, n0 + c + 32, v1, f1);
+          if (lane == 0) ptx::tma_store_wait_read<1>();  // buffer `stg_buf` no longer being read
+          __syncwarp();
+          const uint32_t buf = stg + stg_buf * (32u * 128u) + my_row_off;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {  // 16-byte chunk j / j+4 of this row, XOR-swizzled
+            st_shared_v4(buf + (static_cast<uint32_t>(j ^ (lane & 7)) << 4),
+                         pack_bf16x2(f0[8 * j + 0], f0[8 * j + 1]), pack_bf16x2(f0[8 * j + 2], f0[8 * j + 3]),
+                         pack_bf16x2(f0[8 * j + 4], f0[8 * j + 5]), pack_bf16x2(f0[8 * j + 6], f0[8 * j + 7]));
+            st_shared_v4(buf + (static_cast<uint32_t>((j + 4) ^ (lane & 7)) << 4),
+                         pack_bf16x2(f1[8 * j + 0], f1[8 * j + 1]), pack_bf16x2(f1[8 * j + 2], f1[8 * j + 3]),
+                         pack_bf16x2(f1[8 * j + 4], f1[8 * j + 5]), pack_bf16x2(f1[8 * j + 6], f1[8 * j + 7]));
+          }
+          ptx::fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_store_2d(&tmap_out, stg + stg_buf * (32u * 128u), n0 + c, row0);
+            ptx::tma_store_commit();
+          }
+          stg_buf ^= 1u;
+        }
+      } else if constexpr (ET::kStagedF32) {
+        // 32 output columns (= 128 B of fp32) per staged chunk, TMA reduce-add into X
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N; c += 32) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32(taddr + static_cast<uint32_t>(c), v);
+          ptx::tmem_ld_wait();
+          if (c + 32 >= BLOCK_N) {
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(tmem_empty_bar(acc));
+          }
+          float f[32];
+          epilogue_math<EPI>(p, n0 + c, v, f);
+          if (lane == 0) ptx::tma_store_wait_read<1>();
+          __syncwarp();
+          const uint32_t buf = stg + stg_buf * (32u * 128u) + my_row_off;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            st_shared_v4(buf + (static_cast<uint32_t>(j ^ (lane & 7)) << 4), __float_as_uint(f[4 * j + 0]),
+                         __float_as_uint(f[4 * j + 1]), __float_as_uint(f[4 * j + 2]),
+                         __float_as_uint(f[4 * j + 3]));
+          ptx::fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_reduce_add_2d(&tmap_out, stg + stg_buf * (32u * 128u), n0 + c, row0);
+            ptx::tma_store_commit();
+          }
+          stg_buf ^= 1u;
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N; c += 32) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32(taddr + static_cast<uint32_t>(c), v);
+          ptx::tmem_ld_wait();
+          if (c + 32 >= BLOCK_N) {
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(tmem_empty_bar(acc));
+          }
+          if (valid) {
+            float f[32];
+            epilogue_math<EPI>(p, n0 + c, v, f);
+            epilogue_store_direct<EPI>(p, row, n0 + c, f);
+          }
+        }
       }
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(tmem_empty_bar(acc));
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1u;
       }
+    }
+    if constexpr (ET::kStaged) {
+      if (lane == 0) ptx::tma_store_wait<0>();  // all bulk stores of this warp complete
     }
   }
 
@@ -337,21 +454,23 @@ PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
-// bf16 [rows, cols] row-major (leading dim ld elements); box = box_rows x 64 cols, 128B swizzle.
-int make_tmap_bf16(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld,
-                   int box_rows) {
+// Row-major [rows, cols] matrix (leading dim ld elements); box = box_rows x (128 B of columns),
+// 128B swizzle.  elem_bytes 2 -> bf16, 4 -> fp32.
+int make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld,
+              int box_rows, int elem_bytes) {
   PFN_encodeTiled fn = get_encode_fn();
   if (fn == nullptr) {
     set_error("cuTensorMapEncodeTiled entry point not available");
     return DUO_ERR_CUDA;
   }
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(box_rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * elem_bytes};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / elem_bytes), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride,
-                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(tm, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                  2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed: CUresult %d (rows=%lld cols=%lld ld=%lld)", (int)r,
               (long long)rows, (long long)cols, (long long)ld);
@@ -361,7 +480,8 @@ int make_tmap_bf16(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols
 }
 
 template <int BLOCK_N, int EPI>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const GemmParams& p,
+           cudaStream_t st) {
   using C = Cfg<BLOCK_N>;
   static bool configured = false;
   auto kfn = gemm_tcgen05_kernel<BLOCK_N, EPI>;
@@ -373,24 +493,35 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cu
   const int64_t tiles = static_cast<int64_t>(p.num_m_blocks) * p.num_n_blocks;
   const int sms = device_sm_count();
   const int grid = static_cast<int>(tiles < sms ? tiles : sms);
-  kfn<<<grid, kNumThreads, C::kSmemBytes, st>>>(ta, tb, p);
+  kfn<<<grid, kNumThreads, C::kSmemBytes, st>>>(ta, tb, to, p);
   DUO_LAUNCH_CHECK("gemm_tcgen05_kernel");
   return DUO_OK;
 }
 
 template <int BLOCK_N>
-int dispatch_epi(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int epi,
-                 cudaStream_t st) {
+int dispatch_epi(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
+                 const GemmParams& p, int epi, cudaStream_t st) {
   switch (epi) {
-    case DUO_EPI_BF16: return launch<BLOCK_N, DUO_EPI_BF16>(ta, tb, p, st);
-    case DUO_EPI_GELU_BF16: return launch<BLOCK_N, DUO_EPI_GELU_BF16>(ta, tb, p, st);
-    case DUO_EPI_RESIDUAL_F32: return launch<BLOCK_N, DUO_EPI_RESIDUAL_F32>(ta, tb, p, st);
-    case DUO_EPI_SCATTER_F32: return launch<BLOCK_N, DUO_EPI_SCATTER_F32>(ta, tb, p, st);
-    case DUO_EPI_F32: return launch<BLOCK_N, DUO_EPI_F32>(ta, tb, p, st);
-    case DUO_EPI_SPLIT_BF16: return launch<BLOCK_N, DUO_EPI_SPLIT_BF16>(ta, tb, p, st);
-    case DUO_EPI_GELU_SPLIT_BF16: return launch<BLOCK_N, DUO_EPI_GELU_SPLIT_BF16>(ta, tb, p, st);
+    case DUO_EPI_BF16: return launch<BLOCK_N, DUO_EPI_BF16>(ta, tb, to, p, st);
+    case DUO_EPI_GELU_BF16: return launch<BLOCK_N, DUO_EPI_GELU_BF16>(ta, tb, to, p, st);
+    case DUO_EPI_RESIDUAL_F32: return launch<BLOCK_N, DUO_EPI_RESIDUAL_F32>(ta, tb, to, p, st);
+    case kEpiResidualTma: return launch<BLOCK_N, kEpiResidualTma>(ta, tb, to, p, st);
+    case DUO_EPI_SCATTER_F32: return launch<BLOCK_N, DUO_EPI_SCATTER_F32>(ta, tb, to, p, st);
+    case DUO_EPI_F32: return launch<BLOCK_N, DUO_EPI_F32>(ta, tb, to, p, st);
+    case DUO_EPI_SPLIT_BF16: return launch<BLOCK_N, DUO_EPI_SPLIT_BF16>(ta, tb, to, p, st);
+    case DUO_EPI_GELU_SPLIT_BF16: return launch<BLOCK_N, DUO_EPI_GELU_SPLIT_BF16>(ta, tb, to, p, st);
     default: set_error("duo_gemm: unknown epilogue %d", epi); return DUO_ERR_INVALID;
   }
+}
+
+// DUO_GEMM_RESIDUAL=direct selects the load/add/store residual epilogue instead of TMA reduce-add.
+bool residual_via_tma() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DUO_GEMM_RESIDUAL");
+    v = (e != nullptr && e[0] == 'd') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 }  // namespace
@@ -424,10 +555,20 @@ extern "C" int duo_gemm(const duo_gemm_args* a, duo_stream_t stream) {
   int block_n = 128;
   if (a->N % 256 == 0 && m_blocks * (a->N / 256) >= 2 * device_sm_count()) block_n = 256;
 
-  CUtensorMap ta, tb;
-  int rc = make_tmap_bf16(&ta, a->A, a->M, kcols, a->lda, kBlockM);
+  CUtensorMap ta, tb, to;
+  int rc = make_tmap(&ta, a->A, a->M, kcols, a->lda, kBlockM, 2);
   if (rc != DUO_OK) return rc;
-  rc = make_tmap_bf16(&tb, a->W, a->N, kcols, a->ldw, block_n);
+  rc = make_tmap(&tb, a->W, a->N, kcols, a->ldw, block_n, 2);
+  if (rc != DUO_OK) return rc;
+  int epi = a->epilogue;
+  if (epi == DUO_EPI_RESIDUAL_F32 && residual_via_tma()) epi = kEpiResidualTma;
+  if (epi == DUO_EPI_BF16 || epi == DUO_EPI_GELU_BF16) {
+    rc = make_tmap(&to, a->out, a->M, a->N, a->ldo, 32, 2);
+  } else if (epi == kEpiResidualTma) {
+    rc = make_tmap(&to, a->out, a->M, a->N, a->ldo, 32, 4);
+  } else {
+    to = ta;  // unused by the direct-store epilogues
+  }
   if (rc != DUO_OK) return rc;
 
   GemmParams p;
@@ -447,6 +588,6 @@ extern "C" int duo_gemm(const duo_gemm_args* a, duo_stream_t stream) {
   p.num_m_blocks = static_cast<int32_t>(m_blocks);
   p.num_n_blocks = a->N / block_n;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (block_n == 256) return dispatch_epi<256>(ta, tb, p, a->epilogue, st);
-  return dispatch_epi<128>(ta, tb, p, a->epilogue, st);
+  if (block_n == 256) return dispatch_epi<256>(ta, tb, to, p, epi, st);
+  return dispatch_epi<128>(ta, tb, to, p, epi, st);
 }
