@@ -194,6 +194,101 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
                : "memory");
 }
 
+// One accumulator tile (this warp's 32 rows x BLOCK_N columns): TMEM -> registers -> fused math ->
+// global memory.  `release()` is called as soon as the accumulator has been read completely.
+template <int BLOCK_N, int EPI, typename ReleaseFn>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtensorMap* tmap_out,
+                                              uint32_t taddr, int row0, int lane, int n0, uint32_t stg,
+                                              uint32_t& stg_buf, ReleaseFn release) {
+  using ET = EpiTraits<EPI>;
+  const int64_t row = static_cast<int64_t>(row0) + lane;
+  const bool valid = row < p.M;
+  const uint32_t my_row_off = static_cast<uint32_t>(lane) * 128u;
+  (void)valid;
+  (void)my_row_off;
+  if constexpr (ET::kStagedBf16) {
+    // 64 output columns (= 128 B of bf16) per staged chunk
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N; c += 64) {
+      uint32_t v0[32], v1[32];
+      ptx::tmem_ld_32x32(taddr + static_cast<uint32_t>(c), v0);
+      ptx::tmem_ld_32x32(taddr + static_cast<uint32_t>(c + 32), v1);
+      ptx::tmem_ld_wait();
+      if (c + 64 >= BLOCK_N) {  // accumulator fully read: hand the TMEM buffer back early
+        ptx::tc_fence_before();
+        release();
+      }
+      float f0[32], f1[32];
+      epilogue_math<EPI>(p, n0 + c, v0, f0);
+      epilogue_math<EPI>(p, n0 + c + 32, v1, f1);
+      if (lane == 0) ptx::tma_store_wait_read<1>();  // buffer `stg_buf` no longer being read
+      __syncwarp();
+      const uint32_t buf = stg + stg_buf * (32u * 128u) + my_row_off;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {  // 16-byte chunk j / j+4 of this row, XOR-swizzled
+        st_shared_v4(buf + (static_cast<uint32_t>(j ^ (lane & 7)) << 4),
+                     pack_bf16x2(f0[8 * j + 0], f0[8 * j + 1]), pack_bf16x2(f0[8 * j + 2], f0[8 * j + 3]),
+                     pack_bf16x2(f0[8 * j + 4], f0[8 * j + 5]), pack_bf16x2(f0[8 * j + 6], f0[8 * j + 7]));
+        st_shared_v4(buf + (static_cast<uint32_t>((j + 4) ^ (lane & 7)) << 4),
+                     pack_bf16x2(f1[8 * j + 0], f1[8 * j + 1]), pack_bf16x2(f1[8 * j + 2], f1[8 * j + 3]),
+                     pack_bf16x2(f1[8 * j + 4], f1[8 * j + 5]), pack_bf16x2(f1[8 * j + 6], f1[8 * j + 7]));
+      }
+      ptx::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        ptx::tma_store_2d(tmap_out, stg + stg_buf * (32u * 128u), n0 + c, row0);
+        ptx::tma_store_commit();
+      }
+      stg_buf ^= 1u;
+    }
+  } else if constexpr (ET::kStagedF32) {
+    // 32 output columns (= 128 B of fp32) per staged chunk, TMA reduce-add into X
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N; c += 32) {
+      uint32_t v[32];
+      ptx::tmem_ld_32x32(taddr + static_cast<uint32_t>(c), v);
+      ptx::tmem_ld_wait();
+      if (c + 32 >= BLOCK_N) {
+        ptx::tc_fence_before();
+        release();
+      }
+      float f[32];
+      epilogue_math<EPI>(p, n0 + c, v, f);
+      if (lane == 0) ptx::tma_store_wait_read<1>();
+      __syncwarp();
+      const uint32_t buf = stg + stg_buf * (32u * 128u) + my_row_off;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        st_shared_v4(buf + (static_cast<uint32_t>(j ^ (lane & 7)) << 4), __float_as_uint(f[4 * j + 0]),
+                     __float_as_uint(f[4 * j + 1]), __float_as_uint(f[4 * j + 2]),
+                     __float_as_uint(f[4 * j + 3]));
+      ptx::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        ptx::tma_reduce_add_2d(tmap_out, stg + stg_buf * (32u * 128u), n0 + c, row0);
+        ptx::tma_store_commit();
+      }
+      stg_buf ^= 1u;
+    }
+  } else {
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N; c += 32) {
+      uint32_t v[32];
+      ptx::tmem_ld_32x32(taddr + static_cast<uint32_t>(c), v);
+      ptx::tmem_ld_wait();
+      if (c + 32 >= BLOCK_N) {
+        ptx::tc_fence_before();
+        release();
+      }
+      if (valid) {
+        float f[32];
+        epilogue_math<EPI>(p, n0 + c, v, f);
+        epilogue_store_direct<EPI>(p, row, n0 + c, f);
+      }
+    }
+  }
+}
+
 template <int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
@@ -321,7 +416,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     // ===================== epilogue warps (2..5) =====================
     const int quarter = warp_idx & 3;  // TMEM lane quarter this warp may access
     const uint32_t stg = staging_base + static_cast<uint32_t>(quarter) * kStagingBytesPerWarp;
-    const uint32_t my_row_off = static_cast<uint32_t>(lane) * 128u;
     uint32_t stg_buf = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -329,95 +423,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const int m_blk = static_cast<int>(tile / p.num_n_blocks);
       const int n_blk = static_cast<int>(tile - static_cast<int64_t>(m_blk) * p.num_n_blocks);
       const int row0 = m_blk * kBlockM + quarter * 32;  // first row of this warp's slab
-      const int64_t row = static_cast<int64_t>(row0) + lane;
-      const bool valid = row < p.M;
       const int n0 = n_blk * BLOCK_N;
       ptx::mbar_wait(tmem_full_bar(acc), acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr =
           tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
 
-      if constexpr (ET::kStagedBf16) {
-        // 64 output columns (= 128 B of bf16) per staged chunk
-#pragma unroll 1
-        for (int c = 0; c < BLOCK_N; c += 64) {
-          uint32_t v0[32], v1[32];
-          ptx::tmem_ld_32x32(taddr + static_cast<uint32_t>(c), v0);
-          ptx::tmem_ld_32x32(taddr + static_cast<uint32_t>(c + 32), v1);
-          ptx::tmem_ld_wait();
-          if (c + 64 >= BLOCK_N) {  // accumulator fully read: hand the TMEM buffer back early
-            ptx::tc_fence_before();
-            ptx::mbar_arrive(tmem_empty_bar(acc));
-          }
-          float f0[32], f1[32];
-          epilogue_math<EPI>(p, n0 + c, v0, f0);
-          epilogue_math<EPI>(p, n0 + c + 32, v1, f1);
-          if (lane == 0) ptx::tma_store_wait_read<1>();  // buffer `stg_buf` no longer being read
-          __syncwarp();
-          const uint32_t buf = stg + stg_buf * (32u * 128u) + my_row_off;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {  // 16-byte chunk j / j+4 of this row, XOR-swizzled
-            st_shared_v4(buf + (static_cast<uint32_t>(j ^ (lane & 7)) << 4),
-                         pack_bf16x2(f0[8 * j + 0], f0[8 * j + 1]), pack_bf16x2(f0[8 * j + 2], f0[8 * j + 3]),
-                         pack_bf16x2(f0[8 * j + 4], f0[8 * j + 5]), pack_bf16x2(f0[8 * j + 6], f0[8 * j + 7]));
-            st_shared_v4(buf + (static_cast<uint32_t>((j + 4) ^ (lane & 7)) << 4),
-                         pack_bf16x2(f1[8 * j + 0], f1[8 * j + 1]), pack_bf16x2(f1[8 * j + 2], f1[8 * j + 3]),
-                         pack_bf16x2(f1[8 * j + 4], f1[8 * j + 5]), pack_bf16x2(f1[8 * j + 6], f1[8 * j + 7]));
-          }
-          ptx::fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            ptx::tma_store_2d(&tmap_out, stg + stg_buf * (32u * 128u), n0 + c, row0);
-            ptx::tma_store_commit();
-          }
-          stg_buf ^= 1u;
-        }
-      } else if constexpr (ET::kStagedF32) {
-        // 32 output columns (= 128 B of fp32) per staged chunk, TMA reduce-add into X
-#pragma unroll 1
-        for (int c = 0; c < BLOCK_N; c += 32) {
-          uint32_t v[32];
-          ptx::tmem_ld_32x32(taddr + static_cast<uint32_t>(c), v);
-          ptx::tmem_ld_wait();
-          if (c + 32 >= BLOCK_N) {
-            ptx::tc_fence_before();
-            ptx::mbar_arrive(tmem_empty_bar(acc));
-          }
-          float f[32];
-          epilogue_math<EPI>(p, n0 + c, v, f);
-          if (lane == 0) ptx::tma_store_wait_read<1>();
-          __syncwarp();
-          const uint32_t buf = stg + stg_buf * (32u * 128u) + my_row_off;
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            st_shared_v4(buf + (static_cast<uint32_t>(j ^ (lane & 7)) << 4), __float_as_uint(f[4 * j + 0]),
-                         __float_as_uint(f[4 * j + 1]), __float_as_uint(f[4 * j + 2]),
-                         __float_as_uint(f[4 * j + 3]));
-          ptx::fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            ptx::tma_reduce_add_2d(&tmap_out, stg + stg_buf * (32u * 128u), n0 + c, row0);
-            ptx::tma_store_commit();
-          }
-          stg_buf ^= 1u;
-        }
-      } else {
-#pragma unroll 1
-        for (int c = 0; c < BLOCK_N; c += 32) {
-          uint32_t v[32];
-          ptx::tmem_ld_32x32(taddr + static_cast<uint32_t>(c), v);
-          ptx::tmem_ld_wait();
-          if (c + 32 >= BLOCK_N) {
-            ptx::tc_fence_before();
-            ptx::mbar_arrive(tmem_empty_bar(acc));
-          }
-          if (valid) {
-            float f[32];
-            epilogue_math<EPI>(p, n0 + c, v, f);
-            epilogue_store_direct<EPI>(p, row, n0 + c, f);
-          }
-        }
-      }
+      epilogue_tile<BLOCK_N, EPI>(p, &tmap_out, taddr, row0, lane, n0, stg, stg_buf,
+                                  [&]() { ptx::mbar_arrive(tmem_empty_bar(acc)); });
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1u;
@@ -433,6 +446,193 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   if (warp_idx == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<C::kTmemCols>(tmem_base);
+  }
+}
+
+// ===========================================================================================
+// CTA-pair variant (cta_group::2): a cluster of two CTAs (one SM pair) computes a 256 x 256 tile.
+// Each CTA loads its own 128 A rows and HALF of the W tile (128 of the 256 N rows) per k-block
+// (32 KB / stage instead of 48 KB -> a 6-stage ring, one third less L2->SM operand traffic);
+// the leader CTA's single MMA thread issues tcgen05.mma.cta_group::2 (UMMA 256 x 256 x 16), which
+// reads A from each CTA's shared memory, the two W halves from both, and accumulates rows
+// [0,128) in the leader's TMEM and rows [128,256) in the peer's.  tcgen05.commit multicasts
+// the "slot free" / "accumulator full" arrivals to both CTAs; each CTA runs its own epilogue.
+// ===========================================================================================
+constexpr int kPairBlockN = 256;
+struct PairCfg {
+  static constexpr int kStages = 6;
+  static constexpr uint32_t kABytes = kBlockM * kBlockK * 2;          // 16 KB (this CTA's 128 rows)
+  static constexpr uint32_t kBBytes = (kPairBlockN / 2) * kBlockK * 2;  // 16 KB (this CTA's N half)
+  static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  static constexpr uint32_t kTmemCols = 2 * kPairBlockN;
+  static constexpr uint32_t kStagingBytes = 4 * kStagingBytesPerWarp;
+  static constexpr uint32_t kBarrierBytes = (2 * kStages + 4) * 8 + 8;
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kStagingBytes + kBarrierBytes + 1024;
+};
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
+gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                         const __grid_constant__ CUtensorMap tmap_b,
+                         const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
+  using C = PairCfg;
+  using ET = EpiTraits<EPI>;
+  constexpr int kStages = C::kStages;
+  constexpr int BLOCK_N = kPairBlockN;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t staging_base = smem_base + kStages * C::kStageBytes;
+  const uint32_t bar_base = staging_base + C::kStagingBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };          // used in the leader CTA only
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
+  auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };  // leader only
+  const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * kStages + 4);
+  uint32_t* tmem_ptr_generic =
+      reinterpret_cast<uint32_t*>(smem_raw + (tmem_ptr_smem - ptx::smem_u32(smem_raw)));
+
+  const int warp_idx = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = ptx::cluster_ctarank();
+  const bool is_leader = cta_rank == 0;
+
+  if (warp_idx == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_a);
+    ptx::prefetch_tmap(&tmap_b);
+    if constexpr (ET::kStaged) ptx::prefetch_tmap(&tmap_out);
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) {
+      ptx::mbar_init(full_bar(s), 1);   // leader's producer arms it with both CTAs' bytes
+      ptx::mbar_init(empty_bar(s), 1);  // one multicast tcgen05.commit arrival
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(tmem_full_bar(a), 1);
+      ptx::mbar_init(tmem_empty_bar(a), 2 * kNumEpilogueThreads);  // epilogue threads of BOTH CTAs
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp_idx == 1) {
+    ptx::tmem_alloc_pair<C::kTmemCols>(tmem_ptr_smem);
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync();  // barriers of both CTAs initialised before any remote arrive / TMA signal
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_generic;
+
+  const int kseg_blocks = p.K / kBlockK;
+  const int num_k_blocks = p.split3 ? 3 * kseg_blocks : kseg_blocks;
+  const int64_t num_tiles = static_cast<int64_t>(p.num_m_blocks) * p.num_n_blocks;  // pair tiles
+  const int64_t pair_idx = blockIdx.x >> 1;
+  const int64_t pair_stride = gridDim.x >> 1;
+
+  if (warp_idx == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t tile = pair_idx; tile < num_tiles; tile += pair_stride) {
+        const int m_blk = static_cast<int>(tile / p.num_n_blocks);
+        const int n_blk = static_cast<int>(tile - static_cast<int64_t>(m_blk) * p.num_n_blocks);
+        const int a_row = m_blk * (2 * kBlockM) + static_cast<int>(cta_rank) * kBlockM;
+        const int b_row = n_blk * BLOCK_N + static_cast<int>(cta_rank) * (BLOCK_N / 2);
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          int a_k, b_k;
+          if (p.split3) {
+            const int seg = kb / kseg_blocks;
+            const int r = kb - seg * kseg_blocks;
+            a_k = (seg == 2 ? p.K : 0) + r * kBlockK;
+            b_k = (seg == 1 ? p.K : 0) + r * kBlockK;
+          } else {
+            a_k = b_k = kb * kBlockK;
+          }
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_base + stage * C::kStageBytes;
+          const uint32_t sb = sa + C::kABytes;
+          const uint32_t leader_full = ptx::mapa(full_bar(stage), 0);
+          if (is_leader) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * C::kStageBytes);
+          ptx::tma_load_2d_pair(sa, &tmap_a, leader_full, a_k, a_row);
+          ptx::tma_load_2d_pair(sb, &tmap_b, leader_full, b_k, b_row);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (is_leader && lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(2 * kBlockM, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int64_t tile = pair_idx; tile < num_tiles; tile += pair_stride) {
+        ptx::mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          ptx::mbar_wait(full_bar(stage), phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = smem_base + stage * C::kStageBytes;
+          const uint32_t sb = sa + C::kABytes;
+          const uint64_t desc_a = ptx::make_smem_desc_sw128(sa);
+          const uint64_t desc_b = ptx::make_smem_desc_sw128(sb);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            ptx::umma_bf16_pair(tmem_d, desc_a + static_cast<uint64_t>(2 * k),
+                                desc_b + static_cast<uint64_t>(2 * k), idesc,
+                                (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          ptx::umma_commit_pair(empty_bar(stage), 0b11);  // frees the slot in both CTAs
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        ptx::umma_commit_pair(tmem_full_bar(acc), 0b11);  // accumulator halves ready in both CTAs
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..5, both CTAs) =====================
+    const int quarter = warp_idx & 3;
+    const uint32_t stg = staging_base + static_cast<uint32_t>(quarter) * kStagingBytesPerWarp;
+    uint32_t stg_buf = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int64_t tile = pair_idx; tile < num_tiles; tile += pair_stride) {
+      const int m_blk = static_cast<int>(tile / p.num_n_blocks);
+      const int n_blk = static_cast<int>(tile - static_cast<int64_t>(m_blk) * p.num_n_blocks);
+      const int row0 = m_blk * (2 * kBlockM) + static_cast<int>(cta_rank) * kBlockM + quarter * 32;
+      const int n0 = n_blk * BLOCK_N;
+      ptx::mbar_wait(tmem_full_bar(acc), acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t taddr =
+          tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
+      const uint32_t leader_empty = ptx::mapa(tmem_empty_bar(acc), 0);
+      epilogue_tile<BLOCK_N, EPI>(p, &tmap_out, taddr, row0, lane, n0, stg, stg_buf,
+                                  [&]() { ptx::mbar_arrive_cluster(leader_empty); });
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
+    }
+    if constexpr (ET::kStaged) {
+      if (lane == 0) ptx::tma_store_wait<0>();
+    }
+  }
+
+  ptx::tc_fence_before();
+  ptx::cluster_sync();  // peer may still be reading our smem / signalling our barriers
+  if (warp_idx == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_pair<C::kTmemCols>(tmem_base);
   }
 }
 
@@ -514,6 +714,50 @@ int dispatch_epi(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap
   }
 }
 
+template <int EPI>
+int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const GemmParams& p,
+                cudaStream_t st) {
+  using C = PairCfg;
+  static bool configured = false;
+  auto kfn = gemm_tcgen05_pair_kernel<EPI>;
+  if (!configured) {
+    DUO_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(C::kSmemBytes)));
+    configured = true;
+  }
+  const int64_t tiles = static_cast<int64_t>(p.num_m_blocks) * p.num_n_blocks;
+  const int pairs_max = device_sm_count() / 2;
+  const int pairs = static_cast<int>(tiles < pairs_max ? tiles : pairs_max);
+  kfn<<<2 * pairs, kNumThreads, C::kSmemBytes, st>>>(ta, tb, to, p);
+  DUO_LAUNCH_CHECK("gemm_tcgen05_pair_kernel");
+  return DUO_OK;
+}
+
+int dispatch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
+                  const GemmParams& p, int epi, cudaStream_t st) {
+  switch (epi) {
+    case DUO_EPI_BF16: return launch_pair<DUO_EPI_BF16>(ta, tb, to, p, st);
+    case DUO_EPI_GELU_BF16: return launch_pair<DUO_EPI_GELU_BF16>(ta, tb, to, p, st);
+    case DUO_EPI_RESIDUAL_F32: return launch_pair<DUO_EPI_RESIDUAL_F32>(ta, tb, to, p, st);
+    case kEpiResidualTma: return launch_pair<kEpiResidualTma>(ta, tb, to, p, st);
+    case DUO_EPI_SCATTER_F32: return launch_pair<DUO_EPI_SCATTER_F32>(ta, tb, to, p, st);
+    case DUO_EPI_F32: return launch_pair<DUO_EPI_F32>(ta, tb, to, p, st);
+    case DUO_EPI_SPLIT_BF16: return launch_pair<DUO_EPI_SPLIT_BF16>(ta, tb, to, p, st);
+    case DUO_EPI_GELU_SPLIT_BF16: return launch_pair<DUO_EPI_GELU_SPLIT_BF16>(ta, tb, to, p, st);
+    default: set_error("duo_gemm: unknown epilogue %d", epi); return DUO_ERR_INVALID;
+  }
+}
+
+// DUO_GEMM_PAIR=0 disables the CTA-pair (cta_group::2) kernel.
+bool pair_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DUO_GEMM_PAIR");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 // DUO_GEMM_RESIDUAL=direct selects the load/add/store residual epilogue instead of TMA reduce-add.
 bool residual_via_tma() {
   static int v = -1;
@@ -550,10 +794,17 @@ extern "C" int duo_gemm(const duo_gemm_args* a, duo_stream_t stream) {
   }
   DUO_CHECK_ARG(a->M < (int64_t(1) << 31) - 256, "duo_gemm: M too large for a 32-bit TMA coordinate");
 
-  // BLOCK_N: 256 when it divides N and there are enough tiles to fill the machine, else 128.
-  const int64_t m_blocks = (a->M + kBlockM - 1) / kBlockM;
+  // Tile shape: CTA-pair 256x256 when N allows and there are at least two waves of pair tiles;
+  // else 128 x 256 (enough tiles to fill the machine) or 128 x 128.
+  int64_t m_blocks = (a->M + kBlockM - 1) / kBlockM;
   int block_n = 128;
   if (a->N % 256 == 0 && m_blocks * (a->N / 256) >= 2 * device_sm_count()) block_n = 256;
+  const int64_t m2_blocks = (a->M + 2 * kBlockM - 1) / (2 * kBlockM);
+  const bool use_pair = pair_enabled() && a->N % 256 == 0 && m2_blocks * (a->N / 256) >= device_sm_count();
+  if (use_pair) {
+    block_n = 128;  // W box rows: each CTA loads half of the 256-wide tile
+    m_blocks = m2_blocks;
+  }
 
   CUtensorMap ta, tb, to;
   int rc = make_tmap(&ta, a->A, a->M, kcols, a->lda, kBlockM, 2);
@@ -586,8 +837,9 @@ extern "C" int duo_gemm(const duo_gemm_args* a, duo_stream_t stream) {
   p.dest_rows_per_group = a->dest_rows_per_group;
   p.pos_period = a->pos_period;
   p.num_m_blocks = static_cast<int32_t>(m_blocks);
-  p.num_n_blocks = a->N / block_n;
+  p.num_n_blocks = use_pair ? a->N / kPairBlockN : a->N / block_n;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (use_pair) return dispatch_pair(ta, tb, to, p, epi, st);
   if (block_n == 256) return dispatch_epi<256>(ta, tb, to, p, epi, st);
   return dispatch_epi<128>(ta, tb, to, p, epi, st);
 }

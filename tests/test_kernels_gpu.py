@@ -23,7 +23,8 @@ def _gen(shape, seed, scale=1.0, device="cuda"):
 
 @pytest.mark.parametrize(
     "M,N,K",
-    [(128, 256, 64), (128, 128, 64), (256, 768, 768), (294 * 2, 2304, 768), (1000, 768, 3072), (128 * 300, 768, 256), (98, 768, 2048)],
+    [(128, 256, 64), (128, 128, 64), (256, 768, 768), (294 * 2, 2304, 768), (1000, 768, 3072), (128 * 300, 768, 256),
+     (98, 768, 2048), (256 * 75 + 77, 2304, 768), (256 * 160 + 129, 768, 3072)],
 )
 def test_gemm_bf16_epilogues(M, N, K):
     A = _gen((M, K), 1).to(torch.bfloat16)
@@ -53,8 +54,9 @@ def test_gemm_bf16_epilogues(M, N, K):
     assert relerr(X2, X2r) < 1e-4
 
 
-def test_gemm_split3_fp32_accuracy():
-    M, N, K = 300, 768, 768
+@pytest.mark.parametrize("M", [300, 256 * 150 + 5])
+def test_gemm_split3_fp32_accuracy(M):
+    N, K = 768, 768
     A = _gen((M, K), 11)
     W = _gen((N, K), 12, 0.05)
     bias = _gen((N,), 13)
@@ -75,9 +77,10 @@ def test_gemm_split3_fp32_accuracy():
     assert relerr(rec, torch.nn.functional.gelu(ref)) < 3e-5
 
 
-def test_gemm_scatter_tokens():
-    # 2 images, stage with 8 source rows per image scattered into 5*4 token rows per image
-    B, hw, P, S, N, K = 3, 196, 49, 6, 768, 1024
+@pytest.mark.parametrize("B", [3, 200])
+def test_gemm_scatter_tokens(B):
+    # stage-2-like map: 196 source rows per image scattered into the 49*6 token rows per image
+    hw, P, S, N, K = 196, 49, 6, 768, 1024
     A = _gen((B * hw, K), 21).to(torch.bfloat16)
     W = _gen((N, K), 22, 0.05).to(torch.bfloat16)
     bias = _gen((N,), 23)
