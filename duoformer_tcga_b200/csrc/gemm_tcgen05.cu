@@ -194,12 +194,14 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
                : "memory");
 }
 
-// One accumulator tile (this warp's 32 rows x BLOCK_N columns): TMEM -> registers -> fused math ->
-// global memory.  `release()` is called as soon as the accumulator has been read completely.
-template <int BLOCK_N, int EPI, typename ReleaseFn>
+// One accumulator slab (this warp's 32 rows x columns [c_begin, c_end) of the tile): TMEM ->
+// registers -> fused math -> global memory.  `release()` is called as soon as this warp has read
+// its part of the accumulator completely.
+template <int EPI, int NBUF, typename ReleaseFn>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtensorMap* tmap_out,
-                                              uint32_t taddr, int row0, int lane, int n0, uint32_t stg,
-                                              uint32_t& stg_buf, ReleaseFn release) {
+                                              uint32_t taddr, int row0, int lane, int n0, int c_begin,
+                                              int c_end, uint32_t stg, uint32_t& stg_buf,
+                                              ReleaseFn release) {
   using ET = EpiTraits<EPI>;
   const int64_t row = static_cast<int64_t>(row0) + lane;
   const bool valid = row < p.M;
@@ -207,31 +209,30 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
   (void)valid;
   (void)my_row_off;
   if constexpr (ET::kStagedBf16) {
-    // 64 output columns (= 128 B of bf16) per staged chunk
+    // 64 output columns (= 128 B of bf16) per staged chunk, filled 32 columns at a time
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N; c += 64) {
-      uint32_t v0[32], v1[32];
-      ptx::tmem_ld_32x32(taddr + static_cast<uint32_t>(c), v0);
-      ptx::tmem_ld_32x32(taddr + static_cast<uint32_t>(c + 32), v1);
-      ptx::tmem_ld_wait();
-      if (c + 64 >= BLOCK_N) {  // accumulator fully read: hand the TMEM buffer back early
-        ptx::tc_fence_before();
-        release();
-      }
-      float f0[32], f1[32];
-      epilogue_math<EPI>(p, n0 + c, v0, f0);
-      epilogue_math<EPI>(p, n0 + c + 32, v1, f1);
-      if (lane == 0) ptx::tma_store_wait_read<1>();  // buffer `stg_buf` no longer being read
-      __syncwarp();
+    for (int c = c_begin; c < c_end; c += 64) {
       const uint32_t buf = stg + stg_buf * (32u * 128u) + my_row_off;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {  // 16-byte chunk j / j+4 of this row, XOR-swizzled
-        st_shared_v4(buf + (static_cast<uint32_t>(j ^ (lane & 7)) << 4),
-                     pack_bf16x2(f0[8 * j + 0], f0[8 * j + 1]), pack_bf16x2(f0[8 * j + 2], f0[8 * j + 3]),
-                     pack_bf16x2(f0[8 * j + 4], f0[8 * j + 5]), pack_bf16x2(f0[8 * j + 6], f0[8 * j + 7]));
-        st_shared_v4(buf + (static_cast<uint32_t>((j + 4) ^ (lane & 7)) << 4),
-                     pack_bf16x2(f1[8 * j + 0], f1[8 * j + 1]), pack_bf16x2(f1[8 * j + 2], f1[8 * j + 3]),
-                     pack_bf16x2(f1[8 * j + 4], f1[8 * j + 5]), pack_bf16x2(f1[8 * j + 6], f1[8 * j + 7]));
+      for (int h = 0; h < 2; ++h) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(taddr + static_cast<uint32_t>(c + 32 * h), v);
+        ptx::tmem_ld_wait();
+        if (h == 1 && c + 64 >= c_end) {  // accumulator fully read: hand the TMEM buffer back early
+          ptx::tc_fence_before();
+          release();
+        }
+        float f[32];
+        epilogue_math<EPI>(p, n0 + c + 32 * h, v, f);
+        if (h == 0) {
+          if (lane == 0) ptx::tma_store_wait_read<NBUF - 1>();  // buffer `stg_buf` no longer being read
+          __syncwarp();
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)  // 16-byte chunk (4h + j) of this row, XOR-swizzled
+          st_shared_v4(buf + (static_cast<uint32_t>((4 * h + j) ^ (lane & 7)) << 4),
+                       pack_bf16x2(f[8 * j + 0], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                       pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
       }
       ptx::fence_proxy_async();
       __syncwarp();
@@ -239,22 +240,22 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
         ptx::tma_store_2d(tmap_out, stg + stg_buf * (32u * 128u), n0 + c, row0);
         ptx::tma_store_commit();
       }
-      stg_buf ^= 1u;
+      stg_buf = (NBUF == 1) ? 0u : (stg_buf ^ 1u);
     }
   } else if constexpr (ET::kStagedF32) {
     // 32 output columns (= 128 B of fp32) per staged chunk, TMA reduce-add into X
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N; c += 32) {
+    for (int c = c_begin; c < c_end; c += 32) {
       uint32_t v[32];
       ptx::tmem_ld_32x32(taddr + static_cast<uint32_t>(c), v);
       ptx::tmem_ld_wait();
-      if (c + 32 >= BLOCK_N) {
+      if (c + 32 >= c_end) {
         ptx::tc_fence_before();
         release();
       }
       float f[32];
       epilogue_math<EPI>(p, n0 + c, v, f);
-      if (lane == 0) ptx::tma_store_wait_read<1>();
+      if (lane == 0) ptx::tma_store_wait_read<NBUF - 1>();
       __syncwarp();
       const uint32_t buf = stg + stg_buf * (32u * 128u) + my_row_off;
 #pragma unroll
@@ -268,15 +269,15 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
         ptx::tma_reduce_add_2d(tmap_out, stg + stg_buf * (32u * 128u), n0 + c, row0);
         ptx::tma_store_commit();
       }
-      stg_buf ^= 1u;
+      stg_buf = (NBUF == 1) ? 0u : (stg_buf ^ 1u);
     }
   } else {
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N; c += 32) {
+    for (int c = c_begin; c < c_end; c += 32) {
       uint32_t v[32];
       ptx::tmem_ld_32x32(taddr + static_cast<uint32_t>(c), v);
       ptx::tmem_ld_wait();
-      if (c + 32 >= BLOCK_N) {
+      if (c + 32 >= c_end) {
         ptx::tc_fence_before();
         release();
       }
@@ -429,8 +430,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const uint32_t taddr =
           tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
 
-      epilogue_tile<BLOCK_N, EPI>(p, &tmap_out, taddr, row0, lane, n0, stg, stg_buf,
-                                  [&]() { ptx::mbar_arrive(tmem_empty_bar(acc)); });
+      epilogue_tile<EPI, 2>(p, &tmap_out, taddr, row0, lane, n0, 0, BLOCK_N, stg, stg_buf,
+                         [&]() { ptx::mbar_arrive(tmem_empty_bar(acc)); });
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1u;
@@ -459,23 +460,29 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 // the "slot free" / "accumulator full" arrivals to both CTAs; each CTA runs its own epilogue.
 // ===========================================================================================
 constexpr int kPairBlockN = 256;
+// EPI_WARPS epilogue warps: 4 (one per TMEM lane quarter, all 256 columns, double-buffered
+// staging) or 8 (two per quarter, 128 columns each, single-buffered staging — used when the
+// epilogue math is heavy, i.e. GELU).
+template <int EPI_WARPS>
 struct PairCfg {
   static constexpr int kStages = 6;
+  static constexpr int kThreads = 64 + 32 * EPI_WARPS;
+  static constexpr int kStagingBufs = 8 / EPI_WARPS;
   static constexpr uint32_t kABytes = kBlockM * kBlockK * 2;          // 16 KB (this CTA's 128 rows)
   static constexpr uint32_t kBBytes = (kPairBlockN / 2) * kBlockK * 2;  // 16 KB (this CTA's N half)
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
   static constexpr uint32_t kTmemCols = 2 * kPairBlockN;
-  static constexpr uint32_t kStagingBytes = 4 * kStagingBytesPerWarp;
+  static constexpr uint32_t kStagingBytes = 8 * 32 * 128;  // 32 KB: EPI_WARPS x kStagingBufs x 4 KB
   static constexpr uint32_t kBarrierBytes = (2 * kStages + 4) * 8 + 8;
   static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kStagingBytes + kBarrierBytes + 1024;
 };
 
-template <int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
+template <int EPI, int EPI_WARPS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg<EPI_WARPS>::kThreads, 1)
 gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
                          const __grid_constant__ CUtensorMap tmap_b,
                          const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
-  using C = PairCfg;
+  using C = PairCfg<EPI_WARPS>;
   using ET = EpiTraits<EPI>;
   constexpr int kStages = C::kStages;
   constexpr int BLOCK_N = kPairBlockN;
@@ -509,7 +516,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(tmem_full_bar(a), 1);
-      ptx::mbar_init(tmem_empty_bar(a), 2 * kNumEpilogueThreads);  // epilogue threads of BOTH CTAs
+      ptx::mbar_init(tmem_empty_bar(a), 2 * 32 * EPI_WARPS);  // epilogue threads of BOTH CTAs
     }
     ptx::fence_barrier_init();
   }
@@ -600,9 +607,11 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
       }
     }
   } else {
-    // ===================== epilogue warps (2..5, both CTAs) =====================
-    const int quarter = warp_idx & 3;
-    const uint32_t stg = staging_base + static_cast<uint32_t>(quarter) * kStagingBytesPerWarp;
+    // ===================== epilogue warps (2..9, both CTAs) =====================
+    const int quarter = warp_idx & 3;             // TMEM lane quarter (rows) of this warp
+    const int col_part = (warp_idx - 2) >> 2;     // which slice of the 256 columns (EPI_WARPS == 8)
+    constexpr int kColsPerWarp = BLOCK_N / (EPI_WARPS / 4);
+    const uint32_t stg = staging_base + static_cast<uint32_t>(warp_idx - 2) * (C::kStagingBufs * 32u * 128u);
     uint32_t stg_buf = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -616,8 +625,9 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const uint32_t taddr =
           tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
       const uint32_t leader_empty = ptx::mapa(tmem_empty_bar(acc), 0);
-      epilogue_tile<BLOCK_N, EPI>(p, &tmap_out, taddr, row0, lane, n0, stg, stg_buf,
-                                  [&]() { ptx::mbar_arrive_cluster(leader_empty); });
+      epilogue_tile<EPI, C::kStagingBufs>(p, &tmap_out, taddr, row0, lane, n0, col_part * kColsPerWarp,
+                                          (col_part + 1) * kColsPerWarp, stg, stg_buf,
+                         [&]() { ptx::mbar_arrive_cluster(leader_empty); });
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1u;
@@ -714,12 +724,12 @@ int dispatch_epi(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap
   }
 }
 
-template <int EPI>
+template <int EPI, int EPI_WARPS>
 int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const GemmParams& p,
                 cudaStream_t st) {
-  using C = PairCfg;
+  using C = PairCfg<EPI_WARPS>;
   static bool configured = false;
-  auto kfn = gemm_tcgen05_pair_kernel<EPI>;
+  auto kfn = gemm_tcgen05_pair_kernel<EPI, EPI_WARPS>;
   if (!configured) {
     DUO_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(C::kSmemBytes)));
@@ -728,7 +738,7 @@ int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
   const int64_t tiles = static_cast<int64_t>(p.num_m_blocks) * p.num_n_blocks;
   const int pairs_max = device_sm_count() / 2;
   const int pairs = static_cast<int>(tiles < pairs_max ? tiles : pairs_max);
-  kfn<<<2 * pairs, kNumThreads, C::kSmemBytes, st>>>(ta, tb, to, p);
+  kfn<<<2 * pairs, C::kThreads, C::kSmemBytes, st>>>(ta, tb, to, p);
   DUO_LAUNCH_CHECK("gemm_tcgen05_pair_kernel");
   return DUO_OK;
 }
@@ -736,14 +746,14 @@ int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
 int dispatch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
                   const GemmParams& p, int epi, cudaStream_t st) {
   switch (epi) {
-    case DUO_EPI_BF16: return launch_pair<DUO_EPI_BF16>(ta, tb, to, p, st);
-    case DUO_EPI_GELU_BF16: return launch_pair<DUO_EPI_GELU_BF16>(ta, tb, to, p, st);
-    case DUO_EPI_RESIDUAL_F32: return launch_pair<DUO_EPI_RESIDUAL_F32>(ta, tb, to, p, st);
-    case kEpiResidualTma: return launch_pair<kEpiResidualTma>(ta, tb, to, p, st);
-    case DUO_EPI_SCATTER_F32: return launch_pair<DUO_EPI_SCATTER_F32>(ta, tb, to, p, st);
-    case DUO_EPI_F32: return launch_pair<DUO_EPI_F32>(ta, tb, to, p, st);
-    case DUO_EPI_SPLIT_BF16: return launch_pair<DUO_EPI_SPLIT_BF16>(ta, tb, to, p, st);
-    case DUO_EPI_GELU_SPLIT_BF16: return launch_pair<DUO_EPI_GELU_SPLIT_BF16>(ta, tb, to, p, st);
+    case DUO_EPI_BF16: return launch_pair<DUO_EPI_BF16, 4>(ta, tb, to, p, st);
+    case DUO_EPI_GELU_BF16: return launch_pair<DUO_EPI_GELU_BF16, 8>(ta, tb, to, p, st);
+    case DUO_EPI_RESIDUAL_F32: return launch_pair<DUO_EPI_RESIDUAL_F32, 4>(ta, tb, to, p, st);
+    case kEpiResidualTma: return launch_pair<kEpiResidualTma, 4>(ta, tb, to, p, st);
+    case DUO_EPI_SCATTER_F32: return launch_pair<DUO_EPI_SCATTER_F32, 4>(ta, tb, to, p, st);
+    case DUO_EPI_F32: return launch_pair<DUO_EPI_F32, 4>(ta, tb, to, p, st);
+    case DUO_EPI_SPLIT_BF16: return launch_pair<DUO_EPI_SPLIT_BF16, 4>(ta, tb, to, p, st);
+    case DUO_EPI_GELU_SPLIT_BF16: return launch_pair<DUO_EPI_GELU_SPLIT_BF16, 8>(ta, tb, to, p, st);
     default: set_error("duo_gemm: unknown epilogue %d", epi); return DUO_ERR_INVALID;
   }
 }

@@ -71,7 +71,7 @@ def main():
               ("fc1_gelu", 4 * D, D, ops.EPI_GELU_BF16), ("fc1_nogelu", 4 * D, D, ops.EPI_BF16),
               ("fc2_residual", D, 4 * D, ops.EPI_RESIDUAL_F32)]
     for name, N, K, epi in shapes:
-        if a.only and "gemm" not in a.only and name not in a.only:
+        if a.only and "gemm" not in a.only and not any(tok in name for tok in a.only.split(",")):
             continue
         A = (torch.randn(M, K, device=dev) * 0.5).to(torch.bfloat16)
         W = (torch.randn(N, K, device=dev) * 0.02).to(torch.bfloat16)
