@@ -93,9 +93,9 @@ def load() -> ctypes.CDLL:
     lib.duo_gemm.restype = c_int32
     lib.duo_gemm.argtypes = [POINTER(GemmArgs), c_void_p]
     lib.duo_layernorm.restype = c_int32
-    lib.duo_layernorm.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int32, c_float, c_void_p]
+    lib.duo_layernorm.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int32, c_int64, c_float, c_void_p]
     lib.duo_group_attention.restype = c_int32
-    lib.duo_group_attention.argtypes = [c_void_p, c_int32, c_void_p, c_int32, c_int64, c_int32, c_int32, c_float, c_int32, c_void_p]
+    lib.duo_group_attention.argtypes = [c_void_p, c_int32, c_void_p, c_int32, c_int64, c_int32, c_int32, c_float, c_int32, c_int32, c_void_p]
     lib.duo_fill_scale_token.restype = c_int32
     lib.duo_fill_scale_token.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]
     lib.duo_add_pos.restype = c_int32

@@ -75,21 +75,27 @@ struct GemmParams {
 };
 
 // acc[32] (fp32 bits) -> f[32] = acc + bias (optionally GELU'd / scaled by LayerScale gamma)
-template <int EPI>
-__device__ __forceinline__ void epilogue_math(const GemmParams& p, int col, const uint32_t (&v)[32],
-                                              float (&f)[32]) {
-#pragma unroll
-  for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+// Bias slice [col, col+32) -> registers; issued BEFORE waiting on the TMEM load so both latencies overlap.
+__device__ __forceinline__ void epilogue_bias_load(const GemmParams& p, int col, float4 (&b)[8]) {
   if (p.bias != nullptr) {
     const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float4 b = __ldg(b4 + j);
-      f[4 * j + 0] += b.x;
-      f[4 * j + 1] += b.y;
-      f[4 * j + 2] += b.z;
-      f[4 * j + 3] += b.w;
-    }
+    for (int j = 0; j < 8; ++j) b[j] = __ldg(b4 + j);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) b[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_math(const GemmParams& p, int col, const uint32_t (&v)[32],
+                                              const float4 (&b)[8], float (&f)[32]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b[j].x;
+    f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b[j].y;
+    f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b[j].z;
+    f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b[j].w;
   }
   if constexpr (EPI == DUO_EPI_GELU_BF16) {
 #pragma unroll
@@ -216,14 +222,16 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         uint32_t v[32];
+        float4 bia[8];
         ptx::tmem_ld_32x32(taddr + static_cast<uint32_t>(c + 32 * h), v);
+        epilogue_bias_load(p, n0 + c + 32 * h, bia);
         ptx::tmem_ld_wait();
         if (h == 1 && c + 64 >= c_end) {  // accumulator fully read: hand the TMEM buffer back early
           ptx::tc_fence_before();
           release();
         }
         float f[32];
-        epilogue_math<EPI>(p, n0 + c + 32 * h, v, f);
+        epilogue_math<EPI>(p, n0 + c + 32 * h, v, bia, f);
         if (h == 0) {
           if (lane == 0) ptx::tma_store_wait_read<NBUF - 1>();  // buffer `stg_buf` no longer being read
           __syncwarp();
@@ -247,14 +255,16 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
 #pragma unroll 1
     for (int c = c_begin; c < c_end; c += 32) {
       uint32_t v[32];
+      float4 bia[8];
       ptx::tmem_ld_32x32(taddr + static_cast<uint32_t>(c), v);
+      epilogue_bias_load(p, n0 + c, bia);
       ptx::tmem_ld_wait();
       if (c + 32 >= c_end) {
         ptx::tc_fence_before();
         release();
       }
       float f[32];
-      epilogue_math<EPI>(p, n0 + c, v, f);
+      epilogue_math<EPI>(p, n0 + c, v, bia, f);
       if (lane == 0) ptx::tma_store_wait_read<NBUF - 1>();
       __syncwarp();
       const uint32_t buf = stg + stg_buf * (32u * 128u) + my_row_off;
@@ -275,7 +285,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
 #pragma unroll 1
     for (int c = c_begin; c < c_end; c += 32) {
       uint32_t v[32];
+      float4 bia[8];
       ptx::tmem_ld_32x32(taddr + static_cast<uint32_t>(c), v);
+      epilogue_bias_load(p, n0 + c, bia);
       ptx::tmem_ld_wait();
       if (c + 32 >= c_end) {
         ptx::tc_fence_before();
@@ -283,7 +295,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
       }
       if (valid) {
         float f[32];
-        epilogue_math<EPI>(p, n0 + c, v, f);
+        epilogue_math<EPI>(p, n0 + c, v, bia, f);
         epilogue_store_direct<EPI>(p, row, n0 + c, f);
       }
     }

@@ -43,7 +43,8 @@ __host__ __device__ constexpr int fma_smem_words_per_warp(int S, int kpl) {
 
 template <typename Tin, int OUT_KIND, int KPL>
 __global__ void group_attention_fma_kernel(const Tin* __restrict__ qkv, void* __restrict__ out,
-                                           int64_t num_problems, int S, int H, float scale) {
+                                           int64_t num_problems, int S, int H, float scale,
+                                           int q_rows) {
   constexpr int WPR = ElemTraits<Tin>::kWordsPerRow;
   constexpr int VPR = WPR / 4;          // 16-byte vectors per row
   constexpr int RPP = 32 / VPR;         // rows loaded per warp pass
@@ -88,7 +89,7 @@ __global__ void group_attention_fma_kernel(const Tin* __restrict__ qkv, void* __
     krow[kk] = (j < S ? j : S - 1) * (WPR + 1);
   }
 
-  for (int i = 0; i < S; ++i) {
+  for (int i = 0; i < q_rows; ++i) {
     // q row -> shared (fp32)
     {
       const Tin* qp = base + i * ld + 2 * lane;
@@ -172,7 +173,7 @@ __global__ void group_attention_fma_kernel(const Tin* __restrict__ qkv, void* __
       }
     }
 
-    const int64_t orow = g * S + i;
+    const int64_t orow = g * q_rows + i;
     const int ocol = h * kHeadDim + 2 * lane;
     if constexpr (OUT_KIND == DUO_ACT_BF16) {
       reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(out) + orow * D + ocol)[0] =
@@ -192,7 +193,7 @@ __global__ void group_attention_fma_kernel(const Tin* __restrict__ qkv, void* __
 }
 
 template <typename Tin, int OUT_KIND, int KPL>
-int launch_fma(const void* qkv, void* out, int64_t groups, int S, int H, float scale,
+int launch_fma(const void* qkv, void* out, int64_t groups, int S, int H, float scale, int q_rows,
                cudaStream_t st) {
   const size_t per_warp = static_cast<size_t>(fma_smem_words_per_warp<Tin>(S, KPL)) * 4;
   int warps = 4;
@@ -212,21 +213,21 @@ int launch_fma(const void* qkv, void* out, int64_t groups, int S, int H, float s
     return DUO_ERR_INVALID;
   }
   kfn<<<static_cast<unsigned>(grid), warps * 32, smem, st>>>(reinterpret_cast<const Tin*>(qkv), out,
-                                                            problems, S, H, scale);
+                                                            problems, S, H, scale, q_rows);
   DUO_LAUNCH_CHECK("group_attention_fma_kernel");
   return DUO_OK;
 }
 
 template <typename Tin, int OUT_KIND>
-int dispatch_fma_kpl(const void* qkv, void* out, int64_t groups, int S, int H, float scale,
+int dispatch_fma_kpl(const void* qkv, void* out, int64_t groups, int S, int H, float scale, int q_rows,
                      cudaStream_t st) {
   const int kpl = (S + 31) / 32;
   switch (kpl) {
-    case 1: return launch_fma<Tin, OUT_KIND, 1>(qkv, out, groups, S, H, scale, st);
-    case 2: return launch_fma<Tin, OUT_KIND, 2>(qkv, out, groups, S, H, scale, st);
-    case 3: return launch_fma<Tin, OUT_KIND, 3>(qkv, out, groups, S, H, scale, st);
-    case 4: return launch_fma<Tin, OUT_KIND, 4>(qkv, out, groups, S, H, scale, st);
-    case 5: return launch_fma<Tin, OUT_KIND, 5>(qkv, out, groups, S, H, scale, st);
+    case 1: return launch_fma<Tin, OUT_KIND, 1>(qkv, out, groups, S, H, scale, q_rows, st);
+    case 2: return launch_fma<Tin, OUT_KIND, 2>(qkv, out, groups, S, H, scale, q_rows, st);
+    case 3: return launch_fma<Tin, OUT_KIND, 3>(qkv, out, groups, S, H, scale, q_rows, st);
+    case 4: return launch_fma<Tin, OUT_KIND, 4>(qkv, out, groups, S, H, scale, q_rows, st);
+    case 5: return launch_fma<Tin, OUT_KIND, 5>(qkv, out, groups, S, H, scale, q_rows, st);
     default: set_error("duo_group_attention: S=%d > 160 unsupported", S); return DUO_ERR_INVALID;
   }
 }
@@ -269,7 +270,7 @@ constexpr int kMmaWarps = 2;
 template <int S_PAD>
 __global__ void __launch_bounds__(kMmaWarps * 32)
 group_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
-                           int S, int H, float scale_log2e) {
+                           int S, int H, float scale_log2e, int q_rows) {
   constexpr int MT = S_PAD / 16;  // query m-tiles (also 16-key steps)
   constexpr int NT = S_PAD / 8;   // 8-key n-tiles
   __shared__ __align__(128) uint8_t smem[3 * S_PAD * 128];
@@ -308,7 +309,7 @@ group_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16*
 
   for (int mt = warp; mt < MT; mt += kMmaWarps) {
     const int m0 = mt * 16;
-    if (m0 >= S) break;
+    if (m0 >= q_rows) break;
     // ---- Q fragments (A operand), 4 k-steps of 16 ----
     uint32_t qa[4][4];
 #pragma unroll
@@ -387,13 +388,13 @@ group_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16*
     // ---- normalise and store (heads merged: column h*64 + d) ----
     const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
     const int r0 = m0 + gq, r1 = m0 + gq + 8;
-    __nv_bfloat16* obase = out + (g * S) * D + h * kHeadDim + 2 * tq;
+    __nv_bfloat16* obase = out + (g * q_rows) * D + h * kHeadDim + 2 * tq;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      if (r0 < S)
+      if (r0 < q_rows)
         *reinterpret_cast<uint32_t*>(obase + static_cast<int64_t>(r0) * D + nt * 8) =
             pack_bf16x2(o[nt][0] * inv0, o[nt][1] * inv0);
-      if (r1 < S)
+      if (r1 < q_rows)
         *reinterpret_cast<uint32_t*>(obase + static_cast<int64_t>(r1) * D + nt * 8) =
             pack_bf16x2(o[nt][2] * inv1, o[nt][3] * inv1);
     }
@@ -401,7 +402,7 @@ group_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16*
 }
 
 template <int S_PAD>
-int launch_mma(const void* qkv, void* out, int64_t groups, int S, int H, float scale,
+int launch_mma(const void* qkv, void* out, int64_t groups, int S, int H, float scale, int q_rows,
                cudaStream_t st) {
   const int64_t problems = groups * H;
   if (problems >= (int64_t(1) << 31)) {
@@ -410,7 +411,7 @@ int launch_mma(const void* qkv, void* out, int64_t groups, int S, int H, float s
   }
   group_attention_mma_kernel<S_PAD><<<static_cast<unsigned>(problems), kMmaWarps * 32, 0, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), S, H,
-      scale * 1.4426950408889634f);
+      scale * 1.4426950408889634f, q_rows);
   DUO_LAUNCH_CHECK("group_attention_mma_kernel");
   return DUO_OK;
 }
@@ -420,7 +421,7 @@ int launch_mma(const void* qkv, void* out, int64_t groups, int S, int H, float s
 
 extern "C" int duo_group_attention(const void* qkv, int32_t in_kind, void* out, int32_t out_kind,
                                    int64_t num_groups, int32_t S, int32_t num_heads, float scale,
-                                   int32_t algo, duo_stream_t stream) {
+                                   int32_t algo, int32_t q_rows, duo_stream_t stream) {
   using namespace duo;
   DUO_CHECK_ARG(qkv && out, "duo_group_attention: NULL pointer");
   DUO_CHECK_ARG(num_groups > 0 && S > 0 && num_heads > 0, "duo_group_attention: empty problem");
@@ -431,34 +432,35 @@ extern "C" int duo_group_attention(const void* qkv, int32_t in_kind, void* out, 
   DUO_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 &&
                     (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                 "duo_group_attention: pointers must be 16-byte aligned");
+  DUO_CHECK_ARG(q_rows >= 1 && q_rows <= S, "duo_group_attention: q_rows=%d must be in [1, S=%d]", q_rows, S);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool mma_ok = in_kind == DUO_ACT_BF16 && out_kind == DUO_ACT_BF16 && S > 16 && S <= 96;
   if (algo == 0) algo = mma_ok ? 2 : 1;
   if (algo == 2) {
     DUO_CHECK_ARG(mma_ok, "duo_group_attention: algo 2 needs bf16 in/out and 16 < S <= 96 (S=%d)", S);
-    if (S <= 32) return launch_mma<32>(qkv, out, num_groups, S, num_heads, scale, st);
-    if (S <= 48) return launch_mma<48>(qkv, out, num_groups, S, num_heads, scale, st);
-    if (S <= 64) return launch_mma<64>(qkv, out, num_groups, S, num_heads, scale, st);
-    if (S <= 80) return launch_mma<80>(qkv, out, num_groups, S, num_heads, scale, st);
-    return launch_mma<96>(qkv, out, num_groups, S, num_heads, scale, st);
+    if (S <= 32) return launch_mma<32>(qkv, out, num_groups, S, num_heads, scale, q_rows, st);
+    if (S <= 48) return launch_mma<48>(qkv, out, num_groups, S, num_heads, scale, q_rows, st);
+    if (S <= 64) return launch_mma<64>(qkv, out, num_groups, S, num_heads, scale, q_rows, st);
+    if (S <= 80) return launch_mma<80>(qkv, out, num_groups, S, num_heads, scale, q_rows, st);
+    return launch_mma<96>(qkv, out, num_groups, S, num_heads, scale, q_rows, st);
   }
   DUO_CHECK_ARG(algo == 1, "duo_group_attention: algo=%d", algo);
   if (in_kind == DUO_ACT_BF16) {
     switch (out_kind) {
       case DUO_ACT_BF16:
-        return dispatch_fma_kpl<__nv_bfloat16, DUO_ACT_BF16>(qkv, out, num_groups, S, num_heads, scale, st);
+        return dispatch_fma_kpl<__nv_bfloat16, DUO_ACT_BF16>(qkv, out, num_groups, S, num_heads, scale, q_rows, st);
       case DUO_ACT_SPLIT:
-        return dispatch_fma_kpl<__nv_bfloat16, DUO_ACT_SPLIT>(qkv, out, num_groups, S, num_heads, scale, st);
+        return dispatch_fma_kpl<__nv_bfloat16, DUO_ACT_SPLIT>(qkv, out, num_groups, S, num_heads, scale, q_rows, st);
       default:
-        return dispatch_fma_kpl<__nv_bfloat16, DUO_ACT_F32>(qkv, out, num_groups, S, num_heads, scale, st);
+        return dispatch_fma_kpl<__nv_bfloat16, DUO_ACT_F32>(qkv, out, num_groups, S, num_heads, scale, q_rows, st);
     }
   }
   switch (out_kind) {
     case DUO_ACT_BF16:
-      return dispatch_fma_kpl<float, DUO_ACT_BF16>(qkv, out, num_groups, S, num_heads, scale, st);
+      return dispatch_fma_kpl<float, DUO_ACT_BF16>(qkv, out, num_groups, S, num_heads, scale, q_rows, st);
     case DUO_ACT_SPLIT:
-      return dispatch_fma_kpl<float, DUO_ACT_SPLIT>(qkv, out, num_groups, S, num_heads, scale, st);
+      return dispatch_fma_kpl<float, DUO_ACT_SPLIT>(qkv, out, num_groups, S, num_heads, scale, q_rows, st);
     default:
-      return dispatch_fma_kpl<float, DUO_ACT_F32>(qkv, out, num_groups, S, num_heads, scale, st);
+      return dispatch_fma_kpl<float, DUO_ACT_F32>(qkv, out, num_groups, S, num_heads, scale, q_rows, st);
   }
 }

@@ -21,13 +21,14 @@ __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
 template <int NV, int OUT_KIND>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
-                 const float* __restrict__ beta, void* __restrict__ out, int64_t rows, float eps) {
+                 const float* __restrict__ beta, void* __restrict__ out, int64_t rows, int64_t ldx,
+                 float eps) {
   constexpr int D = NV * 128;
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * kWarpsPerCta + (threadIdx.x >> 5);
   if (row >= rows) return;
 
-  const float4* xr = reinterpret_cast<const float4*>(x + row * D);
+  const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
   float4 v[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) v[i] = ld_stream_f4(xr + lane + 32 * i);
@@ -73,14 +74,14 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
 
 template <int NV>
 int launch_ln(const float* x, const float* g, const float* b, void* out, int out_kind,
-              int64_t rows, float eps, cudaStream_t st) {
+              int64_t rows, int64_t ldx, float eps, cudaStream_t st) {
   const int64_t grid = (rows + kWarpsPerCta - 1) / kWarpsPerCta;
   if (out_kind == DUO_ACT_BF16)
     layernorm_kernel<NV, DUO_ACT_BF16><<<static_cast<unsigned>(grid), kWarpsPerCta * 32, 0, st>>>(
-        x, g, b, out, rows, eps);
+        x, g, b, out, rows, ldx, eps);
   else
     layernorm_kernel<NV, DUO_ACT_SPLIT><<<static_cast<unsigned>(grid), kWarpsPerCta * 32, 0, st>>>(
-        x, g, b, out, rows, eps);
+        x, g, b, out, rows, ldx, eps);
   DUO_LAUNCH_CHECK("layernorm_kernel");
   return DUO_OK;
 }
@@ -89,8 +90,8 @@ int launch_ln(const float* x, const float* g, const float* b, void* out, int out
 }  // namespace duo
 
 extern "C" int duo_layernorm(const float* x, const float* gamma, const float* beta, void* out,
-                             int32_t out_kind, int64_t rows, int32_t dim, float eps,
-                             duo_stream_t stream) {
+                             int32_t out_kind, int64_t rows, int32_t dim, int64_t ldx,
+                             float eps, duo_stream_t stream) {
   using namespace duo;
   DUO_CHECK_ARG(x && gamma && beta && out, "duo_layernorm: NULL pointer");
   DUO_CHECK_ARG(rows > 0, "duo_layernorm: rows=%lld", (long long)rows);
@@ -98,17 +99,19 @@ extern "C" int duo_layernorm(const float* x, const float* gamma, const float* be
                 "duo_layernorm: dim=%d must be a multiple of 128 in [128,1024]", dim);
   DUO_CHECK_ARG(out_kind == DUO_ACT_BF16 || out_kind == DUO_ACT_SPLIT,
                 "duo_layernorm: out_kind=%d", out_kind);
+  DUO_CHECK_ARG(ldx >= dim && ldx % 4 == 0, "duo_layernorm: ldx=%lld must be >= dim and a multiple of 4",
+                (long long)ldx);
   DUO_CHECK_ARG((rows + kWarpsPerCta - 1) / kWarpsPerCta < (int64_t(1) << 31),
                 "duo_layernorm: too many rows");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (dim / 128) {
-    case 1: return launch_ln<1>(x, gamma, beta, out, out_kind, rows, eps, st);
-    case 2: return launch_ln<2>(x, gamma, beta, out, out_kind, rows, eps, st);
-    case 3: return launch_ln<3>(x, gamma, beta, out, out_kind, rows, eps, st);
-    case 4: return launch_ln<4>(x, gamma, beta, out, out_kind, rows, eps, st);
-    case 5: return launch_ln<5>(x, gamma, beta, out, out_kind, rows, eps, st);
-    case 6: return launch_ln<6>(x, gamma, beta, out, out_kind, rows, eps, st);
-    case 7: return launch_ln<7>(x, gamma, beta, out, out_kind, rows, eps, st);
-    default: return launch_ln<8>(x, gamma, beta, out, out_kind, rows, eps, st);
+    case 1: return launch_ln<1>(x, gamma, beta, out, out_kind, rows, ldx, eps, st);
+    case 2: return launch_ln<2>(x, gamma, beta, out, out_kind, rows, ldx, eps, st);
+    case 3: return launch_ln<3>(x, gamma, beta, out, out_kind, rows, ldx, eps, st);
+    case 4: return launch_ln<4>(x, gamma, beta, out, out_kind, rows, ldx, eps, st);
+    case 5: return launch_ln<5>(x, gamma, beta, out, out_kind, rows, ldx, eps, st);
+    case 6: return launch_ln<6>(x, gamma, beta, out, out_kind, rows, ldx, eps, st);
+    case 7: return launch_ln<7>(x, gamma, beta, out, out_kind, rows, ldx, eps, st);
+    default: return launch_ln<8>(x, gamma, beta, out, out_kind, rows, ldx, eps, st);
   }
 }

@@ -85,6 +85,7 @@ def scale_stage(
     capture: Optional[Dict[str, torch.Tensor]] = None,
     attn_algo: int = 0,
     max_chunk_tokens: int = 1 << 21,
+    live_only_last: bool = True,
 ) -> torch.Tensor:
     """L x { X += g1*Attn(LN1 X) ; X += g2*MLP(LN2 X) } in place on the fp32 token tensor
     X [B, P, S, D]  (scale_attention.py:90-93 / multiscale_attn.py:282-285)."""
@@ -114,6 +115,24 @@ def scale_stage(
         for i, blk in enumerate(blocks):
             ops.layernorm(Xc, blk["n1w"], blk["n1b"], Hn, eps)
             ops.gemm(Hn, blk["qkv"][0], blk["qkv"][1], QKV, ops.EPI_F32 if fp32 else ops.EPI_BF16, split3=fp32)
+            if live_only_last and i == len(blocks) - 1:
+                # Last scale block: only the scale token (s = 0) of every patch is consumed downstream
+                # (scale_attention.py:183-185), so K/V are needed for all tokens but the query,
+                # attention output, proj, MLP and both residual updates only for the s = 0 rows
+                # (SURVEY.md App. A.3).  X0 is the strided view of those rows inside X.
+                R = nb * P
+                X0 = Xc.view(R, S, D)[:, 0, :]
+                A0 = Workspace.view(buf, 0, (R, kd * D), torch.bfloat16)
+                ops.group_attention(QKV, A0, S, num_heads, scale, algo=attn_algo, q_rows=1)
+                ops.gemm(A0, blk["proj"][0], blk["proj"][1], X0, ops.EPI_RESIDUAL_F32, gamma=blk["g1"], split3=fp32)
+                ops.layernorm(X0, blk["n2w"], blk["n2b"], A0, eps)
+                H0 = Workspace.view(buf, hn_bytes, (R, kd * hidden), torch.bfloat16)
+                ops.gemm(A0, blk["fc1"][0], blk["fc1"][1], H0,
+                         ops.EPI_GELU_SPLIT_BF16 if fp32 else ops.EPI_GELU_BF16, split3=fp32)
+                ops.gemm(H0, blk["fc2"][0], blk["fc2"][1], X0, ops.EPI_RESIDUAL_F32, gamma=blk["g2"], split3=fp32)
+                if capture is not None:
+                    capture[f"scale_block_{i}_s0"] = X[:, :, 0, :].clone()
+                continue
             ops.group_attention(QKV, Hn, S, num_heads, scale, algo=attn_algo)  # attention output re-uses Hn
             ops.gemm(Hn, blk["proj"][0], blk["proj"][1], Xc, ops.EPI_RESIDUAL_F32, gamma=blk["g1"], split3=fp32)
             ops.layernorm(Xc, blk["n2w"], blk["n2b"], Hn, eps)

@@ -83,6 +83,8 @@ class MultiscaleTransformer(nn.Module):
         self._init_weights()
         self.precision = "bf16"
         self.attn_algo = 0
+        # skip work the reference computes but never consumes (last scale block: only s = 0 rows)
+        self.dead_work_elimination = True
         self._capture: Optional[Dict[str, torch.Tensor]] = None
         self._ws: Optional[engine.Workspace] = None
 
@@ -115,7 +117,7 @@ class MultiscaleTransformer(nn.Module):
         packs = [b.pack(prec) for b in self.blocks]
         scale = self.blocks[0].attn.scale if depth else 1.0
         engine.scale_stage(X, packs, self.num_heads, scale, self.blocks[0].norm1.eps if depth else 1e-6, prec,
-                           self.workspace(X.device), cap, attn_algo=self.attn_algo)
+                           self.workspace(X.device), cap, attn_algo=self.attn_algo, live_only_last=self.dead_work_elimination)
         N = P + 1
         kd = 2 if prec == "fp32" else 1
         logits = torch.empty(B, self.head.out_features, dtype=torch.float32, device=X.device)

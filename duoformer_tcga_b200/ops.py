@@ -98,23 +98,29 @@ def gemm(
 
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out: torch.Tensor, eps: float) -> torch.Tensor:
-    """out (bf16 [rows,D] or split bf16 [rows,2D]) = LayerNorm(x fp32 [rows,D])."""
+    """out (bf16 [rows,D] or split bf16 [rows,2D], dense) = LayerNorm(x fp32 [rows,D]).
+    x may be a 2-D row-strided view (e.g. the s = 0 token of every patch)."""
     D = x.shape[-1]
-    assert x.dtype == torch.float32 and x.is_contiguous() and out.is_contiguous()
-    rows = x.numel() // D
+    assert x.dtype == torch.float32 and out.is_contiguous() and x.stride(-1) == 1
+    if x.is_contiguous():
+        rows, ldx = x.numel() // D, D
+    else:
+        assert x.dim() == 2, "strided LayerNorm input must be a 2-D view"
+        rows, ldx = x.shape[0], x.stride(0)
     kind = _act_kind(out, D)
     assert kind in (ACT_BF16, ACT_SPLIT)
     _lib.check(
-        _lib.load().duo_layernorm(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(out), kind, rows, D, float(eps), _stream()),
+        _lib.load().duo_layernorm(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(out), kind, rows, D, ldx, float(eps), _stream()),
         "duo_layernorm",
     )
     return out
 
 
 def group_attention(
-    qkv: torch.Tensor, out: torch.Tensor, S: int, num_heads: int, scale: float, algo: int = 0
+    qkv: torch.Tensor, out: torch.Tensor, S: int, num_heads: int, scale: float, algo: int = 0, q_rows: int = 0
 ) -> torch.Tensor:
-    """softmax(q k^T * scale) v per (group of S rows, head); qkv [rows, 3*D], out [rows, D | 2D]."""
+    """softmax(q k^T * scale) v per (group of S rows, head); qkv [rows, 3*D], out [rows, D | 2D].
+    q_rows > 0: only the first q_rows query rows per group; out is [groups * q_rows, D | 2D]."""
     assert qkv.is_contiguous() and out.is_contiguous()
     D = qkv.shape[-1] // 3
     rows = qkv.numel() // (3 * D)
@@ -123,7 +129,8 @@ def group_attention(
     out_kind = _act_kind(out, D)
     _lib.check(
         _lib.load().duo_group_attention(
-            _ptr(qkv), in_kind, _ptr(out), out_kind, rows // S, S, num_heads, float(scale), algo, _stream()
+            _ptr(qkv), in_kind, _ptr(out), out_kind, rows // S, S, num_heads, float(scale), algo,
+            q_rows if q_rows > 0 else S, _stream()
         ),
         "duo_group_attention",
     )

@@ -167,6 +167,8 @@ class MultiscaleFormer(nn.Module):
         self._init_weights()
         self.precision = "bf16"
         self.attn_algo = 0
+        # skip work the reference computes but never consumes (last scale block: only s = 0 rows)
+        self.dead_work_elimination = True
         self._capture: Optional[Dict[str, torch.Tensor]] = None
         self._ws: Optional[engine.Workspace] = None
 
@@ -202,7 +204,7 @@ class MultiscaleFormer(nn.Module):
         scale = self.scaleBlocks[0].attn.scale if len(self.scaleBlocks) else 0.125
         engine.scale_stage(X, [b.pack(prec) for b in self.scaleBlocks], self.num_heads, scale,
                            self.scaleBlocks[0].norm1.eps if len(self.scaleBlocks) else 1e-6, prec, ws, cap,
-                           attn_algo=self.attn_algo)
+                           attn_algo=self.attn_algo, live_only_last=self.dead_work_elimination)
         # patch stage: CLS + first scale token of every patch + pos_embed (scale_attention.py:183-193)
         N = P + 1
         kd = 2 if prec == "fp32" else 1

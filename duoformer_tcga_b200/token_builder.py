@@ -21,6 +21,32 @@ from . import engine, ops
 from .index_tables import num_scale_tokens, stages_used, token_row_maps
 
 
+def _fold_batchnorm_(trunk: nn.Module) -> None:
+    """Fold every eval-mode BatchNorm2d of a torchvision ResNet trunk into the convolution that
+    feeds it (stem conv1/bn1, each Bottleneck's conv{1,2,3}/bn{1,2,3} and downsample.{0,1});
+    the BN modules become Identity.  Works for both the index-named Sequential wrapper
+    (children '0','1',...) and the name-based ResNetTrunkByScale."""
+    from torch.nn.utils.fusion import fuse_conv_bn_eval
+
+    def fold_pairs(parent: nn.Module, pairs):
+        for conv_name, bn_name in pairs:
+            conv, bn = getattr(parent, conv_name, None), getattr(parent, bn_name, None)
+            if isinstance(conv, nn.Conv2d) and isinstance(bn, nn.BatchNorm2d):
+                setattr(parent, conv_name, fuse_conv_bn_eval(conv, bn))
+                setattr(parent, bn_name, nn.Identity())
+
+    if isinstance(trunk, nn.Sequential):
+        fold_pairs(trunk, [("0", "1")])
+    else:
+        fold_pairs(trunk, [("conv1", "bn1")])
+    for m in trunk.modules():
+        if m.__class__.__name__ in ("Bottleneck", "BasicBlock"):
+            fold_pairs(m, [("conv1", "bn1"), ("conv2", "bn2"), ("conv3", "bn3")])
+            ds = getattr(m, "downsample", None)
+            if isinstance(ds, nn.Sequential) and len(ds) == 2:
+                fold_pairs(ds, [("0", "1")])
+
+
 class TrunkRunner:
     """Runs the torch/cuDNN ResNet trunk in the precision of the path (bf16 channels-last copy
     of the fp32 master weights, re-made when they change) and returns the tapped stage maps."""
@@ -32,8 +58,9 @@ class TrunkRunner:
     def _packed_trunk(self, trunk: nn.Module, precision: str) -> nn.Module:
         sig = engine.param_signature(trunk, precision)
         if self._trunk is None or self._sig != sig:
-            t = copy.deepcopy(trunk).eval()
+            t = copy.deepcopy(trunk).eval().float()
             if precision == "bf16":
+                _fold_batchnorm_(t)  # eval-mode BN -> scale/shift of the preceding conv (fp32, before the bf16 cast)
                 t = t.to(dtype=torch.bfloat16, memory_format=torch.channels_last)
             else:
                 t = t.to(dtype=torch.float32, memory_format=torch.channels_last)

@@ -100,10 +100,12 @@ int duo_gemm(const duo_gemm_args* args, duo_stream_t stream);
 /*
  * LayerNorm over the last dim (fp32 statistics, two-pass), fp32 in -> bf16 / split bf16 out.
  * Replaces nn.LayerNorm(eps=1e-6): scale_attention.py:65,78,91-92; multiscale_attn.py:282-285.
- * dim % 128 == 0, dim <= 1024.
+ * dim % 128 == 0, dim <= 1024.  ldx = input row stride in elements (>= dim; rows of a strided view,
+ * e.g. the s = 0 token of every patch, can be normalised without a gather); out is dense.
  */
 int duo_layernorm(const float* x, const float* gamma, const float* beta, void* out,
-                  int32_t out_kind, int64_t rows, int32_t dim, float eps, duo_stream_t stream);
+                  int32_t out_kind, int64_t rows, int32_t dim, int64_t ldx, float eps,
+                  duo_stream_t stream);
 
 /*
  * Grouped multi-head attention over S consecutive rows of a fused qkv matrix:
@@ -115,10 +117,14 @@ int duo_layernorm(const float* x, const float* gamma, const float* beta, void* o
  * in_kind: DUO_ACT_BF16 or DUO_ACT_F32; out_kind: DUO_ACT_BF16 / DUO_ACT_SPLIT / DUO_ACT_F32.
  * algo: 0 = auto, 1 = warp-per-(group,head) register/shuffle FMA kernel (any S <= 160),
  *       2 = warp-level tensor-core (mma.sync) kernel (bf16 in, bf16 out, 16 < S <= 96).
+ * q_rows: only the first q_rows query rows of every group are computed and `out` is the dense
+ *       [num_groups * q_rows, D] matrix of those rows (q_rows = S: everything; q_rows = 1: the
+ *       scale-token / CLS query only — all that the reference consumes after the LAST scale
+ *       block, scale_attention.py:183-185, and after the last patch block, :341).
  */
 int duo_group_attention(const void* qkv, int32_t in_kind, void* out, int32_t out_kind,
                         int64_t num_groups, int32_t S, int32_t num_heads, float scale,
-                        int32_t algo, duo_stream_t stream);
+                        int32_t algo, int32_t q_rows, duo_stream_t stream);
 
 /*
  * Scale token row (s = 0) of the token tensor:  X[b,p,0,:] = tok[b,p,:] + pos0[:]

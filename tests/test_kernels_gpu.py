@@ -134,6 +134,33 @@ def test_group_attention_bf16(S, G, algo):
     assert relerr(out, ref) < (1.5e-2 if algo == 2 else 8e-3)
 
 
+@pytest.mark.parametrize("S,G,algo,q_rows", [(86, 49, 2, 1), (86, 49, 1, 1), (22, 10, 2, 3), (6, 30, 1, 1), (50, 5, 2, 17)])
+def test_group_attention_leading_query_rows(S, G, algo, q_rows):
+    H = 12
+    qkv = _gen((G * S, 3 * H * 64), 91 + S, 2.0).to(torch.bfloat16)
+    ref = _attn_ref(qkv, S, H, 0.125).reshape(G, S, H * 64)[:, :q_rows].reshape(G * q_rows, H * 64)
+    out = torch.empty(G * q_rows, H * 64, dtype=torch.bfloat16, device="cuda")
+    ops.group_attention(qkv, out, S, H, 0.125, algo=algo, q_rows=q_rows)
+    assert relerr(out, ref) < 1.5e-2
+
+
+def test_layernorm_strided_rows_and_residual_into_strided_view():
+    R, S, D = 300, 6, 768
+    X = _gen((R, S, D), 95, 5.0)
+    g, b = _gen((D,), 96), _gen((D,), 97)
+    X0 = X[:, 0, :]
+    out = torch.empty(R, D, dtype=torch.bfloat16, device="cuda")
+    ops.layernorm(X0, g, b, out, 1e-6)
+    assert relerr(out, torch.nn.functional.layer_norm(X0, (D,), g, b, 1e-6)) < 6e-3
+    A = _gen((R, D), 98).to(torch.bfloat16)
+    W = _gen((D, D), 99, 0.05).to(torch.bfloat16)
+    bias = _gen((D,), 100)
+    ref = X.clone()
+    ref[:, 0, :] += A.float() @ W.float().t() + bias
+    ops.gemm(A, W, bias, X0, ops.EPI_RESIDUAL_F32)
+    assert relerr(X, ref) < 1e-4
+
+
 @pytest.mark.parametrize("S,G", [(6, 98), (86, 10), (50, 4)])
 def test_group_attention_fp32(S, G):
     H = 12
