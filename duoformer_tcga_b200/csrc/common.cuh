@@ -130,6 +130,38 @@ __device__ __forceinline__ void gelu_erf_fast_x2(float& a, float& b) {
 #undef DUO_C2
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// GELU(erf) for the bf16 epilogue in "sigmoid of the probit logit" form:
+//   gelu(x) = x * Phi(x) = x / (1 + exp(-L(x))),  L(x) = logit(Phi(x)) = ln(Phi(x) / Phi(-x)),
+// L is odd and smooth; an odd degree-7 polynomial fitted (reweighted least squares, minimax on the
+// gelu error, |x| clamped to 5.5 inside L only) reproduces the exact erf-GELU to 1.2e-5 absolute
+// (fp32 simulation, x in [-12, 12]) — about 300x below bf16 rounding of O(1) activations — with
+// 7 FMA-pipe operations + 2 MUFU (ex2, rcp) per element instead of ~18 + 1 for the rational erf.
+// The coefficients below are -log2(e) * c_k so that exp(-L) = ex2(x * r(x^2)).
+__device__ __forceinline__ void gelu_erf_sigmoid_x2(float& a, float& b) {
+#define DUO_C2(v) pack2((v), (v))
+  const uint64_t x = pack2(a, b);
+  const float ca = fminf(fmaxf(a, -5.5f), 5.5f);
+  const float cb = fminf(fmaxf(b, -5.5f), 5.5f);
+  const uint64_t xc = pack2(ca, cb);
+  const uint64_t u = mul2(xc, xc);
+  uint64_t r = fma2(DUO_C2(2.4836352167767473e-05f), u, DUO_C2(7.360616000369191e-04f));
+  r = fma2(r, u, DUO_C2(-1.0598272830247879e-01f));
+  r = fma2(r, u, DUO_C2(-2.301647186279297f));
+  float ea, eb;
+  unpack2(mul2(xc, r), ea, eb);
+  const uint64_t d = add2(pack2(ex2_approx(ea), ex2_approx(eb)), DUO_C2(1.0f));
+  float da, db;
+  unpack2(d, da, db);
+  unpack2(mul2(x, pack2(rcp_approx(da), rcp_approx(db))), a, b);
+#undef DUO_C2
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);  // .x = a (low 16 bits), .y = b
   return *reinterpret_cast<uint32_t*>(&v);

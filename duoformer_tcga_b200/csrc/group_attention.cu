@@ -267,12 +267,14 @@ __device__ __forceinline__ uint32_t swz(int r, int c) {
 
 constexpr int kMmaWarps = 2;
 
-template <int S_PAD>
+// S_CT > 0: S known at compile time (masks and fully-padded key tiles are pruned); 0: runtime S.
+template <int S_PAD, int S_CT>
 __global__ void __launch_bounds__(kMmaWarps * 32)
 group_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
-                           int S, int H, float scale_log2e, int q_rows) {
+                           int S_rt, int H, float scale_log2e, int q_rows) {
   constexpr int MT = S_PAD / 16;  // query m-tiles (also 16-key steps)
   constexpr int NT = S_PAD / 8;   // 8-key n-tiles
+  const int S = S_CT > 0 ? S_CT : S_rt;
   __shared__ __align__(128) uint8_t smem[3 * S_PAD * 128];
   const uint32_t sQ = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
   const uint32_t sK = sQ + S_PAD * 128;
@@ -289,16 +291,24 @@ group_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16*
   const __nv_bfloat16* base = qkv + (g * S) * ld + h * kHeadDim;
 
   // ---- stage Q, K, V (S rows x 128 B each) with cp.async; zero the padding rows ----
-  for (int idx = tid; idx < 3 * S_PAD * 8; idx += kMmaWarps * 32) {
-    const int which = idx / (S_PAD * 8);
-    const int rem = idx - which * (S_PAD * 8);
-    const int r = rem >> 3;
-    const int c = rem & 7;
-    const uint32_t dst = sQ + which * (S_PAD * 128) + swz(r, c);
-    if (r < S) {
-      cp_async_16(dst, base + r * ld + which * D + c * 8);
-    } else {
-      asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0u) : "memory");
+  {
+    const int c = tid & 7;          // 16-byte chunk of the row (constant per thread)
+    const int r_first = tid >> 3;   // 0..7
+    const uint32_t swz_c = static_cast<uint32_t>((c ^ (r_first & 7)) << 4);  // (r & 7) == r_first: rows step by 8
+    const __nv_bfloat16* src = base + static_cast<int64_t>(r_first) * ld + c * 8;
+#pragma unroll
+    for (int which = 0; which < 3; ++which) {
+      const uint32_t dst0 = sQ + which * (S_PAD * 128) + r_first * 128 + swz_c;
+      const __nv_bfloat16* s0 = src + which * D;
+#pragma unroll
+      for (int i = 0; i < S_PAD / 8; ++i) {
+        const int r = r_first + 8 * i;
+        if (r < S) {
+          cp_async_16(dst0 + i * 1024, s0 + static_cast<int64_t>(8 * i) * ld);
+        } else {
+          asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(dst0 + i * 1024), "r"(0u) : "memory");
+        }
+      }
     }
   }
   cp_async_wait_all();
@@ -306,6 +316,18 @@ group_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16*
 
   const int gq = lane >> 2;  // fragment row group
   const int tq = lane & 3;   // fragment column pair
+  // Per-lane ldmatrix offsets.  Row offsets added later are multiples of 8 rows, so the XOR
+  // swizzle term (row & 7) == (lane & 7) is a per-lane constant.
+  const uint32_t x7 = static_cast<uint32_t>(lane & 7);
+  uint32_t q_off[4], k_off[4], v_off[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    q_off[i] = static_cast<uint32_t>(((lane & 7) + ((lane >> 3) & 1) * 8) * 128) + (((2 * i + (lane >> 4)) ^ x7) << 4);
+    k_off[i] = static_cast<uint32_t>(((lane & 7) + ((lane >> 4) & 1) * 8) * 128) + (((2 * i + ((lane >> 3) & 1)) ^ x7) << 4);
+    v_off[i] = q_off[i];  // V (transposed load) uses the same lane -> (row, chunk) pattern as Q
+  }
+  // number of 16-key steps / 8-key tiles that contain at least one real key
+  const int kt_live = (S + 15) >> 4;
 
   for (int mt = warp; mt < MT; mt += kMmaWarps) {
     const int m0 = mt * 16;
@@ -313,34 +335,35 @@ group_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16*
     // ---- Q fragments (A operand), 4 k-steps of 16 ----
     uint32_t qa[4][4];
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-      const int r = m0 + (lane & 7) + ((lane >> 3) & 1) * 8;
-      const int c = 2 * ks + (lane >> 4);
-      ldmatrix_x4(sQ + swz(r, c), qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3]);
-    }
+    for (int ks = 0; ks < 4; ++ks)
+      ldmatrix_x4(sQ + m0 * 128 + q_off[ks], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3]);
     // ---- scores = Q K^T ----
     float sc[NT][4];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
 #pragma unroll
     for (int np = 0; np < MT; ++np) {
+      if (S_CT > 0 ? (np * 16 < S_CT) : (np < kt_live)) {
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        uint32_t b0, b1, b2, b3;
-        const int r = np * 16 + (lane & 7) + ((lane >> 4) & 1) * 8;
-        const int c = 2 * ks + ((lane >> 3) & 1);
-        ldmatrix_x4(sK + swz(r, c), b0, b1, b2, b3);
-        mma_bf16_16816(sc[2 * np], qa[ks], b0, b1);
-        mma_bf16_16816(sc[2 * np + 1], qa[ks], b2, b3);
+        for (int ks = 0; ks < 4; ++ks) {
+          uint32_t b0, b1, b2, b3;
+          ldmatrix_x4(sK + np * 2048 + k_off[ks], b0, b1, b2, b3);
+          mma_bf16_16816(sc[2 * np], qa[ks], b0, b1);
+          if (S_CT == 0 || np * 16 + 8 < S_CT) mma_bf16_16816(sc[2 * np + 1], qa[ks], b2, b3);
+        }
       }
     }
     // ---- softmax over keys (rows gq and gq+8 of this m-tile) ----
     float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
-      const int col = nt * 8 + 2 * tq;
-      if (col >= S) sc[nt][0] = sc[nt][2] = -INFINITY;
-      if (col + 1 >= S) sc[nt][1] = sc[nt][3] = -INFINITY;
+      if (S_CT > 0 && nt * 8 + 8 <= S_CT) {
+        // tile entirely inside the real keys: no masking
+      } else {
+        const int col = nt * 8 + 2 * tq;
+        if (col >= S) sc[nt][0] = sc[nt][2] = -INFINITY;
+        if (col + 1 >= S) sc[nt][1] = sc[nt][3] = -INFINITY;
+      }
       mx0 = fmaxf(mx0, fmaxf(sc[nt][0], sc[nt][1]));
       mx1 = fmaxf(mx1, fmaxf(sc[nt][2], sc[nt][3]));
     }
@@ -352,12 +375,16 @@ group_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16*
     float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
-      sc[nt][0] = exp2f(fmaf(sc[nt][0], scale_log2e, -off0));
-      sc[nt][1] = exp2f(fmaf(sc[nt][1], scale_log2e, -off0));
-      sc[nt][2] = exp2f(fmaf(sc[nt][2], scale_log2e, -off1));
-      sc[nt][3] = exp2f(fmaf(sc[nt][3], scale_log2e, -off1));
-      sum0 += sc[nt][0] + sc[nt][1];
-      sum1 += sc[nt][2] + sc[nt][3];
+      if (S_CT > 0 && nt * 8 >= S_CT) {  // tile entirely padding: probabilities are exactly 0
+        sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+      } else {
+        sc[nt][0] = exp2f(fmaf(sc[nt][0], scale_log2e, -off0));
+        sc[nt][1] = exp2f(fmaf(sc[nt][1], scale_log2e, -off0));
+        sc[nt][2] = exp2f(fmaf(sc[nt][2], scale_log2e, -off1));
+        sc[nt][3] = exp2f(fmaf(sc[nt][3], scale_log2e, -off1));
+        sum0 += sc[nt][0] + sc[nt][1];
+        sum1 += sc[nt][2] + sc[nt][3];
+      }
     }
     sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
     sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
@@ -370,38 +397,39 @@ group_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16*
     for (int nt = 0; nt < 8; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
 #pragma unroll
     for (int kk = 0; kk < MT; ++kk) {
-      uint32_t pa[4];
-      pa[0] = pack_bf16x2(sc[2 * kk][0], sc[2 * kk][1]);
-      pa[1] = pack_bf16x2(sc[2 * kk][2], sc[2 * kk][3]);
-      pa[2] = pack_bf16x2(sc[2 * kk + 1][0], sc[2 * kk + 1][1]);
-      pa[3] = pack_bf16x2(sc[2 * kk + 1][2], sc[2 * kk + 1][3]);
+      if (S_CT > 0 ? (kk * 16 < S_CT) : (kk < kt_live)) {
+        uint32_t pa[4];
+        pa[0] = pack_bf16x2(sc[2 * kk][0], sc[2 * kk][1]);
+        pa[1] = pack_bf16x2(sc[2 * kk][2], sc[2 * kk][3]);
+        pa[2] = pack_bf16x2(sc[2 * kk + 1][0], sc[2 * kk + 1][1]);
+        pa[3] = pack_bf16x2(sc[2 * kk + 1][2], sc[2 * kk + 1][3]);
 #pragma unroll
-      for (int dp = 0; dp < 4; ++dp) {
-        uint32_t b0, b1, b2, b3;
-        const int r = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-        const int c = 2 * dp + (lane >> 4);
-        ldmatrix_x4_trans(sV + swz(r, c), b0, b1, b2, b3);
-        mma_bf16_16816(o[2 * dp], pa, b0, b1);
-        mma_bf16_16816(o[2 * dp + 1], pa, b2, b3);
+        for (int dp = 0; dp < 4; ++dp) {
+          uint32_t b0, b1, b2, b3;
+          ldmatrix_x4_trans(sV + kk * 2048 + v_off[dp], b0, b1, b2, b3);
+          mma_bf16_16816(o[2 * dp], pa, b0, b1);
+          mma_bf16_16816(o[2 * dp + 1], pa, b2, b3);
+        }
       }
     }
     // ---- normalise and store (heads merged: column h*64 + d) ----
     const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
     const int r0 = m0 + gq, r1 = m0 + gq + 8;
     __nv_bfloat16* obase = out + (g * q_rows) * D + h * kHeadDim + 2 * tq;
+    const bool st0 = r0 < q_rows && r0 < S, st1 = r1 < q_rows && r1 < S;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      if (r0 < q_rows)
+      if (st0)
         *reinterpret_cast<uint32_t*>(obase + static_cast<int64_t>(r0) * D + nt * 8) =
             pack_bf16x2(o[nt][0] * inv0, o[nt][1] * inv0);
-      if (r1 < q_rows)
+      if (st1)
         *reinterpret_cast<uint32_t*>(obase + static_cast<int64_t>(r1) * D + nt * 8) =
             pack_bf16x2(o[nt][2] * inv1, o[nt][3] * inv1);
     }
   }
 }
 
-template <int S_PAD>
+template <int S_PAD, int S_CT>
 int launch_mma(const void* qkv, void* out, int64_t groups, int S, int H, float scale, int q_rows,
                cudaStream_t st) {
   const int64_t problems = groups * H;
@@ -409,7 +437,7 @@ int launch_mma(const void* qkv, void* out, int64_t groups, int S, int H, float s
     set_error("duo_group_attention: too many groups");
     return DUO_ERR_INVALID;
   }
-  group_attention_mma_kernel<S_PAD><<<static_cast<unsigned>(problems), kMmaWarps * 32, 0, st>>>(
+  group_attention_mma_kernel<S_PAD, S_CT><<<static_cast<unsigned>(problems), kMmaWarps * 32, 0, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), S, H,
       scale * 1.4426950408889634f, q_rows);
   DUO_LAUNCH_CHECK("group_attention_mma_kernel");
@@ -438,11 +466,15 @@ extern "C" int duo_group_attention(const void* qkv, int32_t in_kind, void* out, 
   if (algo == 0) algo = mma_ok ? 2 : 1;
   if (algo == 2) {
     DUO_CHECK_ARG(mma_ok, "duo_group_attention: algo 2 needs bf16 in/out and 16 < S <= 96 (S=%d)", S);
-    if (S <= 32) return launch_mma<32>(qkv, out, num_groups, S, num_heads, scale, q_rows, st);
-    if (S <= 48) return launch_mma<48>(qkv, out, num_groups, S, num_heads, scale, q_rows, st);
-    if (S <= 64) return launch_mma<64>(qkv, out, num_groups, S, num_heads, scale, q_rows, st);
-    if (S <= 80) return launch_mma<80>(qkv, out, num_groups, S, num_heads, scale, q_rows, st);
-    return launch_mma<96>(qkv, out, num_groups, S, num_heads, scale, q_rows, st);
+    // the model's own sizes get compile-time S (masks / padded tiles pruned)
+    if (S == 86) return launch_mma<96, 86>(qkv, out, num_groups, S, num_heads, scale, q_rows, st);
+    if (S == 22) return launch_mma<32, 22>(qkv, out, num_groups, S, num_heads, scale, q_rows, st);
+    if (S == 50) return launch_mma<64, 50>(qkv, out, num_groups, S, num_heads, scale, q_rows, st);
+    if (S <= 32) return launch_mma<32, 0>(qkv, out, num_groups, S, num_heads, scale, q_rows, st);
+    if (S <= 48) return launch_mma<48, 0>(qkv, out, num_groups, S, num_heads, scale, q_rows, st);
+    if (S <= 64) return launch_mma<64, 0>(qkv, out, num_groups, S, num_heads, scale, q_rows, st);
+    if (S <= 80) return launch_mma<80, 0>(qkv, out, num_groups, S, num_heads, scale, q_rows, st);
+    return launch_mma<96, 0>(qkv, out, num_groups, S, num_heads, scale, q_rows, st);
   }
   DUO_CHECK_ARG(algo == 1, "duo_group_attention: algo=%d", algo);
   if (in_kind == DUO_ACT_BF16) {

@@ -181,7 +181,10 @@ __device__ __forceinline__ uint32_t mapa(uint32_t smem_addr, uint32_t cta) {
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+  // default semantics (.release at CTA scope): the cluster-scope release form costs a
+  // MEMBAR.ALL.GPU + ERRBAR per arrival and is not needed — the only thing ordered before this
+  // arrive is the completion of tcgen05.ld (tcgen05.wait::ld + tcgen05.fence::before_thread_sync).
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 // TMA load whose completion may signal an mbarrier in the peer CTA of the pair.
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t smem_dst, const void* tmap,

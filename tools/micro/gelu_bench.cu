@@ -19,6 +19,7 @@ __global__ void k(const float* in, float* out, int iters) {
     if (V == 0) { for (int j = 0; j < 32; ++j) x[j] = gelu_erf(x[j]) + 0.5f; }
     if (V == 1) { for (int j = 0; j < 32; ++j) x[j] = gelu_erf_fast(x[j]) + 0.5f; }
     if (V == 2) { for (int j = 0; j < 32; j += 2) { gelu_erf_fast_x2(x[j], x[j + 1]); x[j] += 0.5f; x[j+1] += 0.5f; } }
+    if (V == 4) { for (int j = 0; j < 32; j += 2) { gelu_erf_sigmoid_x2(x[j], x[j + 1]); x[j] += 0.5f; x[j+1] += 0.5f; } }
     if (V == 3) { for (int j = 0; j < 32; ++j) x[j] = gelu_poly(x[j]) + 0.5f; }
   }
   float s = 0; for (int j = 0; j < 32; ++j) s += x[j];
@@ -36,7 +37,7 @@ template <int V> void run(const char* name, float* in, float* out, int warps_per
 int main() {
   float *in, *out; cudaMalloc(&in, 4096 * 4); cudaMalloc(&out, 148 * 1024 * 4); cudaMemset(in, 0, 4096 * 4);
   for (int w : {4, 8, 16}) {
-    run<0>("erff", in, out, w); run<1>("rational scalar", in, out, w); run<2>("rational packed x2", in, out, w); run<3>("poly5 scalar", in, out, w);
+    run<0>("erff", in, out, w); run<1>("rational scalar", in, out, w); run<2>("rational packed x2", in, out, w); run<3>("poly5 scalar", in, out, w); run<4>("sigmoid packed x2", in, out, w);
   }
   return 0;
 }
