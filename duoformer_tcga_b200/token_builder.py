@@ -47,6 +47,42 @@ def _fold_batchnorm_(trunk: nn.Module) -> None:
                 fold_pairs(ds, [("0", "1")])
 
 
+def _conv_args(conv: nn.Conv2d):
+    return list(conv.stride), list(conv.padding), list(conv.dilation), conv.groups
+
+
+def _fused_bottleneck(blk: nn.Module, x: torch.Tensor) -> torch.Tensor:
+    """BN-folded torchvision Bottleneck through cuDNN's fused conv+bias+ReLU / conv+add+bias+ReLU
+    (ATen cudnn_convolution_relu / cudnn_convolution_add_relu): no separate bias / ReLU / add kernels."""
+    out = torch.cudnn_convolution_relu(x, blk.conv1.weight, blk.conv1.bias, *_conv_args(blk.conv1))
+    out = torch.cudnn_convolution_relu(out, blk.conv2.weight, blk.conv2.bias, *_conv_args(blk.conv2))
+    if blk.downsample is not None:
+        identity = blk.downsample(x)
+    else:
+        identity = x
+    return torch.cudnn_convolution_add_relu(out, blk.conv3.weight, identity, 1.0, blk.conv3.bias,
+                                            *_conv_args(blk.conv3))
+
+
+def _fused_trunk_forward(t: nn.Module, x: torch.Tensor, by_scale: bool) -> Dict[int, torch.Tensor]:
+    """Forward of a BN-folded ResNet-50 trunk with fused cuDNN epilogues; returns the four stage maps."""
+    if by_scale:
+        stem, pool = t.conv1, t.maxpool
+        layers = [t.layer1, t.layer2, t.layer3, t.layer4]
+    else:
+        ch = dict(t.named_children())
+        stem, pool = ch["0"], ch["3"]
+        layers = [ch["4"], ch["5"], ch["6"], ch["7"]]
+    x = torch.cudnn_convolution_relu(x, stem.weight, stem.bias, *_conv_args(stem))
+    x = pool(x)
+    feats: Dict[int, torch.Tensor] = {}
+    for i, layer in enumerate(layers):
+        for blk in layer:
+            x = _fused_bottleneck(blk, x)
+        feats[i] = x
+    return feats
+
+
 class TrunkRunner:
     """Runs the torch/cuDNN ResNet trunk in the precision of the path (bf16 channels-last copy
     of the fp32 master weights, re-made when they change) and returns the tapped stage maps."""
@@ -54,6 +90,7 @@ class TrunkRunner:
     def __init__(self):
         self._sig = None
         self._trunk: Optional[nn.Module] = None
+        self.fused_ok: Optional[bool] = None  # None = not tried yet
 
     def _packed_trunk(self, trunk: nn.Module, precision: str) -> nn.Module:
         sig = engine.param_signature(trunk, precision)
@@ -78,19 +115,38 @@ class TrunkRunner:
         if precision == "fp32":
             torch.backends.cudnn.allow_tf32 = False
         try:
-            if by_scale:  # ResNetTrunkByScale returns [layer1..layer4]  (resnet50ssl.py:35-45)
-                outs = t(x)
-                return {i: o for i, o in enumerate(outs)}
-            feats: Dict[int, torch.Tensor] = {}
-            # nn.Sequential(conv1,bn1,relu,maxpool,layer1..4): children '4'..'7' are the stage taps
-            # (model_wo_extra_params.py:214-224, model.py:213-223)
-            for name, module in t.named_children():
-                x = module(x)
-                if name in ("4", "5", "6", "7"):
-                    feats[int(name) - 4] = x
-            return feats
+            if precision == "bf16" and self.fused_ok is not False:
+                # BN-folded bottlenecks through cuDNN's fused conv+bias(+add)+ReLU; verified once
+                # against the plain module path, with a permanent fallback if unsupported.
+                try:
+                    feats = _fused_trunk_forward(t, x, by_scale)
+                    if self.fused_ok is None:
+                        ref = self._plain_forward(t, x, by_scale)
+                        ok = all(torch.allclose(feats[k].float(), ref[k].float(), rtol=5e-2, atol=5e-2 * float(ref[k].float().abs().max()))
+                                 for k in ref)
+                        self.fused_ok = bool(ok)
+                        if not ok:
+                            return ref
+                    return feats
+                except (RuntimeError, AttributeError, KeyError, TypeError):
+                    self.fused_ok = False
+            return self._plain_forward(t, x, by_scale)
         finally:
             torch.backends.cudnn.allow_tf32 = old_tf32
+
+    @staticmethod
+    def _plain_forward(t: nn.Module, x: torch.Tensor, by_scale: bool) -> Dict[int, torch.Tensor]:
+        if by_scale:  # ResNetTrunkByScale returns [layer1..layer4]  (resnet50ssl.py:35-45)
+            outs = t(x)
+            return {i: o for i, o in enumerate(outs)}
+        feats: Dict[int, torch.Tensor] = {}
+        # nn.Sequential(conv1,bn1,relu,maxpool,layer1..4): children '4'..'7' are the stage taps
+        # (model_wo_extra_params.py:214-224, model.py:213-223)
+        for name, module in t.named_children():
+            x = module(x)
+            if name in ("4", "5", "6", "7"):
+                feats[int(name) - 4] = x
+        return feats
 
 
 class TokenBuilder(engine.PackCache):
