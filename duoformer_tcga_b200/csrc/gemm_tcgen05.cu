@@ -281,6 +281,68 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
       }
       stg_buf = (NBUF == 1) ? 0u : (stg_buf ^ 1u);
     }
+  } else if constexpr (EPI == DUO_EPI_SCATTER_F32) {
+    // Token scatter: every source row goes to its own destination row (p*S + s), so no tensor
+    // store applies.  Rows are transposed through the warp's swizzled staging tile so that each
+    // store instruction writes four complete 128-byte lines (8 lanes x 16 B per row) instead of
+    // 32 partial ones.
+    int64_t dst_row = -1;
+    int32_t dst_s = 0;
+    if (valid) {
+      const int64_t grp = row / p.rows_per_group;
+      const int32_t in_grp = static_cast<int32_t>(row - grp * p.rows_per_group);
+      const int32_t dst_in_grp = __ldg(p.row_map + in_grp);
+      dst_row = grp * p.dest_rows_per_group + dst_in_grp;
+      dst_s = p.pos != nullptr ? dst_in_grp % p.pos_period : 0;
+    }
+    const int sub_row = lane >> 3;  // row inside a group of four handled by one store instruction
+    const int chunk = lane & 7;     // 16-byte chunk of the 128-byte row
+    const uint32_t buf0 = stg + stg_buf * (32u * 128u);
+#pragma unroll 1
+    for (int c = c_begin; c < c_end; c += 32) {
+      uint32_t v[32];
+      float4 bia[8];
+      ptx::tmem_ld_32x32(taddr + static_cast<uint32_t>(c), v);
+      epilogue_bias_load(p, n0 + c, bia);
+      ptx::tmem_ld_wait();
+      if (c + 32 >= c_end) {
+        ptx::tc_fence_before();
+        release();
+      }
+      float f[32];
+      epilogue_math<EPI>(p, n0 + c, v, bia, f);
+      if (valid && p.pos != nullptr) {
+        const float4* q4 = reinterpret_cast<const float4*>(p.pos + static_cast<int64_t>(dst_s) * p.N + n0 + c);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 q = __ldg(q4 + j);
+          f[4 * j + 0] += q.x;
+          f[4 * j + 1] += q.y;
+          f[4 * j + 2] += q.z;
+          f[4 * j + 3] += q.w;
+        }
+      }
+      __syncwarp();  // previous chunk's reads of the staging tile are done
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        st_shared_v4(buf0 + my_row_off + (static_cast<uint32_t>(j ^ (lane & 7)) << 4),
+                     __float_as_uint(f[4 * j + 0]), __float_as_uint(f[4 * j + 1]),
+                     __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3]));
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = 4 * i + sub_row;  // row of the warp slab this lane now stores
+        const int64_t d = __shfl_sync(0xffffffffu, dst_row, r);
+        uint32_t w0, w1, w2, w3;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                     : "r"(buf0 + static_cast<uint32_t>(r) * 128u + (static_cast<uint32_t>(chunk ^ (r & 7)) << 4)));
+        if (d >= 0) {
+          uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<float*>(p.out) + d * p.ldo + n0 + c) + chunk;
+          *o = make_uint4(w0, w1, w2, w3);
+        }
+      }
+    }
   } else {
 #pragma unroll 1
     for (int c = c_begin; c < c_end; c += 32) {
