@@ -157,6 +157,10 @@ def main():
         run_reference_arm(args)
         return
 
+    # keep stdout to exactly one JSON line: NCCL prints its version banner to stdout at VERSION/INFO level
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
+
     import torch
     import torch.distributed as dist
 

@@ -123,3 +123,34 @@ def test_cpu_input_and_training_mode_raise():
     model.train()
     with pytest.raises(NotImplementedError):
         model(torch.zeros(1, 3, 224, 224, device="cuda"))
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_384_tiles_generalised_grid_against_oracle(precision):
+    """BASELINE.json configs[3]: 4-scale at 384x384 (g = 12, P = 144, N = 145).  The reference
+    hard-codes 7x7, so this case is 'parity unpinned': the oracle's
+    g-generalisation is the definition; the CUDA path must agree with it stage-wise."""
+    import duoformer_tcga_b200 as duo
+    from common import COMMON
+    from oracle import duoformer_oracle as orc
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    model = duo.MyModel_no_extra_params(depth=2, num_layers=4, num_patches=144, pretrained=False, **COMMON).eval()
+    sd = synth.synth_state_dict(model.state_dict(), seed=3)
+    model.load_state_dict(sd)
+    x = synth.synth_images(1, size=384, seed=11)
+    ocap = {}
+    with torch.no_grad():
+        yo = orc.forward_wo_extra(x, sd, 2, COMMON["num_heads"], 4, capture=ocap)
+    model = model.cuda().set_precision(precision)
+    cap = {}
+    model.vision_transformer._capture = cap
+    with torch.no_grad():
+        y = model(x.cuda()).float().cpu()
+    assert cap["tokens"].shape == (1, 144, 86, 768)
+    tol = TOL[precision]
+    for key, t in cap.items():
+        ref_t = ocap[key[:-3]][:, :, 0, :] if key.endswith("_s0") else ocap[key]
+        assert relerr(t, ref_t) < tol, key
+    assert relerr(y, yo) < tol
+    assert torch.equal(y.argmax(-1), yo.argmax(-1))
