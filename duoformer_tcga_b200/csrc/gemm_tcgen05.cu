@@ -3,22 +3,31 @@
 //   C[M,N] = A[M,K] * W[N,K]^T (+ fused epilogue), bf16 operands, fp32 accumulation in TMEM.
 //
 // Replaces every nn.Linear / 1x1 Conv2d of the reference forward (see include/duoformer_sm100.h
-// for the file:line map).  Structure (one CTA per SM, static round-robin tile scheduler, N
-// fastest so concurrently running CTAs share one A row-panel in L2):
+// for the file:line map).  Two kernels share one epilogue:
 //
-//   warp 0      TMA producer: A tile 128x64 and W tile BLOCK_Nx64 (both K-major, SWIZZLE_128B)
-//               into a kStages-deep shared-memory ring, completion on `full` mbarriers.
-//   warp 1      MMA issuer: one elected lane issues tcgen05.mma (UMMA 128 x BLOCK_N x 16),
-//               accumulating into one of two TMEM accumulator buffers; tcgen05.commit releases
-//               ring slots (`empty`) and publishes finished accumulators (`tmem_full`).
-//   warps 2..5  epilogue: tcgen05.ld the accumulator (one TMEM lane quarter per warp, one output
-//               row per thread), fuse bias / GELU(erf) / LayerScale, then
-//                 * bf16 outputs: rows staged in a per-warp double-buffered 128B-swizzled
-//                   shared-memory tile and written with TMA stores (full-line, coalesced);
+//   gemm_tcgen05_pair_kernel  (large problems) a cluster of two CTAs on one SM pair computes a
+//       256 x 256 tile with tcgen05.mma.cta_group::2 — see the block comment above that kernel;
+//   gemm_tcgen05_kernel       (small problems) one CTA per 128 x {128,256} tile.
+//
+// Common structure (persistent CTAs, static round-robin tile scheduler, N fastest so concurrently
+// running CTAs share one A row-panel in L2):
+//
+//   epilogue warps 0..3 (0..7 for the GELU epilogue of the pair kernel): tcgen05.ld the fp32
+//               accumulator (one TMEM lane quarter per warp, one output row per thread), fuse
+//               bias / GELU(erf) / LayerScale, then
+//                 * bf16 outputs: rows staged in a per-warp 128B-swizzled shared-memory tile and
+//                   written with TMA stores (full-line, coalesced);
 //                 * residual (X += ...): staged fp32 tile + TMA reduce-add into the fp32 residual
 //                   stream (the read-modify-write happens in L2, no SM-side loads);
-//                 * token scatter / fp32 / hi-lo split outputs: direct 16-byte global stores.
+//                 * token scatter: rows transposed through the staging tile, four complete
+//                   128-byte lines per store instruction;
+//                 * fp32 / hi-lo split outputs (fp32 mode only): direct 16-byte global stores.
 //               Double-buffered TMEM lets the epilogue of tile i overlap the MMAs of tile i+1.
+//   TMA warp    one lane streams A (128x64) and W (BLOCK_N x 64) tiles (K-major, SWIZZLE_128B)
+//               into a kStages-deep shared-memory ring, completion on `full` mbarriers.
+//   MMA warp    one lane issues tcgen05.mma (K = 16 per instruction) into one of two TMEM
+//               accumulator buffers; tcgen05.commit releases ring slots (`empty`) and publishes
+//               finished accumulators (`tmem_full`).
 //
 // split3 mode (fp32-accuracy path): A and W hold bf16 hi|lo halves; the K loop runs three
 // segments (Ah*Wh, Ah*Wl, Al*Wh) into the same accumulator.
