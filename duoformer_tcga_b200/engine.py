@@ -74,6 +74,77 @@ def _align(n: int, a: int = 1024) -> int:
     return (n + a - 1) // a * a
 
 
+def _scale_chunk_ops(X, b0, nb, buf, blocks, num_heads, scale, eps, precision, capture, attn_algo, live_only_last):
+    """Generator over the kernel launches of all scale blocks for images [b0, b0+nb): yields after
+    every launch so that two chunks can be issued interleaved on two streams (see scale_stage)."""
+    B, P, S, D = X.shape
+    fp32 = precision == "fp32"
+    kd = 2 if fp32 else 1
+    hidden = blocks[0]["fc1"][0].shape[0]
+    T = nb * P * S
+    hn_bytes = _align(T * kd * D * 2)
+    Xc = X[b0 : b0 + nb].view(T, D)
+    Hn = Workspace.view(buf, 0, (T, kd * D), torch.bfloat16)
+    QKV = Workspace.view(buf, hn_bytes, (T, 3 * D), torch.float32 if fp32 else torch.bfloat16)
+    HID = Workspace.view(buf, hn_bytes, (T, kd * hidden), torch.bfloat16)  # aliases QKV (dead after attention)
+    gelu = ops.EPI_GELU_SPLIT_BF16 if fp32 else ops.EPI_GELU_BF16
+    for i, blk in enumerate(blocks):
+        ops.layernorm(Xc, blk["n1w"], blk["n1b"], Hn, eps)
+        yield
+        ops.gemm(Hn, blk["qkv"][0], blk["qkv"][1], QKV, ops.EPI_F32 if fp32 else ops.EPI_BF16, split3=fp32)
+        yield
+        if live_only_last and i == len(blocks) - 1:
+            # Last scale block: only the scale token (s = 0) of every patch is consumed downstream
+            # (scale_attention.py:183-185), so K/V are needed for all tokens but the query,
+            # attention output, proj, MLP and both residual updates only for the s = 0 rows
+            # (SURVEY.md App. A.3).  X0 is the strided view of those rows inside X.
+            R = nb * P
+            X0 = Xc.view(R, S, D)[:, 0, :]
+            A0 = Workspace.view(buf, 0, (R, kd * D), torch.bfloat16)
+            ops.group_attention(QKV, A0, S, num_heads, scale, algo=attn_algo, q_rows=1)
+            yield
+            ops.gemm(A0, blk["proj"][0], blk["proj"][1], X0, ops.EPI_RESIDUAL_F32, gamma=blk["g1"], split3=fp32)
+            yield
+            ops.layernorm(X0, blk["n2w"], blk["n2b"], A0, eps)
+            yield
+            H0 = Workspace.view(buf, hn_bytes, (R, kd * hidden), torch.bfloat16)
+            ops.gemm(A0, blk["fc1"][0], blk["fc1"][1], H0, gelu, split3=fp32)
+            yield
+            ops.gemm(H0, blk["fc2"][0], blk["fc2"][1], X0, ops.EPI_RESIDUAL_F32, gamma=blk["g2"], split3=fp32)
+            yield
+            if capture is not None:
+                capture[f"scale_block_{i}_s0"] = X[:, :, 0, :].clone()
+            continue
+        ops.group_attention(QKV, Hn, S, num_heads, scale, algo=attn_algo)  # attention output re-uses Hn
+        yield
+        ops.gemm(Hn, blk["proj"][0], blk["proj"][1], Xc, ops.EPI_RESIDUAL_F32, gamma=blk["g1"], split3=fp32)
+        yield
+        ops.layernorm(Xc, blk["n2w"], blk["n2b"], Hn, eps)
+        yield
+        ops.gemm(Hn, blk["fc1"][0], blk["fc1"][1], HID, gelu, split3=fp32)
+        yield
+        ops.gemm(HID, blk["fc2"][0], blk["fc2"][1], Xc, ops.EPI_RESIDUAL_F32, gamma=blk["g2"], split3=fp32)
+        yield
+        if capture is not None:
+            capture[f"scale_block_{i}"] = X.clone()
+
+
+def _chunk_workspace_bytes(nb, P, S, D, hidden, fp32):
+    T = nb * P * S
+    kd = 2 if fp32 else 1
+    return _align(T * kd * D * 2) + _align(max(T * 3 * D * (4 if fp32 else 2), T * kd * hidden * 2))
+
+
+# Optional two-lane issue: the HBM-bound kernels (LayerNorm) of one half of the batch overlap the
+# tensor-bound GEMMs of the other half (LN CTAs need no shared memory, so they co-reside with the
+# persistent GEMM CTAs).  Lane 1 trails lane 0 by _LANE_OFFSET launches.  Measured on a
+# power-capped B200 (profiles/r01_notes.md): 1 217 vs 1 210 images/s — within noise, because the
+# step is limited by the 1 kW cap rather than by idle pipes — so it is OFF by default.
+OVERLAP_LANES = False
+_LANE_OFFSET = 1
+_side_streams: Dict[int, Tuple[torch.cuda.Stream, torch.cuda.Stream]] = {}
+
+
 def scale_stage(
     X: torch.Tensor,
     blocks: List[Dict],
@@ -93,54 +164,59 @@ def scale_stage(
     if not blocks:
         return X
     fp32 = precision == "fp32"
-    kd = 2 if fp32 else 1
     hidden = blocks[0]["fc1"][0].shape[0]
     tokens_per_image = P * S
     chunk_images = max(1, min(B, max_chunk_tokens // tokens_per_image))
     if capture is not None:
         chunk_images = B  # captures want whole-batch tensors after every block
-    Tc = chunk_images * tokens_per_image
-    # workspace: Hn | max(QKV, HID)
-    hn_bytes = _align(Tc * kd * D * 2)
-    qkv_bytes = Tc * 3 * D * (4 if fp32 else 2)
-    hid_bytes = Tc * kd * hidden * 2
-    buf = ws.get(hn_bytes + _align(max(qkv_bytes, hid_bytes)))
-    for b0 in range(0, B, chunk_images):
-        nb = min(chunk_images, B - b0)
-        T = nb * tokens_per_image
-        Xc = X[b0 : b0 + nb].view(T, D)
-        Hn = Workspace.view(buf, 0, (T, kd * D), torch.bfloat16)
-        QKV = Workspace.view(buf, hn_bytes, (T, 3 * D), torch.float32 if fp32 else torch.bfloat16)
-        HID = Workspace.view(buf, hn_bytes, (T, kd * hidden), torch.bfloat16)
-        for i, blk in enumerate(blocks):
-            ops.layernorm(Xc, blk["n1w"], blk["n1b"], Hn, eps)
-            ops.gemm(Hn, blk["qkv"][0], blk["qkv"][1], QKV, ops.EPI_F32 if fp32 else ops.EPI_BF16, split3=fp32)
-            if live_only_last and i == len(blocks) - 1:
-                # Last scale block: only the scale token (s = 0) of every patch is consumed downstream
-                # (scale_attention.py:183-185), so K/V are needed for all tokens but the query,
-                # attention output, proj, MLP and both residual updates only for the s = 0 rows
-                # (SURVEY.md App. A.3).  X0 is the strided view of those rows inside X.
-                R = nb * P
-                X0 = Xc.view(R, S, D)[:, 0, :]
-                A0 = Workspace.view(buf, 0, (R, kd * D), torch.bfloat16)
-                ops.group_attention(QKV, A0, S, num_heads, scale, algo=attn_algo, q_rows=1)
-                ops.gemm(A0, blk["proj"][0], blk["proj"][1], X0, ops.EPI_RESIDUAL_F32, gamma=blk["g1"], split3=fp32)
-                ops.layernorm(X0, blk["n2w"], blk["n2b"], A0, eps)
-                H0 = Workspace.view(buf, hn_bytes, (R, kd * hidden), torch.bfloat16)
-                ops.gemm(A0, blk["fc1"][0], blk["fc1"][1], H0,
-                         ops.EPI_GELU_SPLIT_BF16 if fp32 else ops.EPI_GELU_BF16, split3=fp32)
-                ops.gemm(H0, blk["fc2"][0], blk["fc2"][1], X0, ops.EPI_RESIDUAL_F32, gamma=blk["g2"], split3=fp32)
-                if capture is not None:
-                    capture[f"scale_block_{i}_s0"] = X[:, :, 0, :].clone()
-                continue
-            ops.group_attention(QKV, Hn, S, num_heads, scale, algo=attn_algo)  # attention output re-uses Hn
-            ops.gemm(Hn, blk["proj"][0], blk["proj"][1], Xc, ops.EPI_RESIDUAL_F32, gamma=blk["g1"], split3=fp32)
-            ops.layernorm(Xc, blk["n2w"], blk["n2b"], Hn, eps)
-            ops.gemm(Hn, blk["fc1"][0], blk["fc1"][1], HID,
-                     ops.EPI_GELU_SPLIT_BF16 if fp32 else ops.EPI_GELU_BF16, split3=fp32)
-            ops.gemm(HID, blk["fc2"][0], blk["fc2"][1], Xc, ops.EPI_RESIDUAL_F32, gamma=blk["g2"], split3=fp32)
-            if capture is not None:
-                capture[f"scale_block_{i}"] = X.clone()
+    two_lanes = OVERLAP_LANES and capture is None and B >= 2 and B * tokens_per_image >= (1 << 13)
+    if two_lanes:
+        chunk_images = max(1, min(chunk_images, (B + 1) // 2))
+    chunks = [(b0, min(chunk_images, B - b0)) for b0 in range(0, B, chunk_images)]
+    per_chunk = _chunk_workspace_bytes(chunk_images, P, S, D, hidden, fp32)
+    args = (blocks, num_heads, scale, eps, precision, capture, attn_algo, live_only_last)
+    if not two_lanes:
+        buf = ws.get(per_chunk)
+        for b0, nb in chunks:
+            for _ in _scale_chunk_ops(X, b0, nb, buf, *args):
+                pass
+        return X
+
+    buf = ws.get(2 * per_chunk)
+    bufs = (buf[:per_chunk], buf[per_chunk:])
+    dev = X.device.index if X.device.index is not None else torch.cuda.current_device()
+    if dev not in _side_streams:
+        _side_streams[dev] = (torch.cuda.Stream(device=X.device), torch.cuda.Stream(device=X.device))
+    lanes = _side_streams[dev]
+    main = torch.cuda.current_stream(X.device)
+    start = torch.cuda.Event()
+    start.record(main)
+    for s in lanes:
+        s.wait_event(start)
+    for c in range(0, len(chunks), 2):
+        gens = [_scale_chunk_ops(X, chunks[c][0], chunks[c][1], bufs[0], *args)]
+        if c + 1 < len(chunks):
+            gens.append(_scale_chunk_ops(X, chunks[c + 1][0], chunks[c + 1][1], bufs[1], *args))
+        alive = [True] * len(gens)
+
+        def step(k):
+            if alive[k]:
+                with torch.cuda.stream(lanes[k]):
+                    try:
+                        next(gens[k])
+                    except StopIteration:
+                        alive[k] = False
+
+        for _ in range(_LANE_OFFSET):
+            step(0)
+        while any(alive):
+            if len(gens) > 1:
+                step(1)
+            step(0)
+    for s in lanes:
+        done = torch.cuda.Event()
+        done.record(s)
+        main.wait_event(done)
     return X
 
 

@@ -154,3 +154,24 @@ def test_384_tiles_generalised_grid_against_oracle(precision):
         assert relerr(t, ref_t) < tol, key
     assert relerr(y, yo) < tol
     assert torch.equal(y.argmax(-1), yo.argmax(-1))
+
+
+def test_two_lane_overlap_option_gives_same_logits():
+    """engine.OVERLAP_LANES issues the two halves of the batch on two streams (LayerNorm of one
+    half overlapping the GEMMs of the other); results must not change."""
+    from duoformer_tcga_b200 import engine
+
+    gold = load_golden("wo4_d2")
+    case = gold["case"]
+    model = build_product(case)
+    model.load_state_dict(synth.synth_state_dict(model.state_dict(), seed=0))
+    model = model.cuda().eval()
+    x = synth.synth_images(5, seed=21).cuda()
+    with torch.no_grad():
+        y_off = model(x).float().cpu()
+        engine.OVERLAP_LANES = True
+        try:
+            y_on = model(x).float().cpu()
+        finally:
+            engine.OVERLAP_LANES = False
+    assert relerr(y_on, y_off) < 2e-3
