@@ -29,7 +29,8 @@ PER_GPU_BATCH = 256
 IMG = 224
 # Algorithmic FLOPs per image of the scale-block GEMMs: 24*T*D^2 per block
 T_TOKENS = 49 * 86
-WORKLOAD = "DuoFormer 4-scale (S=86), batch 256 per GPU, bf16 inference, synthetic 224x224 tiles"
+WORKLOAD = ("DuoFormer 4-scale (S=86) forward, MyModel_no_extra_params r50 depth 12 D 768 12 heads 10 classes "
+            "(random init), batch 256 per GPU, bf16 inference, synthetic 224x224 tiles")
 
 
 def measured_peaks():
@@ -255,7 +256,6 @@ def main():
             "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": world * B,
-                       "model": "MyModel_no_extra_params r50 4-scale depth12 D768 H12 ncls10, random init",
                        "parallelism": f"dp{world} (batch-sharded, NCCL all-gather of logits)" if world > 1 else "single GPU",
                        "l2": "no flush needed: per-step working set (3.3 GB fp32 tokens + 8 GB activations) >> 126 MB L2"},
             "gpu_launches": int(launches),

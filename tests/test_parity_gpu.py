@@ -175,3 +175,11 @@ def test_two_lane_overlap_option_gives_same_logits():
         finally:
             engine.OVERLAP_LANES = False
     assert relerr(y_on, y_off) < 2e-3
+
+
+def test_empty_batch_returns_empty_logits():
+    gold = load_golden("wo2_d12")
+    model = build_product(gold["case"]).cuda().eval()
+    with torch.no_grad():
+        y = model(torch.zeros(0, 3, 224, 224, device="cuda"))
+    assert tuple(y.shape) == (0, 10)
