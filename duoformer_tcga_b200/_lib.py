@@ -57,7 +57,10 @@ class GemmArgs(Structure):
         ("rows_per_group", c_int32),
         ("dest_rows_per_group", c_int32),
         ("pos_period", c_int32),
-        ("reserved", c_int32),
+        ("ln_eps", c_float),
+        ("ln_gamma", c_void_p),
+        ("ln_beta", c_void_p),
+        ("ln_out", c_void_p),
     ]
 
 

@@ -49,11 +49,12 @@ constexpr uint32_t kStagingBytesPerWarp = 2 * 32 * 128;  // two 32-row x 128 B b
 
 // Internal epilogue variants (superset of the ABI's DUO_EPI_*): staged TMA paths.
 constexpr int kEpiResidualTma = 100;  // DUO_EPI_RESIDUAL_F32 through TMA reduce-add
+constexpr int kEpiResidualLn = 101;   // residual update + fused LayerNorm of the updated rows (pair kernel)
 
 template <int EPI>
 struct EpiTraits {
   static constexpr bool kStagedBf16 = (EPI == DUO_EPI_BF16 || EPI == DUO_EPI_GELU_BF16);
-  static constexpr bool kStagedF32 = (EPI == kEpiResidualTma);
+  static constexpr bool kStagedF32 = (EPI == kEpiResidualTma || EPI == kEpiResidualLn);
   static constexpr bool kStaged = kStagedBf16 || kStagedF32;
 };
 
@@ -73,6 +74,9 @@ struct GemmParams {
   const float* bias;
   void* out;
   const float* gamma;
+  const float* ln_gamma;  // fused LayerNorm (kEpiResidualLn)
+  const float* ln_beta;
+  float ln_eps;
   const int32_t* row_map;
   const float* pos;
   int64_t M;
@@ -553,26 +557,227 @@ constexpr int kPairBlockN = 256;
 // EPI_WARPS epilogue warps: 4 (one per TMEM lane quarter, all 256 columns, double-buffered
 // staging) or 8 (two per quarter, 128 columns each, single-buffered staging — used when the
 // epilogue math is heavy, i.e. GELU).
-template <int EPI_WARPS>
+// FUSED_LN: the residual+LayerNorm epilogue needs four 4 KB staging buffers per warp (three for
+// the TMA-load -> modify -> TMA-store pipeline of X chunks, one for the bf16 LayerNorm output)
+// and three load mbarriers per warp; it gives up one ring stage for them.
+template <int EPI_WARPS, bool FUSED_LN = false>
 struct PairCfg {
-  static constexpr int kStages = 6;
+  static constexpr int kStages = FUSED_LN ? 5 : 6;
   static constexpr int kThreads = 64 + 32 * EPI_WARPS;
-  static constexpr int kStagingBufs = 8 / EPI_WARPS;
+  static constexpr int kStagingBufs = FUSED_LN ? 4 : 8 / EPI_WARPS;
   static constexpr uint32_t kABytes = kBlockM * kBlockK * 2;          // 16 KB (this CTA's 128 rows)
   static constexpr uint32_t kBBytes = (kPairBlockN / 2) * kBlockK * 2;  // 16 KB (this CTA's N half)
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
   static constexpr uint32_t kTmemCols = 2 * kPairBlockN;
-  static constexpr uint32_t kStagingBytes = 8 * 32 * 128;  // 32 KB: EPI_WARPS x kStagingBufs x 4 KB
-  static constexpr uint32_t kBarrierBytes = (2 * kStages + 4) * 8 + 8;
+  static constexpr uint32_t kStagingBytes = EPI_WARPS * kStagingBufs * 32 * 128;  // 32 KB (64 KB fused LN)
+  static constexpr uint32_t kBarrierBytes = (2 * kStages + 4) * 8 + 8 + (FUSED_LN ? EPI_WARPS * 3 * 8 : 0);
   static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kStagingBytes + kBarrierBytes + 1024;
 };
+
+// ---- residual update + fused LayerNorm (kEpiResidualLn, pair kernel, row-panel tile order) ------
+// Per-thread statistics of the row this thread owns, accumulated across the N tiles of the panel
+// (shifted by the row's first value to avoid cancellation in E[d^2] - E[d]^2), plus the parity
+// bits of the warp's three X-load mbarriers.
+struct LnRowStats {
+  float pivot = 0.f, s1 = 0.f, s2 = 0.f;
+  uint32_t ld_phase = 0;
+};
+
+__device__ __forceinline__ void ld_shared_v4(uint32_t addr, float4& r) {
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "r"(addr));
+}
+
+// X moves only through TMA (coalesced 128-byte lines): a 32-row x 32-column fp32 chunk is loaded
+// into one of three swizzled 4 KB buffers (two chunks ahead), updated IN PLACE by the thread that
+// owns each row, and stored back from the same buffer.
+//   pass 1 (every N tile):  x_new = x_old + gamma * (acc + bias); row statistics in registers.
+//   pass 2 (after the panel's last N tile): the freshly written rows are re-loaded (L2 hits),
+//   normalised and stored as the bf16 operand of the next GEMM (fourth buffer, 64 columns/store).
+template <typename ReleaseFn>
+__device__ __forceinline__ void epilogue_residual_ln(const GemmParams& p, const CUtensorMap* tmap_x,
+                                                     const CUtensorMap* tmap_ln, uint32_t taddr, int row0,
+                                                     int lane, int n0, bool last_n_tile, uint32_t stg,
+                                                     uint32_t ldbar, LnRowStats& st, ReleaseFn release) {
+  const uint32_t my_row_off = static_cast<uint32_t>(lane) * 128u;
+  const uint32_t x7 = static_cast<uint32_t>(lane & 7);
+  auto buf_addr = [&](int b) { return stg + static_cast<uint32_t>(b) * 4096u; };
+  auto issue_load = [&](int b, int col) {  // lane 0 only
+    ptx::mbar_arrive_expect_tx(ldbar + 8u * b, 4096u);
+    ptx::tma_load_2d(buf_addr(b), tmap_x, ldbar + 8u * b, col, row0);
+  };
+  auto wait_load = [&](int b) {
+    ptx::mbar_wait(ldbar + 8u * b, (st.ld_phase >> b) & 1u);
+    st.ld_phase ^= (1u << b);
+  };
+
+  // ---------------- pass 1 ----------------
+  if (lane == 0) {
+    ptx::tma_store_wait_read<0>();  // buffers 0 / 1 free (previous N tile's stores have read them)
+    issue_load(0, n0);
+    issue_load(1, n0 + 32);
+  }
+#pragma unroll 1
+  for (int c8 = 0; c8 < kPairBlockN / 32; ++c8) {
+    const int b = c8 % 3;
+    const int c = c8 * 32;
+    uint32_t v[32];
+    float4 bia[8];
+    ptx::tmem_ld_32x32(taddr + static_cast<uint32_t>(c), v);
+    epilogue_bias_load(p, n0 + c, bia);
+    wait_load(b);
+    ptx::tmem_ld_wait();
+    if (c8 == kPairBlockN / 32 - 1) {
+      ptx::tc_fence_before();
+      release();
+    }
+    const uint32_t rowbuf = buf_addr(b) + my_row_off;
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + bia[j].x;
+      f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bia[j].y;
+      f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bia[j].z;
+      f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bia[j].w;
+    }
+    if (p.gamma != nullptr) {
+      const float4* g4 = reinterpret_cast<const float4*>(p.gamma + n0 + c);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 g = __ldg(g4 + j);
+        f[4 * j + 0] *= g.x;
+        f[4 * j + 1] *= g.y;
+        f[4 * j + 2] *= g.z;
+        f[4 * j + 3] *= g.w;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 xo;
+      ld_shared_v4(rowbuf + ((static_cast<uint32_t>(j) ^ x7) << 4), xo);
+      f[4 * j + 0] += xo.x;
+      f[4 * j + 1] += xo.y;
+      f[4 * j + 2] += xo.z;
+      f[4 * j + 3] += xo.w;
+    }
+    if (n0 == 0 && c8 == 0) {
+      st.pivot = f[0];
+      st.s1 = 0.f;
+      st.s2 = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float d = f[j] - st.pivot;
+      st.s1 += d;
+      st.s2 = fmaf(d, d, st.s2);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      st_shared_v4(rowbuf + ((static_cast<uint32_t>(j) ^ x7) << 4), __float_as_uint(f[4 * j + 0]),
+                   __float_as_uint(f[4 * j + 1]), __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3]));
+    ptx::fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      ptx::tma_store_2d(tmap_x, buf_addr(b), n0 + c, row0);
+      ptx::tma_store_commit();
+      if (c8 + 2 < kPairBlockN / 32) {
+        ptx::tma_store_wait_read<1>();  // chunk c8-1's store (buffer (c8+2)%3) has read its buffer
+        issue_load((c8 + 2) % 3, n0 + c + 64);
+      }
+    }
+  }
+  if (!last_n_tile) return;
+
+  // ---------------- pass 2: LayerNorm of the updated rows ----------------
+  if (lane == 0) ptx::tma_store_wait<0>();  // this warp's X stores have completed (visible in L2)
+  __syncwarp();
+  const float inv_n = 1.0f / static_cast<float>(p.N);
+  const float m1 = st.s1 * inv_n;
+  const float mean = st.pivot + m1;
+  const float var = fmaxf(st.s2 * inv_n - m1 * m1, 0.f);
+  const float rstd = rsqrtf(var + p.ln_eps);
+  const float shift = -mean * rstd;
+  if (lane == 0) {
+    issue_load(0, 0);
+    issue_load(1, 32);
+  }
+  const int nchunks = p.N / 32;
+#pragma unroll 1
+  for (int q = 0; q < nchunks; ++q) {
+    const int b = q % 3;
+    const int h = q & 1;
+    const int col = q * 32;
+    wait_load(b);
+    const uint32_t rowbuf = buf_addr(b) + my_row_off;
+    const float4* g4 = reinterpret_cast<const float4*>(p.ln_gamma + col);
+    const float4* b4 = reinterpret_cast<const float4*>(p.ln_beta + col);
+    float y[32];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 xo;
+      ld_shared_v4(rowbuf + ((static_cast<uint32_t>(j) ^ x7) << 4), xo);
+      const float4 g = __ldg(g4 + j);
+      const float4 be = __ldg(b4 + j);
+      y[4 * j + 0] = fmaf(fmaf(xo.x, rstd, shift), g.x, be.x);
+      y[4 * j + 1] = fmaf(fmaf(xo.y, rstd, shift), g.y, be.y);
+      y[4 * j + 2] = fmaf(fmaf(xo.z, rstd, shift), g.z, be.z);
+      y[4 * j + 3] = fmaf(fmaf(xo.w, rstd, shift), g.w, be.w);
+    }
+    if (h == 0) {
+      if (lane == 0) ptx::tma_store_wait_read<0>();  // previous bf16 store has read buffer 3
+    }
+    __syncwarp();  // all lanes finished reading buffer b (it may be re-filled) / buffer 3 is free
+    const uint32_t obuf = buf_addr(3) + my_row_off;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      st_shared_v4(obuf + ((static_cast<uint32_t>(4 * h + j) ^ x7) << 4),
+                   pack_bf16x2(y[8 * j + 0], y[8 * j + 1]), pack_bf16x2(y[8 * j + 2], y[8 * j + 3]),
+                   pack_bf16x2(y[8 * j + 4], y[8 * j + 5]), pack_bf16x2(y[8 * j + 6], y[8 * j + 7]));
+    if (h == 1) {
+      ptx::fence_proxy_async();
+      __syncwarp();
+    }
+    if (lane == 0) {
+      if (h == 1) {
+        ptx::tma_store_2d(tmap_ln, buf_addr(3), col - 32, row0);
+        ptx::tma_store_commit();
+      }
+      if (q + 2 < nchunks) issue_load((q + 2) % 3, col + 64);
+    }
+  }
+}
+
+// Tile order of the pair kernels.  Default: tiles round-robin over pairs, N fastest.  ROW_PANEL:
+// a pair owns whole 256-row panels and walks their N tiles consecutively (needed when the
+// epilogue accumulates per-row statistics across the full row — fused LayerNorm).
+template <bool ROW_PANEL>
+__device__ __forceinline__ bool pair_tile(int64_t it, int64_t pair_idx, int64_t pair_stride, int nmb,
+                                          int nnb, int& m_blk, int& n_blk) {
+  if constexpr (ROW_PANEL) {
+    const int64_t r = it / nnb;
+    const int64_t mb = pair_idx + r * pair_stride;
+    if (mb >= nmb) return false;
+    m_blk = static_cast<int>(mb);
+    n_blk = static_cast<int>(it - r * nnb);
+    return true;
+  } else {
+    const int64_t tile = pair_idx + it * pair_stride;
+    if (tile >= static_cast<int64_t>(nmb) * nnb) return false;
+    m_blk = static_cast<int>(tile / nnb);
+    n_blk = static_cast<int>(tile - static_cast<int64_t>(m_blk) * nnb);
+    return true;
+  }
+}
 
 template <int EPI, int EPI_WARPS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg<EPI_WARPS>::kThreads, 1)
 gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
                          const __grid_constant__ CUtensorMap tmap_b,
-                         const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
-  using C = PairCfg<EPI_WARPS>;
+                         const __grid_constant__ CUtensorMap tmap_out,
+                         const __grid_constant__ CUtensorMap tmap_ln, const GemmParams p) {
+  constexpr bool kRowPanel = (EPI == kEpiResidualLn);
+  using C = PairCfg<EPI_WARPS, EPI == kEpiResidualLn>;
   using ET = EpiTraits<EPI>;
   constexpr int kStages = C::kStages;
   constexpr int BLOCK_N = kPairBlockN;
@@ -599,6 +804,10 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
     ptx::prefetch_tmap(&tmap_a);
     ptx::prefetch_tmap(&tmap_b);
     if constexpr (ET::kStaged) ptx::prefetch_tmap(&tmap_out);
+    if constexpr (EPI == kEpiResidualLn) {
+      ptx::prefetch_tmap(&tmap_ln);
+      for (int i = 0; i < EPI_WARPS * 3; ++i) ptx::mbar_init(tmem_ptr_smem + 8u + 8u * i, 1);  // X-load barriers
+    }
 #pragma unroll
     for (int s = 0; s < kStages; ++s) {
       ptx::mbar_init(full_bar(s), 1);   // leader's producer arms it with both CTAs' bytes
@@ -621,18 +830,16 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
   const int kseg_blocks = p.K / kBlockK;
   const int num_k_blocks = p.split3 ? 3 * kseg_blocks : kseg_blocks;
-  const int64_t num_tiles = static_cast<int64_t>(p.num_m_blocks) * p.num_n_blocks;  // pair tiles
   const int64_t pair_idx = blockIdx.x >> 1;
   const int64_t pair_stride = gridDim.x >> 1;
+  int m_blk = 0, n_blk = 0;
 
   if (warp_idx == kTmaWarp) {
     // ===================== TMA producer (both CTAs) =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int64_t tile = pair_idx; tile < num_tiles; tile += pair_stride) {
-        const int m_blk = static_cast<int>(tile / p.num_n_blocks);
-        const int n_blk = static_cast<int>(tile - static_cast<int64_t>(m_blk) * p.num_n_blocks);
+      for (int64_t it = 0; pair_tile<kRowPanel>(it, pair_idx, pair_stride, p.num_m_blocks, p.num_n_blocks, m_blk, n_blk); ++it) {
         const int a_row = m_blk * (2 * kBlockM) + static_cast<int>(cta_rank) * kBlockM;
         const int b_row = n_blk * BLOCK_N + static_cast<int>(cta_rank) * (BLOCK_N / 2);
         for (int kb = 0; kb < num_k_blocks; ++kb) {
@@ -667,7 +874,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int64_t tile = pair_idx; tile < num_tiles; tile += pair_stride) {
+      for (int64_t it = 0; pair_tile<kRowPanel>(it, pair_idx, pair_stride, p.num_m_blocks, p.num_n_blocks, m_blk, n_blk); ++it) {
         ptx::mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
@@ -706,9 +913,8 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
     uint32_t stg_buf = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int64_t tile = pair_idx; tile < num_tiles; tile += pair_stride) {
-      const int m_blk = static_cast<int>(tile / p.num_n_blocks);
-      const int n_blk = static_cast<int>(tile - static_cast<int64_t>(m_blk) * p.num_n_blocks);
+    LnRowStats ln_stats;
+    for (int64_t it = 0; pair_tile<kRowPanel>(it, pair_idx, pair_stride, p.num_m_blocks, p.num_n_blocks, m_blk, n_blk); ++it) {
       const int row0 = m_blk * (2 * kBlockM) + static_cast<int>(cta_rank) * kBlockM + quarter * 32;
       const int n0 = n_blk * BLOCK_N;
       ptx::mbar_wait(tmem_full_bar(acc), acc_phase);
@@ -716,6 +922,13 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const uint32_t taddr =
           tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
       const uint32_t leader_empty = ptx::mapa(tmem_empty_bar(acc), 0);
+      if constexpr (EPI == kEpiResidualLn) {
+        epilogue_residual_ln(p, &tmap_out, &tmap_ln, taddr, row0, lane, n0, n_blk == p.num_n_blocks - 1, stg,
+                             tmem_ptr_smem + 8u + 24u * static_cast<uint32_t>(warp_idx), ln_stats, [&]() {
+                               __syncwarp();
+                               if (lane == 0) ptx::mbar_arrive_cluster(leader_empty);
+                             });
+      } else
       epilogue_tile<EPI, C::kStagingBufs>(p, &tmap_out, taddr, row0, lane, n0, col_part * kColsPerWarp,
                                           (col_part + 1) * kColsPerWarp, stg, stg_buf,
                          [&]() {
@@ -819,9 +1032,9 @@ int dispatch_epi(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap
 }
 
 template <int EPI, int EPI_WARPS>
-int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const GemmParams& p,
-                cudaStream_t st) {
-  using C = PairCfg<EPI_WARPS>;
+int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tl,
+                const GemmParams& p, cudaStream_t st) {
+  using C = PairCfg<EPI_WARPS, EPI == kEpiResidualLn>;
   static bool configured = false;
   auto kfn = gemm_tcgen05_pair_kernel<EPI, EPI_WARPS>;
   if (!configured) {
@@ -829,29 +1042,32 @@ int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
                                   static_cast<int>(C::kSmemBytes)));
     configured = true;
   }
-  const int64_t tiles = static_cast<int64_t>(p.num_m_blocks) * p.num_n_blocks;
+  // work units: tiles (round-robin) or whole row panels (fused LayerNorm)
+  const int64_t units = EPI == kEpiResidualLn ? static_cast<int64_t>(p.num_m_blocks)
+                                              : static_cast<int64_t>(p.num_m_blocks) * p.num_n_blocks;
   const int pairs_max = device_sm_count() / 2;
-  const int pairs = static_cast<int>(tiles < pairs_max ? tiles : pairs_max);
-  kfn<<<2 * pairs, C::kThreads, C::kSmemBytes, st>>>(ta, tb, to, p);
+  const int pairs = static_cast<int>(units < pairs_max ? units : pairs_max);
+  kfn<<<2 * pairs, C::kThreads, C::kSmemBytes, st>>>(ta, tb, to, tl, p);
   DUO_LAUNCH_CHECK("gemm_tcgen05_pair_kernel");
   return DUO_OK;
 }
 
-int dispatch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
+int dispatch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tl,
                   const GemmParams& p, int epi, cudaStream_t st) {
   switch (epi) {
-    case DUO_EPI_BF16: return launch_pair<DUO_EPI_BF16, 4>(ta, tb, to, p, st);
+    case kEpiResidualLn: return launch_pair<kEpiResidualLn, 4>(ta, tb, to, tl, p, st);
+    case DUO_EPI_BF16: return launch_pair<DUO_EPI_BF16, 4>(ta, tb, to, to, p, st);
     case DUO_EPI_GELU_BF16: {
       static const int gelu_warps = [] { const char* e = getenv("DUO_GEMM_GELU_WARPS"); return (e && e[0] == '4') ? 4 : 8; }();
-      return gelu_warps == 8 ? launch_pair<DUO_EPI_GELU_BF16, 8>(ta, tb, to, p, st)
-                             : launch_pair<DUO_EPI_GELU_BF16, 4>(ta, tb, to, p, st);
+      return gelu_warps == 8 ? launch_pair<DUO_EPI_GELU_BF16, 8>(ta, tb, to, to, p, st)
+                             : launch_pair<DUO_EPI_GELU_BF16, 4>(ta, tb, to, to, p, st);
     }
-    case DUO_EPI_RESIDUAL_F32: return launch_pair<DUO_EPI_RESIDUAL_F32, 4>(ta, tb, to, p, st);
-    case kEpiResidualTma: return launch_pair<kEpiResidualTma, 4>(ta, tb, to, p, st);
-    case DUO_EPI_SCATTER_F32: return launch_pair<DUO_EPI_SCATTER_F32, 4>(ta, tb, to, p, st);
-    case DUO_EPI_F32: return launch_pair<DUO_EPI_F32, 4>(ta, tb, to, p, st);
-    case DUO_EPI_SPLIT_BF16: return launch_pair<DUO_EPI_SPLIT_BF16, 4>(ta, tb, to, p, st);
-    case DUO_EPI_GELU_SPLIT_BF16: return launch_pair<DUO_EPI_GELU_SPLIT_BF16, 8>(ta, tb, to, p, st);
+    case DUO_EPI_RESIDUAL_F32: return launch_pair<DUO_EPI_RESIDUAL_F32, 4>(ta, tb, to, to, p, st);
+    case kEpiResidualTma: return launch_pair<kEpiResidualTma, 4>(ta, tb, to, to, p, st);
+    case DUO_EPI_SCATTER_F32: return launch_pair<DUO_EPI_SCATTER_F32, 4>(ta, tb, to, to, p, st);
+    case DUO_EPI_F32: return launch_pair<DUO_EPI_F32, 4>(ta, tb, to, to, p, st);
+    case DUO_EPI_SPLIT_BF16: return launch_pair<DUO_EPI_SPLIT_BF16, 4>(ta, tb, to, to, p, st);
+    case DUO_EPI_GELU_SPLIT_BF16: return launch_pair<DUO_EPI_GELU_SPLIT_BF16, 8>(ta, tb, to, to, p, st);
     default: set_error("duo_gemm: unknown epilogue %d", epi); return DUO_ERR_INVALID;
   }
 }
@@ -920,17 +1136,34 @@ extern "C" int duo_gemm(const duo_gemm_args* a, duo_stream_t stream) {
   rc = make_tmap(&tb, a->W, a->N, kcols, a->ldw, block_n, 2);
   if (rc != DUO_OK) return rc;
   int epi = a->epilogue;
+  const bool want_ln = a->ln_out != nullptr;
+  if (want_ln) {
+    DUO_CHECK_ARG(epi == DUO_EPI_RESIDUAL_F32 && !a->split3 && a->ln_gamma && a->ln_beta,
+                  "duo_gemm: fused LayerNorm needs the bf16 residual epilogue and ln_gamma / ln_beta");
+    DUO_CHECK_ARG(a->N % 128 == 0 && a->N <= 1024, "duo_gemm: fused LayerNorm needs N %% 128 == 0, N <= 1024");
+    DUO_CHECK_ARG((reinterpret_cast<uintptr_t>(a->ln_out) & 15) == 0, "duo_gemm: ln_out must be 16-byte aligned");
+  }
+  const bool fused_ln = want_ln && use_pair;
+  if (fused_ln) epi = kEpiResidualLn;
   if (epi == DUO_EPI_RESIDUAL_F32 && residual_via_tma()) epi = kEpiResidualTma;
   if (epi == DUO_EPI_BF16 || epi == DUO_EPI_GELU_BF16) {
     rc = make_tmap(&to, a->out, a->M, a->N, a->ldo, 32, 2);
-  } else if (epi == kEpiResidualTma) {
+  } else if (epi == kEpiResidualTma || epi == kEpiResidualLn) {
     rc = make_tmap(&to, a->out, a->M, a->N, a->ldo, 32, 4);
   } else {
     to = ta;  // unused by the direct-store epilogues
   }
   if (rc != DUO_OK) return rc;
+  CUtensorMap tl = to;
+  if (fused_ln) {
+    rc = make_tmap(&tl, a->ln_out, a->M, a->N, a->N, 32, 2);
+    if (rc != DUO_OK) return rc;
+  }
 
   GemmParams p;
+  p.ln_gamma = a->ln_gamma;
+  p.ln_beta = a->ln_beta;
+  p.ln_eps = a->ln_eps;
   p.bias = a->bias;
   p.out = a->out;
   p.gamma = a->gamma;
@@ -947,7 +1180,10 @@ extern "C" int duo_gemm(const duo_gemm_args* a, duo_stream_t stream) {
   p.num_m_blocks = static_cast<int32_t>(m_blocks);
   p.num_n_blocks = use_pair ? a->N / kPairBlockN : a->N / block_n;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (use_pair) return dispatch_pair(ta, tb, to, p, epi, st);
-  if (block_n == 256) return dispatch_epi<256>(ta, tb, to, p, epi, st);
-  return dispatch_epi<128>(ta, tb, to, p, epi, st);
+  if (use_pair) return dispatch_pair(ta, tb, to, tl, p, epi, st);
+  rc = block_n == 256 ? dispatch_epi<256>(ta, tb, to, p, epi, st) : dispatch_epi<128>(ta, tb, to, p, epi, st);
+  if (rc != DUO_OK || !want_ln) return rc;
+  // small problems: unfused — LayerNorm of the updated rows as a second launch
+  return duo_layernorm(reinterpret_cast<const float*>(a->out), a->ln_gamma, a->ln_beta, a->ln_out, DUO_ACT_BF16,
+                       a->M, a->N, a->ldo, a->ln_eps, stream);
 }

@@ -74,56 +74,89 @@ def _align(n: int, a: int = 1024) -> int:
     return (n + a - 1) // a * a
 
 
+# bf16 mode: fuse each LayerNorm into the epilogue of the preceding residual GEMM (duo_gemm's ln_out).
+# Correct (tests/test_kernels_gpu.py, parity suite with the flag on) but OFF by default: the fused
+# epilogue must move X through a TMA-load -> modify -> TMA-store pipeline that the 32-64 KB of
+# staging shared memory cannot keep deep enough — measured 3.40 ms (proj+LN2) / 4.77 ms (fc2+LN1)
+# per launch against 1.35+0.76 / 3.62+0.76 ms unfused (profiles/r01_notes.md).
+FUSE_LAYERNORM = False
+
+
 def _scale_chunk_ops(X, b0, nb, buf, blocks, num_heads, scale, eps, precision, capture, attn_algo, live_only_last):
     """Generator over the kernel launches of all scale blocks for images [b0, b0+nb): yields after
-    every launch so that two chunks can be issued interleaved on two streams (see scale_stage)."""
+    every launch so that two chunks can be issued interleaved on two streams (see scale_stage).
+
+    bf16 mode, per block (5 launches): QKV GEMM, attention, proj GEMM (+residual +LayerNorm2),
+    fc1 GEMM (+GELU), fc2 GEMM (+residual +LayerNorm1 of the NEXT block); only block 0 needs a
+    standalone LayerNorm launch.  fp32 mode keeps the LayerNorm launches (split hi|lo outputs)."""
     B, P, S, D = X.shape
     fp32 = precision == "fp32"
+    fuse = FUSE_LAYERNORM and not fp32
     kd = 2 if fp32 else 1
     hidden = blocks[0]["fc1"][0].shape[0]
     T = nb * P * S
     hn_bytes = _align(T * kd * D * 2)
     Xc = X[b0 : b0 + nb].view(T, D)
-    Hn = Workspace.view(buf, 0, (T, kd * D), torch.bfloat16)
-    QKV = Workspace.view(buf, hn_bytes, (T, 3 * D), torch.float32 if fp32 else torch.bfloat16)
-    HID = Workspace.view(buf, hn_bytes, (T, kd * hidden), torch.bfloat16)  # aliases QKV (dead after attention)
+    Ha = Workspace.view(buf, 0, (T, kd * D), torch.bfloat16)             # LayerNorm outputs
+    Hb = Workspace.view(buf, hn_bytes, (T, kd * D), torch.bfloat16)      # attention output
+    QKV = Workspace.view(buf, 2 * hn_bytes, (T, 3 * D), torch.float32 if fp32 else torch.bfloat16)
+    HID = Workspace.view(buf, 2 * hn_bytes, (T, kd * hidden), torch.bfloat16)  # aliases QKV (dead after attention)
     gelu = ops.EPI_GELU_SPLIT_BF16 if fp32 else ops.EPI_GELU_BF16
+    L = len(blocks)
     for i, blk in enumerate(blocks):
-        ops.layernorm(Xc, blk["n1w"], blk["n1b"], Hn, eps)
+        last = i == L - 1
+        if i == 0 or not fuse:
+            ops.layernorm(Xc, blk["n1w"], blk["n1b"], Ha, eps)
+            yield
+        ops.gemm(Ha, blk["qkv"][0], blk["qkv"][1], QKV, ops.EPI_F32 if fp32 else ops.EPI_BF16, split3=fp32)
         yield
-        ops.gemm(Hn, blk["qkv"][0], blk["qkv"][1], QKV, ops.EPI_F32 if fp32 else ops.EPI_BF16, split3=fp32)
-        yield
-        if live_only_last and i == len(blocks) - 1:
+        if live_only_last and last:
             # Last scale block: only the scale token (s = 0) of every patch is consumed downstream
             # (scale_attention.py:183-185), so K/V are needed for all tokens but the query,
             # attention output, proj, MLP and both residual updates only for the s = 0 rows
             # (SURVEY.md App. A.3).  X0 is the strided view of those rows inside X.
             R = nb * P
             X0 = Xc.view(R, S, D)[:, 0, :]
-            A0 = Workspace.view(buf, 0, (R, kd * D), torch.bfloat16)
+            A0 = Workspace.view(buf, hn_bytes, (R, kd * D), torch.bfloat16)
+            N0 = Workspace.view(buf, 0, (R, kd * D), torch.bfloat16)
             ops.group_attention(QKV, A0, S, num_heads, scale, algo=attn_algo, q_rows=1)
             yield
-            ops.gemm(A0, blk["proj"][0], blk["proj"][1], X0, ops.EPI_RESIDUAL_F32, gamma=blk["g1"], split3=fp32)
-            yield
-            ops.layernorm(X0, blk["n2w"], blk["n2b"], A0, eps)
-            yield
-            H0 = Workspace.view(buf, hn_bytes, (R, kd * hidden), torch.bfloat16)
-            ops.gemm(A0, blk["fc1"][0], blk["fc1"][1], H0, gelu, split3=fp32)
+            if fuse:
+                ops.gemm(A0, blk["proj"][0], blk["proj"][1], X0, ops.EPI_RESIDUAL_F32, gamma=blk["g1"],
+                         ln_gamma=blk["n2w"], ln_beta=blk["n2b"], ln_out=N0, ln_eps=eps)
+                yield
+            else:
+                ops.gemm(A0, blk["proj"][0], blk["proj"][1], X0, ops.EPI_RESIDUAL_F32, gamma=blk["g1"], split3=fp32)
+                yield
+                ops.layernorm(X0, blk["n2w"], blk["n2b"], N0, eps)
+                yield
+            H0 = Workspace.view(buf, 2 * hn_bytes, (R, kd * hidden), torch.bfloat16)
+            ops.gemm(N0, blk["fc1"][0], blk["fc1"][1], H0, gelu, split3=fp32)
             yield
             ops.gemm(H0, blk["fc2"][0], blk["fc2"][1], X0, ops.EPI_RESIDUAL_F32, gamma=blk["g2"], split3=fp32)
             yield
             if capture is not None:
                 capture[f"scale_block_{i}_s0"] = X[:, :, 0, :].clone()
             continue
-        ops.group_attention(QKV, Hn, S, num_heads, scale, algo=attn_algo)  # attention output re-uses Hn
+        ops.group_attention(QKV, Hb, S, num_heads, scale, algo=attn_algo)
         yield
-        ops.gemm(Hn, blk["proj"][0], blk["proj"][1], Xc, ops.EPI_RESIDUAL_F32, gamma=blk["g1"], split3=fp32)
+        if fuse:
+            ops.gemm(Hb, blk["proj"][0], blk["proj"][1], Xc, ops.EPI_RESIDUAL_F32, gamma=blk["g1"],
+                     ln_gamma=blk["n2w"], ln_beta=blk["n2b"], ln_out=Ha, ln_eps=eps)
+            yield
+        else:
+            ops.gemm(Hb, blk["proj"][0], blk["proj"][1], Xc, ops.EPI_RESIDUAL_F32, gamma=blk["g1"], split3=fp32)
+            yield
+            ops.layernorm(Xc, blk["n2w"], blk["n2b"], Ha, eps)
+            yield
+        ops.gemm(Ha, blk["fc1"][0], blk["fc1"][1], HID, gelu, split3=fp32)
         yield
-        ops.layernorm(Xc, blk["n2w"], blk["n2b"], Hn, eps)
-        yield
-        ops.gemm(Hn, blk["fc1"][0], blk["fc1"][1], HID, gelu, split3=fp32)
-        yield
-        ops.gemm(HID, blk["fc2"][0], blk["fc2"][1], Xc, ops.EPI_RESIDUAL_F32, gamma=blk["g2"], split3=fp32)
+        if fuse and not last:
+            nxt = blocks[i + 1]
+            ops.gemm(HID, blk["fc2"][0], blk["fc2"][1], Xc, ops.EPI_RESIDUAL_F32, gamma=blk["g2"],
+                     ln_gamma=nxt["n1w"], ln_beta=nxt["n1b"], ln_out=Ha, ln_eps=eps)
+        else:
+            ops.gemm(HID, blk["fc2"][0], blk["fc2"][1], Xc, ops.EPI_RESIDUAL_F32, gamma=blk["g2"], split3=fp32)
         yield
         if capture is not None:
             capture[f"scale_block_{i}"] = X.clone()
@@ -132,7 +165,7 @@ def _scale_chunk_ops(X, b0, nb, buf, blocks, num_heads, scale, eps, precision, c
 def _chunk_workspace_bytes(nb, P, S, D, hidden, fp32):
     T = nb * P * S
     kd = 2 if fp32 else 1
-    return _align(T * kd * D * 2) + _align(max(T * 3 * D * (4 if fp32 else 2), T * kd * hidden * 2))
+    return 2 * _align(T * kd * D * 2) + _align(max(T * 3 * D * (4 if fp32 else 2), T * kd * hidden * 2))
 
 
 # Optional two-lane issue: the HBM-bound kernels (LayerNorm) of one half of the batch overlap the

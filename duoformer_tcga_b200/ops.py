@@ -65,8 +65,13 @@ def gemm(
     dest_rows_per_group: int = 0,
     pos: Optional[torch.Tensor] = None,
     pos_period: int = 0,
+    ln_gamma: Optional[torch.Tensor] = None,
+    ln_beta: Optional[torch.Tensor] = None,
+    ln_out: Optional[torch.Tensor] = None,
+    ln_eps: float = 1e-6,
 ) -> torch.Tensor:
-    """out = epilogue(A @ W.T + bias).  A [M,K] / W [N,K] bf16 (or [.,2K] split when split3)."""
+    """out = epilogue(A @ W.T + bias).  A [M,K] / W [N,K] bf16 (or [.,2K] split when split3).
+    ln_out (bf16 [M,N], with EPI_RESIDUAL_F32): also LayerNorm(updated out rows) in the same kernel."""
     assert A.dim() == 2 and W.dim() == 2 and A.dtype == torch.bfloat16 and W.dtype == torch.bfloat16
     assert A.stride(1) == 1 and W.stride(1) == 1 and out.stride(-1) == 1
     M = A.shape[0]
@@ -82,6 +87,9 @@ def gemm(
     a.split3 = 1 if split3 else 0
     a.epilogue = epilogue
     a.rows_per_group, a.dest_rows_per_group, a.pos_period = rows_per_group, dest_rows_per_group, pos_period
+    if ln_out is not None:
+        assert ln_out.dtype == torch.bfloat16 and ln_out.is_contiguous() and ln_out.shape[-1] == N
+        a.ln_gamma, a.ln_beta, a.ln_out, a.ln_eps = _ptr(ln_gamma), _ptr(ln_beta), _ptr(ln_out), float(ln_eps)
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() == N
     if row_map is not None:

@@ -93,7 +93,13 @@ typedef struct duo_gemm_args {
   int32_t rows_per_group;      /* SCATTER: source rows per image (h*w of the stage)        */
   int32_t dest_rows_per_group; /* SCATTER: token rows per image (P*S)                      */
   int32_t pos_period;          /* SCATTER: S                                               */
-  int32_t reserved;
+  float ln_eps;                /* fused LayerNorm epsilon                                  */
+  /* RESIDUAL_F32 + fused LayerNorm (optional, ln_out != NULL, bf16 operands, N <= 1024):     */
+  /* after out += gamma*(acc+bias), ln_out[M,N] (bf16, dense) = LayerNorm(out rows) — the      */
+  /* x = x + f(x); norm(x) pair of scale_attention.py:91-92 in one kernel.                     */
+  const float* ln_gamma;
+  const float* ln_beta;
+  void* ln_out;
 } duo_gemm_args;
 int duo_gemm(const duo_gemm_args* args, duo_stream_t stream);
 

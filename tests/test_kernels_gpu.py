@@ -220,3 +220,23 @@ def test_invalid_arguments_raise():
     with pytest.raises(RuntimeError):
         ops.layernorm(torch.zeros(4, 100, device="cuda"), torch.zeros(100, device="cuda"),
                       torch.zeros(100, device="cuda"), torch.zeros(4, 100, dtype=torch.bfloat16, device="cuda"), 1e-6)
+
+
+@pytest.mark.parametrize("M,K,with_gamma", [(256 * 60 + 77, 768, False), (256 * 60 + 77, 768, True), (256 * 52, 3072, False), (300, 768, True)])
+def test_gemm_residual_with_fused_layernorm(M, K, with_gamma):
+    """x = x + gamma*(A W^T + b); ln = LayerNorm(x) in one kernel (pair kernel, row-panel order);
+    small M falls back to GEMM + LayerNorm launches with the same result."""
+    N = 768
+    A = _gen((M, K), 111).to(torch.bfloat16)
+    W = _gen((N, K), 112, 0.05).to(torch.bfloat16)
+    bias = _gen((N,), 113)
+    gamma = _gen((N,), 114) if with_gamma else None
+    X = _gen((M, N), 115, 5.0) + 7.0  # non-zero row mean: exercises the shifted variance
+    lg, lb = _gen((N,), 116) + 1.0, _gen((N,), 117)
+    upd = A.float() @ W.float().t() + bias
+    Xr = X + (gamma * upd if with_gamma else upd)
+    lnr = torch.nn.functional.layer_norm(Xr, (N,), lg, lb, 1e-6)
+    ln = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    ops.gemm(A, W, bias, X, ops.EPI_RESIDUAL_F32, gamma=gamma, ln_gamma=lg, ln_beta=lb, ln_out=ln, ln_eps=1e-6)
+    assert relerr(X, Xr) < 1e-4
+    assert relerr(ln, lnr) < 8e-3

@@ -183,3 +183,23 @@ def test_empty_batch_returns_empty_logits():
     with torch.no_grad():
         y = model(torch.zeros(0, 3, 224, 224, device="cuda"))
     assert tuple(y.shape) == (0, 10)
+
+
+def test_fused_layernorm_option_gives_same_logits():
+    """engine.FUSE_LAYERNORM folds each LayerNorm into the preceding residual GEMM (opt-in)."""
+    from duoformer_tcga_b200 import engine
+
+    gold = load_golden("wo4_d2")
+    case = gold["case"]
+    model = build_product(case)
+    model.load_state_dict(synth.synth_state_dict(model.state_dict(), seed=0))
+    model = model.cuda().eval()
+    x = synth.synth_images(8, seed=23).cuda()  # 8 x 4214 rows: large enough for the pair kernel
+    with torch.no_grad():
+        y_off = model(x).float().cpu()
+        engine.FUSE_LAYERNORM = True
+        try:
+            y_on = model(x).float().cpu()
+        finally:
+            engine.FUSE_LAYERNORM = False
+    assert relerr(y_on, y_off) < 5e-3
