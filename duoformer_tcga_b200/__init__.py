@@ -18,43 +18,17 @@ from .scale_attention import (AttentionForPatch, AttentionForScale, MultiscaleFo
 __version__ = "0.1.0"
 
 
-def build_model(
-    depth=12,
-    patch_size=49,
-    embed_dim=256,
-    num_heads=6,
-    init_values=1e-5,
-    num_classes=100,
-    num_layers=4,
-    proj_dim=384,
-    model_ver="scaleformer",
-    pretrained=True,
-    freeze=True,
-):
-    """models/__init__.py:12-37."""
-    return MyModel(depth=depth, patch_size=patch_size, embed_dim=embed_dim, num_heads=num_heads,
-                   num_classes=num_classes, init_values=init_values, num_layers=num_layers, proj_dim=proj_dim,
-                   model_ver=model_ver, pretrained=pretrained, freeze=freeze)
+def build_model(depth=12, patch_size=49, embed_dim=256, num_heads=6, init_values=1e-5, num_classes=100,
+                num_layers=4, proj_dim=384, model_ver="scaleformer", pretrained=True, freeze=True):
+    """Factory of the "with extra params" DuoFormer; signature of the reference's models/__init__.py:12-24
+    (positional order and defaults kept), every argument forwarded by keyword (:25-37)."""
+    return MyModel(**dict(locals()))
 
 
-def build_model_no_extra_params(
-    depth=12,
-    embed_dim=256,
-    num_heads=6,
-    num_classes=100,
-    num_layers=4,
-    num_patches=49,
-    proj_dim=384,
-    mlp_ratio=4.0,
-    attn_drop_rate=0.0,
-    proj_drop_rate=0.0,
-    freeze_backbone=True,
-    backbone="r50",
-    pretrained=True,
-):
-    """models/__init__.py:40-70 (its `pretrained=` kwarg is honoured here, App. A D2)."""
-    return MyModel_no_extra_params(depth=depth, embed_dim=embed_dim, num_heads=num_heads, num_classes=num_classes,
-                                   num_layers=num_layers, num_patches=num_patches, proj_dim=proj_dim,
-                                   mlp_ratio=mlp_ratio, attn_drop_rate=attn_drop_rate,
-                                   proj_drop_rate=proj_drop_rate, freeze_backbone=freeze_backbone,
-                                   backbone=backbone, pretrained=pretrained)
+def build_model_no_extra_params(depth=12, embed_dim=256, num_heads=6, num_classes=100, num_layers=4,
+                                num_patches=49, proj_dim=384, mlp_ratio=4.0, attn_drop_rate=0.0,
+                                proj_drop_rate=0.0, freeze_backbone=True, backbone="r50", pretrained=True):
+    """Factory of the from-scratch MultiscaleFormer DuoFormer; signature of models/__init__.py:40-54.
+    The reference forwards `pretrained=` to a class that does not accept it (:53,:69, App. A D2);
+    here it is honoured (False = random-init trunk, no network)."""
+    return MyModel_no_extra_params(**dict(locals()))
