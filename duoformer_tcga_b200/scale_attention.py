@@ -169,6 +169,10 @@ class MultiscaleFormer(nn.Module):
         self.attn_algo = 0
         # skip work the reference computes but never consumes (last scale block: only s = 0 rows)
         self.dead_work_elimination = True
+        # precision of the 12 residual-free patch blocks (< 1 % of the FLOPs): None = same as
+        # `precision`; "fp32" runs them as 3-pass split GEMMs so that their bf16 rounding does not
+        # compound through the stack (no residual stream to absorb it).
+        self.patch_precision: Optional[str] = "fp32"
         self._capture: Optional[Dict[str, torch.Tensor]] = None
         self._ws: Optional[engine.Workspace] = None
 
@@ -207,6 +211,7 @@ class MultiscaleFormer(nn.Module):
                            attn_algo=self.attn_algo, live_only_last=self.dead_work_elimination)
         # patch stage: CLS + first scale token of every patch + pos_embed (scale_attention.py:183-193)
         N = P + 1
+        prec = self.patch_precision or prec
         kd = 2 if prec == "fp32" else 1
         Z = torch.empty(B * N, kd * D, dtype=torch.bfloat16, device=X.device)
         ops.assemble_patch_tokens(X, engine._f32(self.cls_token).view(-1), engine._f32(self.pos_embed).view(N, D), Z.view(B, N, kd * D))

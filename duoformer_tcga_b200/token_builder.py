@@ -91,16 +91,24 @@ class TrunkRunner:
         self._sig = None
         self._trunk: Optional[nn.Module] = None
         self.fused_ok: Optional[bool] = None  # None = not tried yet
+        # dtype of the cuDNN trunk in bf16 mode: "fp16" (default: same speed as bf16, 11-bit mantissa —
+        # the ~50 stacked convolutions otherwise contribute ~1e-2 of the 2e-2 bf16 error budget before
+        # the first transformer block), "bf16", or "fp32"
+        self.trunk_dtype = "fp16"
+
+    def _dtype(self, precision: str) -> torch.dtype:
+        if precision == "fp32":
+            return torch.float32
+        return {"fp16": torch.float16, "bf16": torch.bfloat16, "fp32": torch.float32}[self.trunk_dtype]
 
     def _packed_trunk(self, trunk: nn.Module, precision: str) -> nn.Module:
-        sig = engine.param_signature(trunk, precision)
+        dt = self._dtype(precision)
+        sig = engine.param_signature(trunk, precision + str(dt))
         if self._trunk is None or self._sig != sig:
             t = copy.deepcopy(trunk).eval().float()
-            if precision == "bf16":
-                _fold_batchnorm_(t)  # eval-mode BN -> scale/shift of the preceding conv (fp32, before the bf16 cast)
-                t = t.to(dtype=torch.bfloat16, memory_format=torch.channels_last)
-            else:
-                t = t.to(dtype=torch.float32, memory_format=torch.channels_last)
+            if dt != torch.float32:
+                _fold_batchnorm_(t)  # eval-mode BN -> scale/shift of the preceding conv (fp32, before the cast)
+            t = t.to(dtype=dt, memory_format=torch.channels_last)
             for p in t.parameters():
                 p.requires_grad_(False)
             self._trunk, self._sig = t, sig
@@ -109,13 +117,13 @@ class TrunkRunner:
     @torch.no_grad()
     def features(self, trunk: nn.Module, x: torch.Tensor, precision: str, by_scale: bool) -> Dict[int, torch.Tensor]:
         t = self._packed_trunk(trunk, precision)
-        dt = torch.bfloat16 if precision == "bf16" else torch.float32
+        dt = self._dtype(precision)
         x = x.to(dtype=dt).contiguous(memory_format=torch.channels_last)
         old_tf32 = torch.backends.cudnn.allow_tf32
         if precision == "fp32":
             torch.backends.cudnn.allow_tf32 = False
         try:
-            if precision == "bf16" and self.fused_ok is not False:
+            if dt != torch.float32 and self.fused_ok is not False:
                 # BN-folded bottlenecks through cuDNN's fused conv+bias(+add)+ReLU; verified once
                 # against the plain module path, with a permanent fallback if unsupported.
                 try:

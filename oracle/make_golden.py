@@ -25,6 +25,8 @@ CASES = {
     # BASELINE.json configs[0]: main_toy 2-scale, batch 2 (wo-extra kwargs, main_toy.py:84-98)
     "wo2_d12": dict(kind="wo", depth=12, num_layers=2, batch=2, backbone="r50", scale_token="random"),
     "wo4_d2": dict(kind="wo", depth=2, num_layers=4, batch=2, backbone="r50", scale_token="random"),
+    # BASELINE.json configs[1] model (4-scale, depth 12) at batch 2: the bench workload's architecture
+    "wo4_d12": dict(kind="wo", depth=12, num_layers=4, batch=2, backbone="r50", scale_token="random"),
     "wo3_d2": dict(kind="wo", depth=2, num_layers=3, batch=1, backbone="r50", scale_token="random"),
     "wo2_channel_d2": dict(kind="wo", depth=2, num_layers=2, batch=2, backbone="r50", scale_token="channel"),
     "wo2_swav_d2": dict(kind="wo", depth=2, num_layers=2, batch=2, backbone="r50_Swav", scale_token="random"),

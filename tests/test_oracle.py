@@ -10,7 +10,7 @@ from common import build_product, load_golden, oracle_forward, probe_values, rel
 from oracle import duoformer_oracle as orc
 from oracle import synth
 
-CASES = ["wo2_d12", "wo4_d2", "wo3_d2", "wo2_channel_d2", "wo2_swav_d2", "mm2_d12", "mm2_d1", "mm2_d2_b1"]
+CASES = ["wo2_d12", "wo4_d2", "wo4_d12", "wo3_d2", "wo2_channel_d2", "wo2_swav_d2", "mm2_d12", "mm2_d1", "mm2_d2_b1"]
 
 
 @pytest.mark.parametrize("name", CASES)

@@ -34,7 +34,7 @@ def _run(name, precision, capture=False):
 
 
 @pytest.mark.parametrize("precision", ["bf16", "fp32"])
-@pytest.mark.parametrize("name", ["wo2_d12", "wo4_d2", "wo3_d2", "wo2_channel_d2", "wo2_swav_d2", "mm2_d12", "mm2_d1", "mm2_d2_b1"])
+@pytest.mark.parametrize("name", ["wo2_d12", "wo4_d2", "wo4_d12", "wo3_d2", "wo2_channel_d2", "wo2_swav_d2", "mm2_d12", "mm2_d1", "mm2_d2_b1"])
 def test_logits_match_reference(name, precision):
     gold, case, sd, x, y, _ = _run(name, precision)
     ref = gold["logits"]
@@ -45,7 +45,7 @@ def test_logits_match_reference(name, precision):
 
 
 @pytest.mark.parametrize("precision", ["bf16", "fp32"])
-@pytest.mark.parametrize("name", ["wo2_d12", "wo4_d2", "mm2_d12"])
+@pytest.mark.parametrize("name", ["wo2_d12", "wo4_d2", "wo4_d12", "mm2_d12"])
 def test_stagewise_against_oracle(name, precision):
     torch.set_num_threads(os.cpu_count() or 1)
     gold, case, sd, x, y, cap = _run(name, precision, capture=True)
