@@ -203,3 +203,29 @@ def test_fused_layernorm_option_gives_same_logits():
         finally:
             engine.FUSE_LAYERNORM = False
     assert relerr(y_on, y_off) < 5e-3
+
+
+def test_full_bench_size_batch_256_properties():
+    """BASELINE.json configs[1] at its full size (4-scale, depth 12, batch 256): the oracle cannot run this
+    in seconds, so check size-independent properties — the two golden images embedded in the batch of 256
+    reproduce the reference logits, every image is independent of its batch neighbours (sub-batch and
+    permutation invariance), and all logits are finite."""
+    gold = load_golden("wo4_d12")
+    case = gold["case"]
+    model = build_product(case)
+    model.load_state_dict(synth.synth_state_dict(model.state_dict(), seed=gold["weight_seed"]))
+    model = model.cuda().eval()
+    xg = synth.synth_images(case["batch"], seed=gold["input_seed"])
+    x = torch.cat([synth.synth_images(100, seed=77), xg, synth.synth_images(154, seed=78)], dim=0).cuda()
+    with torch.no_grad():
+        y = model(x).float()
+        y_sub = model(x[96:104]).float()
+        perm = torch.randperm(256, generator=torch.Generator().manual_seed(1)).cuda()
+        y_perm = model(x[perm]).float()
+    assert y.shape == (256, 10) and torch.isfinite(y).all()
+    assert relerr(y[100:102], gold["logits"]) < 2e-2
+    assert torch.equal(y[100:102].argmax(-1).cpu(), gold["logits"].argmax(-1))
+    # the sm_100a kernels are bit-exact under permutation (tools/perm_check.py); cuDNN's layer4 convolution
+    # differs by one fp16 ulp depending on the position of an image in the batch, hence a small tolerance
+    assert relerr(y_sub, y[96:104]) < 5e-3
+    assert relerr(y_perm, y[perm]) < 5e-3
