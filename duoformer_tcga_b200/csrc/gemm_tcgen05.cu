@@ -431,7 +431,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const uint32_t tmem_base = *tmem_ptr_generic;
 
   const int kseg_blocks = p.K / kBlockK;
-  const int num_k_blocks = p.split3 ? 3 * kseg_blocks : kseg_blocks;
+  const int num_k_blocks = p.split3 == 1 ? 3 * kseg_blocks : (p.split3 == 2 ? 2 * kseg_blocks : kseg_blocks);
   const int64_t num_tiles = static_cast<int64_t>(p.num_m_blocks) * p.num_n_blocks;
 
   if (warp_idx == kTmaWarp) {
@@ -444,11 +444,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const int n_blk = static_cast<int>(tile - static_cast<int64_t>(m_blk) * p.num_n_blocks);
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           int a_k, b_k;
-          if (p.split3) {
+          if (p.split3 == 1) {  // Ah*Wh, Ah*Wl, Al*Wh
             const int seg = kb / kseg_blocks;
             const int r = kb - seg * kseg_blocks;
             a_k = (seg == 2 ? p.K : 0) + r * kBlockK;
             b_k = (seg == 1 ? p.K : 0) + r * kBlockK;
+          } else if (p.split3 == 2) {  // A is plain bf16: A*Wh, A*Wl
+            const int seg = kb / kseg_blocks;
+            const int r = kb - seg * kseg_blocks;
+            a_k = r * kBlockK;
+            b_k = seg * p.K + r * kBlockK;
           } else {
             a_k = b_k = kb * kBlockK;
           }
@@ -829,7 +834,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const uint32_t tmem_base = *tmem_ptr_generic;
 
   const int kseg_blocks = p.K / kBlockK;
-  const int num_k_blocks = p.split3 ? 3 * kseg_blocks : kseg_blocks;
+  const int num_k_blocks = p.split3 == 1 ? 3 * kseg_blocks : (p.split3 == 2 ? 2 * kseg_blocks : kseg_blocks);
   const int64_t pair_idx = blockIdx.x >> 1;
   const int64_t pair_stride = gridDim.x >> 1;
   int m_blk = 0, n_blk = 0;
@@ -844,11 +849,16 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const int b_row = n_blk * BLOCK_N + static_cast<int>(cta_rank) * (BLOCK_N / 2);
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           int a_k, b_k;
-          if (p.split3) {
+          if (p.split3 == 1) {  // Ah*Wh, Ah*Wl, Al*Wh
             const int seg = kb / kseg_blocks;
             const int r = kb - seg * kseg_blocks;
             a_k = (seg == 2 ? p.K : 0) + r * kBlockK;
             b_k = (seg == 1 ? p.K : 0) + r * kBlockK;
+          } else if (p.split3 == 2) {  // A is plain bf16: A*Wh, A*Wl
+            const int seg = kb / kseg_blocks;
+            const int r = kb - seg * kseg_blocks;
+            a_k = r * kBlockK;
+            b_k = seg * p.K + r * kBlockK;
           } else {
             a_k = b_k = kb * kBlockK;
           }
@@ -1103,8 +1113,10 @@ extern "C" int duo_gemm(const duo_gemm_args* a, duo_stream_t stream) {
                 (long long)a->M, a->N, a->K);
   DUO_CHECK_ARG(a->N % 128 == 0, "duo_gemm: N=%d must be a multiple of 128", a->N);
   DUO_CHECK_ARG(a->K % kBlockK == 0, "duo_gemm: K=%d must be a multiple of 64", a->K);
-  const int kcols = a->split3 ? 2 * a->K : a->K;
-  DUO_CHECK_ARG(a->lda >= kcols && a->ldw >= kcols && a->lda % 8 == 0 && a->ldw % 8 == 0,
+  DUO_CHECK_ARG(a->split3 >= 0 && a->split3 <= 2, "duo_gemm: split3=%d", a->split3);
+  const int kcols = a->split3 ? 2 * a->K : a->K;         // W columns
+  const int acols = a->split3 == 1 ? 2 * a->K : a->K;    // A columns
+  DUO_CHECK_ARG(a->lda >= acols && a->ldw >= kcols && a->lda % 8 == 0 && a->ldw % 8 == 0,
                 "duo_gemm: bad leading dims lda=%lld ldw=%lld", (long long)a->lda, (long long)a->ldw);
   DUO_CHECK_ARG((reinterpret_cast<uintptr_t>(a->A) & 15) == 0 &&
                     (reinterpret_cast<uintptr_t>(a->W) & 15) == 0 &&
@@ -1131,7 +1143,7 @@ extern "C" int duo_gemm(const duo_gemm_args* a, duo_stream_t stream) {
   }
 
   CUtensorMap ta, tb, to;
-  int rc = make_tmap(&ta, a->A, a->M, kcols, a->lda, kBlockM, 2);
+  int rc = make_tmap(&ta, a->A, a->M, acols, a->lda, kBlockM, 2);
   if (rc != DUO_OK) return rc;
   rc = make_tmap(&tb, a->W, a->N, kcols, a->ldw, block_n, 2);
   if (rc != DUO_OK) return rc;
@@ -1173,7 +1185,7 @@ extern "C" int duo_gemm(const duo_gemm_args* a, duo_stream_t stream) {
   p.ldo = a->ldo;
   p.N = a->N;
   p.K = a->K;
-  p.split3 = a->split3 ? 1 : 0;
+  p.split3 = a->split3;
   p.rows_per_group = a->rows_per_group;
   p.dest_rows_per_group = a->dest_rows_per_group;
   p.pos_period = a->pos_period;

@@ -41,7 +41,10 @@ __host__ __device__ constexpr int fma_smem_words_per_warp(int S, int kpl) {
   return (words + 3) & ~3;
 }
 
-template <typename Tin, int OUT_KIND, int KPL>
+// COOP = false: one warp per (group, head), several problems per CTA (small S).
+// COOP = true : the whole CTA works on ONE (group, head): K/V are staged once for all warps and the
+//               query rows are dealt round-robin to the warps (S >= 32: 4x the warps per staged byte).
+template <typename Tin, int OUT_KIND, int KPL, bool COOP>
 __global__ void group_attention_fma_kernel(const Tin* __restrict__ qkv, void* __restrict__ out,
                                            int64_t num_problems, int S, int H, float scale,
                                            int q_rows) {
@@ -54,23 +57,36 @@ __global__ void group_attention_fma_kernel(const Tin* __restrict__ qkv, void* __
   const int warps_per_cta = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int64_t prob = static_cast<int64_t>(blockIdx.x) * warps_per_cta + warp;
-  if (prob >= num_problems) return;
+  const int64_t prob = COOP ? static_cast<int64_t>(blockIdx.x)
+                            : static_cast<int64_t>(blockIdx.x) * warps_per_cta + warp;
+  if (prob >= num_problems) return;  // (COOP: never true — grid == num_problems)
   const int64_t g = prob / H;
   const int h = static_cast<int>(prob - g * H);
   const int D = H * kHeadDim;
   const int64_t ld = 3 * static_cast<int64_t>(D);
 
-  uint32_t* Vs = smem_words + static_cast<size_t>(warp) * fma_smem_words_per_warp<Tin>(S, KPL);
-  float* qs = reinterpret_cast<float*>(Vs + S * WPR);
-  float* ps = qs + 64;
-  uint32_t* Ks = reinterpret_cast<uint32_t*>(ps + KPL * 32);
+  uint32_t *Vs, *Ks;
+  float *qs, *ps;
+  if constexpr (COOP) {
+    Vs = smem_words;
+    Ks = Vs + S * WPR;
+    float* scratch = reinterpret_cast<float*>(smem_words + ((S * WPR + S * (WPR + 1) + 3) & ~3));
+    qs = scratch + warp * (64 + KPL * 32);
+    ps = qs + 64;
+  } else {
+    Vs = smem_words + static_cast<size_t>(warp) * fma_smem_words_per_warp<Tin>(S, KPL);
+    qs = reinterpret_cast<float*>(Vs + S * WPR);
+    ps = qs + 64;
+    Ks = reinterpret_cast<uint32_t*>(ps + KPL * 32);
+  }
 
   const Tin* base = qkv + (g * S) * ld + h * kHeadDim;
   // ---- stage K and V of this head ----
-  for (int r0 = 0; r0 < S; r0 += RPP) {
-    const int r = r0 + lane / VPR;
-    const int vec = lane % VPR;
+  const int stage_tid = COOP ? static_cast<int>(threadIdx.x) : lane;
+  const int stage_rows = (COOP ? static_cast<int>(blockDim.x) : 32) / VPR;
+  for (int r0 = 0; r0 < S; r0 += stage_rows) {
+    const int r = r0 + stage_tid / VPR;
+    const int vec = stage_tid % VPR;
     if (r < S) {
       const uint4 kv = __ldg(reinterpret_cast<const uint4*>(base + r * ld + D) + vec);
       const uint4 vv = __ldg(reinterpret_cast<const uint4*>(base + r * ld + 2 * D) + vec);
@@ -80,7 +96,7 @@ __global__ void group_attention_fma_kernel(const Tin* __restrict__ qkv, void* __
       vd[0] = vv.x; vd[1] = vv.y; vd[2] = vv.z; vd[3] = vv.w;
     }
   }
-  __syncwarp();
+  if constexpr (COOP) __syncthreads(); else __syncwarp();
 
   int krow[KPL];
 #pragma unroll
@@ -89,7 +105,7 @@ __global__ void group_attention_fma_kernel(const Tin* __restrict__ qkv, void* __
     krow[kk] = (j < S ? j : S - 1) * (WPR + 1);
   }
 
-  for (int i = 0; i < q_rows; ++i) {
+  for (int i = COOP ? warp : 0; i < q_rows; i += COOP ? warps_per_cta : 1) {
     // q row -> shared (fp32)
     {
       const Tin* qp = base + i * ld + 2 * lane;
@@ -195,6 +211,23 @@ __global__ void group_attention_fma_kernel(const Tin* __restrict__ qkv, void* __
 template <typename Tin, int OUT_KIND, int KPL>
 int launch_fma(const void* qkv, void* out, int64_t groups, int S, int H, float scale, int q_rows,
                cudaStream_t st) {
+  const int64_t problems = groups * H;
+  if (S >= 32 && q_rows > 1) {
+    // cooperative CTA per problem: one K/V copy shared by four warps
+    constexpr int WPR = ElemTraits<Tin>::kWordsPerRow;
+    const int warps = 4;
+    const size_t smem = (static_cast<size_t>((S * WPR + S * (WPR + 1) + 3) & ~3) + warps * (64 + KPL * 32)) * 4;
+    if (smem > 220 * 1024 || problems >= (int64_t(1) << 31)) {
+      set_error("duo_group_attention: S=%d / %lld problems unsupported", S, (long long)problems);
+      return DUO_ERR_INVALID;
+    }
+    auto kfn = group_attention_fma_kernel<Tin, OUT_KIND, KPL, true>;
+    DUO_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    kfn<<<static_cast<unsigned>(problems), warps * 32, smem, st>>>(reinterpret_cast<const Tin*>(qkv), out,
+                                                                   problems, S, H, scale, q_rows);
+    DUO_LAUNCH_CHECK("group_attention_fma_kernel");
+    return DUO_OK;
+  }
   const size_t per_warp = static_cast<size_t>(fma_smem_words_per_warp<Tin>(S, KPL)) * 4;
   int warps = 4;
   while (warps > 1 && per_warp * warps > 100 * 1024) warps >>= 1;
@@ -203,10 +236,9 @@ int launch_fma(const void* qkv, void* out, int64_t groups, int S, int H, float s
     set_error("duo_group_attention: S=%d needs %zu B of shared memory", S, smem);
     return DUO_ERR_INVALID;
   }
-  auto kfn = group_attention_fma_kernel<Tin, OUT_KIND, KPL>;
+  auto kfn = group_attention_fma_kernel<Tin, OUT_KIND, KPL, false>;
   DUO_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(smem)));
-  const int64_t problems = groups * H;
   const int64_t grid = (problems + warps - 1) / warps;
   if (grid >= (int64_t(1) << 31)) {
     set_error("duo_group_attention: too many groups");

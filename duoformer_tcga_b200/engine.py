@@ -261,31 +261,49 @@ def region_attention(
     scale: float,
     precision: str,
     out_f32: bool,
+    cls_only: bool = False,
 ) -> torch.Tensor:
     """One patch ("region") attention block without residual / norm / MLP:
     Z <- proj(softmax(q k^T * scale) v)   (scale_attention.py:195-209, multiscale_attn.py:205-219).
-    Z: bf16 [B*N, D] (or split [B*N, 2D]); returns the same kind, or fp32 [B*N, D] if out_f32."""
+
+    precision "bf16":  Z bf16 [B*N, D], everything bf16.
+              "fp32":  Z split [B*N, 2D]; 3-pass split GEMMs, fp32 qkv, fp32 FMA attention.
+              "mixed": Z split [B*N, 2D] (the tensor handed from block to block keeps ~16 mantissa
+                       bits, weights are split too), but qkv and the attention output are bf16 so the
+                       attention runs on the mma.sync kernel; proj multiplies the exact bf16
+                       attention output with the split weight (2-pass).
+    Returns the same kind as Z, or fp32 [rows, D] if out_f32."""
+    split_io = precision in ("fp32", "mixed")
     fp32 = precision == "fp32"
-    kd = 2 if fp32 else 1
+    kd_io = 2 if split_io else 1
+    kd_ao = 2 if fp32 else 1
     rows = Z.shape[0]
-    D = Z.shape[1] // kd
+    D = Z.shape[1] // kd_io
     dev = Z.device
     QKV = torch.empty(rows, 3 * D, dtype=torch.float32 if fp32 else torch.bfloat16, device=dev)
-    ops.gemm(Z, blk["qkv"][0], blk["qkv"][1], QKV, ops.EPI_F32 if fp32 else ops.EPI_BF16, split3=fp32)
-    AO = torch.empty(rows, kd * D, dtype=torch.bfloat16, device=dev)
-    ops.group_attention(QKV, AO, N, num_heads, scale)
+    ops.gemm(Z, blk["qkv"][0], blk["qkv"][1], QKV, ops.EPI_F32 if fp32 else ops.EPI_BF16, split3=1 if split_io else 0)
+    if cls_only:
+        # last patch block: only the CLS query row of every image reaches the head (scale_attention.py:341)
+        rows = rows // N
+        AO = torch.empty(rows, kd_ao * D, dtype=torch.bfloat16, device=dev)
+        ops.group_attention(QKV, AO, N, num_heads, scale, q_rows=1)
+    else:
+        AO = torch.empty(rows, kd_ao * D, dtype=torch.bfloat16, device=dev)
+        ops.group_attention(QKV, AO, N, num_heads, scale)
+    proj_split = 1 if fp32 else (2 if precision == "mixed" else 0)
     if out_f32:
         out = torch.empty(rows, D, dtype=torch.float32, device=dev)
-        ops.gemm(AO, blk["proj"][0], blk["proj"][1], out, ops.EPI_F32, split3=fp32)
+        ops.gemm(AO, blk["proj"][0], blk["proj"][1], out, ops.EPI_F32, split3=proj_split)
     else:
-        out = torch.empty(rows, kd * D, dtype=torch.bfloat16, device=dev)
-        ops.gemm(AO, blk["proj"][0], blk["proj"][1], out, ops.EPI_SPLIT_BF16 if fp32 else ops.EPI_BF16, split3=fp32)
+        out = torch.empty(rows, kd_io * D, dtype=torch.bfloat16, device=dev)
+        ops.gemm(AO, blk["proj"][0], blk["proj"][1], out, ops.EPI_SPLIT_BF16 if split_io else ops.EPI_BF16,
+                 split3=proj_split)
     return out
 
 
 def unsplit(t: torch.Tensor, precision: str) -> torch.Tensor:
     """Debug/capture helper: fp32 view of a bf16 / split-bf16 activation."""
-    if precision == "fp32" and t.dtype == torch.bfloat16:
+    if precision in ("fp32", "mixed") and t.dtype == torch.bfloat16:
         D = t.shape[-1] // 2
         return t[..., :D].float() + t[..., D:].float()
     return t.float()

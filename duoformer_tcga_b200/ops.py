@@ -58,7 +58,7 @@ def gemm(
     out: torch.Tensor,
     epilogue: int,
     *,
-    split3: bool = False,
+    split3=False,
     gamma: Optional[torch.Tensor] = None,
     row_map: Optional[torch.Tensor] = None,
     rows_per_group: int = 0,
@@ -76,15 +76,16 @@ def gemm(
     assert A.stride(1) == 1 and W.stride(1) == 1 and out.stride(-1) == 1
     M = A.shape[0]
     N = W.shape[0]
+    split3 = int(split3)  # 0 plain, 1 both operands split (hi|lo), 2 only W split (A exact bf16)
     K = W.shape[1] // 2 if split3 else W.shape[1]
-    assert A.shape[1] == W.shape[1], (A.shape, W.shape)
+    assert A.shape[1] == (2 * K if split3 == 1 else K), (A.shape, W.shape, split3)
     a = _lib.GemmArgs()
     a.A, a.W, a.bias, a.out = _ptr(A), _ptr(W), _ptr(bias), _ptr(out)
     a.gamma, a.row_map, a.pos = _ptr(gamma), _ptr(row_map), _ptr(pos)
     a.M, a.N, a.K = M, N, K
     a.lda, a.ldw = A.stride(0), W.stride(0)
     a.ldo = out.stride(-2) if out.dim() >= 2 else out.shape[-1]
-    a.split3 = 1 if split3 else 0
+    a.split3 = split3
     a.epilogue = epilogue
     a.rows_per_group, a.dest_rows_per_group, a.pos_period = rows_per_group, dest_rows_per_group, pos_period
     if ln_out is not None:
@@ -101,7 +102,7 @@ def gemm(
     _lib.check(_lib.load().duo_gemm(ctypes.byref(a), _stream()), "duo_gemm")
     if prof is not None:
         e1.record()
-        prof.append((e0, e1, 2.0 * M * N * K * (3 if split3 else 1), f"{N}x{K}:epi{epilogue}"))
+        prof.append((e0, e1, 2.0 * M * N * K * (3 if split3 == 1 else (2 if split3 == 2 else 1)), f"{N}x{K}:epi{epilogue}"))
     return out
 
 

@@ -212,24 +212,30 @@ class MultiscaleFormer(nn.Module):
         # patch stage: CLS + first scale token of every patch + pos_embed (scale_attention.py:183-193)
         N = P + 1
         prec = self.patch_precision or prec
-        kd = 2 if prec == "fp32" else 1
+        kd = 2 if prec in ("fp32", "mixed") else 1
         Z = torch.empty(B * N, kd * D, dtype=torch.bfloat16, device=X.device)
         ops.assemble_patch_tokens(X, engine._f32(self.cls_token).view(-1), engine._f32(self.pos_embed).view(N, D), Z.view(B, N, kd * D))
         if cap is not None:
             cap["patch_in"] = engine.unsplit(Z, prec).view(B, N, D)
         nblk = len(self.blocks)
+        cls_only = False
         for i, blk in enumerate(self.blocks):
             last = i == nblk - 1
-            Z = engine.region_attention(Z, blk.pack(prec), N, self.num_heads, blk.attn.scale, prec, out_f32=last)
+            cls_only = last and self.dead_work_elimination
+            Z = engine.region_attention(Z, blk.pack("bf16" if prec == "bf16" else "fp32"), N, self.num_heads, blk.attn.scale, prec, out_f32=last,
+                                        cls_only=cls_only)
             if cap is not None:
-                cap[f"patch_block_{i}"] = engine.unsplit(Z, prec).view(B, N, D).clone()
+                if cls_only:
+                    cap[f"patch_block_{i}_cls"] = Z.view(B, D).clone()
+                else:
+                    cap[f"patch_block_{i}"] = engine.unsplit(Z, prec).view(B, N, D).clone()
         if nblk == 0:
             Zf = engine.unsplit(Z, prec).contiguous()
         else:
             Zf = Z
         logits = torch.empty(B, self.head.out_features, dtype=torch.float32, device=X.device)
         # head on the CLS row; fc_norm is computed-and-discarded in the reference (:341-344)
-        ops.head(Zf, N * D, engine._f32(self.head.weight), engine._f32(self.head.bias), logits)
+        ops.head(Zf, D if cls_only else N * D, engine._f32(self.head.weight), engine._f32(self.head.bias), logits)
         return logits
 
     @torch.no_grad()

@@ -75,7 +75,8 @@ void duo_launch_count_reset(void);
  *                         model_wo_extra_params.py:252-299 via DUO_EPI_SCATTER_F32)
  *   residual / LayerScale scale_attention.py:91-92 ; multiscale_attn.py:282-285
  * Requirements: N % 128 == 0, K % 64 == 0, A/W 16-byte aligned, lda/ldw multiples of 8.
- * split3 != 0: A is split bf16 [M,2K], W is split bf16 [N,2K]; computes Ah*Wh + Ah*Wl + Al*Wh.
+ * split3 == 1: A is split bf16 [M,2K], W is split bf16 [N,2K]; computes Ah*Wh + Ah*Wl + Al*Wh.
+ * split3 == 2: A is plain bf16 [M,K] (exact), W is split bf16 [N,2K]; computes A*Wh + A*Wl.
  */
 typedef struct duo_gemm_args {
   const void* A;       /* bf16 [M, K] (or [M, 2K] when split3) row-major, leading dim lda */

@@ -20,12 +20,12 @@ for variant in sys.argv[1:] or ["default"]:
     model.set_precision("bf16")
     model._trunk_runner.trunk_dtype = "fp32" if "trunk32" in variant else ("bf16" if "trunkbf16" in variant else "fp16")
     model._trunk_runner._trunk = None
-    model.vision_transformer.patch_precision = None if "patchbf16" in variant else "fp32"
+    model.vision_transformer.patch_precision = None if "patchbf16" in variant else ("mixed" if "patchmixed" in variant else "fp32")
     cap = {}
     model.vision_transformer._capture = cap
     with torch.no_grad():
         y = model(x.cuda()).float().cpu()
     print("==", variant, "logits rel err", round(relerr(y, yo), 5))
     for k, t in cap.items():
-        ref = ocap[k[:-3]][:, :, 0, :] if k.endswith("_s0") else ocap[k]
+        ref = ocap[k[:-3]][:, :, 0, :] if k.endswith("_s0") else (ocap[k[:-4]][:, 0, :] if k.endswith("_cls") else ocap[k])
         print(f"   {k:18s} {relerr(t, ref):.4e}")

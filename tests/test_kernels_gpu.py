@@ -240,3 +240,15 @@ def test_gemm_residual_with_fused_layernorm(M, K, with_gamma):
     ops.gemm(A, W, bias, X, ops.EPI_RESIDUAL_F32, gamma=gamma, ln_gamma=lg, ln_beta=lb, ln_out=ln, ln_eps=1e-6)
     assert relerr(X, Xr) < 1e-4
     assert relerr(ln, lnr) < 8e-3
+
+
+def test_gemm_split_mode_2_plain_A_split_W():
+    """split3 == 2: exact bf16 activations times hi|lo-split weights (A*Wh + A*Wl)."""
+    M, N, K = 700, 768, 768
+    A = _gen((M, K), 121).to(torch.bfloat16)
+    W = _gen((N, K), 122, 0.05)
+    bias = _gen((N,), 123)
+    ref = (A.double() @ W.double().t() + bias.double()).float()
+    out = torch.empty(M, N, dtype=torch.float32, device="cuda")
+    ops.gemm(A, ops.split_weight(W), bias, out, ops.EPI_F32, split3=2)
+    assert relerr(out, ref) < 2e-5

@@ -57,6 +57,8 @@ def test_stagewise_against_oracle(name, precision):
     for key, t in cap.items():
         if key.endswith("_s0"):  # last scale block, live rows only (dead-work elimination)
             ref_t = ocap[key[:-3]][:, :, 0, :]
+        elif key.endswith("_cls"):  # last patch block, CLS row only
+            ref_t = ocap[key[:-4]][:, 0, :]
         else:
             assert key in ocap, key
             ref_t = ocap[key]
@@ -150,7 +152,8 @@ def test_384_tiles_generalised_grid_against_oracle(precision):
     assert cap["tokens"].shape == (1, 144, 86, 768)
     tol = TOL[precision]
     for key, t in cap.items():
-        ref_t = ocap[key[:-3]][:, :, 0, :] if key.endswith("_s0") else ocap[key]
+        ref_t = (ocap[key[:-3]][:, :, 0, :] if key.endswith("_s0") else
+                 ocap[key[:-4]][:, 0, :] if key.endswith("_cls") else ocap[key])
         assert relerr(t, ref_t) < tol, key
     assert relerr(y, yo) < tol
     assert torch.equal(y.argmax(-1), yo.argmax(-1))
