@@ -257,6 +257,8 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": world * B,
                        "parallelism": f"dp{world} (batch-sharded, NCCL all-gather of logits)" if world > 1 else "single GPU",
+                       "precision": "bf16 operands / fp32 accumulate, fp32 residual stream (scale blocks, 98% of FLOPs); "
+                                    "fp16 cuDNN trunk; patch blocks as 3-pass split-bf16 GEMMs (DESIGN.md precision policy)",
                        "l2": "no flush needed: per-step working set (3.3 GB fp32 tokens + 8 GB activations) >> 126 MB L2"},
             "gpu_launches": int(launches),
             "clocks": clocks,
