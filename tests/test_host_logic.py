@@ -166,3 +166,25 @@ def test_pack_cache_invalidates_on_parameter_update():
     assert p2 is not p1 and not torch.equal(p1["qkv"][0], p2["qkv"][0])
     p3 = blk.pack("fp32")
     assert p3["qkv"][0].shape == (2304, 1536)
+
+
+def test_token_row_maps_properties_over_random_grids():
+    """hypothesis: for any patch grid g and 1..4 scales the scatter maps tile the non-scale-token rows
+    exactly once, and every pixel lands in the patch that geometrically contains it."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=25, deadline=None)
+    @given(g=st.integers(min_value=1, max_value=13), num_layers=st.integers(min_value=1, max_value=4))
+    def check(g, num_layers):
+        S = index_tables.num_scale_tokens(num_layers)
+        maps = index_tables.token_row_maps(num_layers, g)
+        rows = torch.cat(list(maps.values())).long()
+        assert rows.numel() == g * g * (S - 1) == rows.unique().numel()
+        for k, m in maps.items():
+            w = 2 ** (3 - k)
+            G = g * w
+            ys, xs = torch.meshgrid(torch.arange(G), torch.arange(G), indexing="ij")
+            patch_of_pixel = (ys // w) * g + (xs // w)
+            assert torch.equal((m.long() // S).view(G, G), patch_of_pixel)
+
+    check()

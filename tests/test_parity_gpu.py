@@ -232,3 +232,39 @@ def test_full_bench_size_batch_256_properties():
     # differs by one fp16 ulp depending on the position of an image in the batch, hence a small tolerance
     assert relerr(y_sub, y[96:104]) < 5e-3
     assert relerr(y_perm, y[perm]) < 5e-3
+
+
+def test_cuda_graph_replay_matches_eager_and_is_faster_at_small_batch():
+    """The whole forward (cuDNN trunk + every sm_100a kernel) is CUDA-graph capturable."""
+    import time
+
+    from duoformer_tcga_b200.graphs import GraphedForward
+
+    gold = load_golden("wo2_d12")
+    case = gold["case"]
+    model = build_product(case)
+    model.load_state_dict(synth.synth_state_dict(model.state_dict(), seed=0))
+    model = model.cuda().eval()
+    x = synth.synth_images(2, seed=gold["input_seed"]).cuda()
+    with torch.no_grad():
+        y_eager = model(x).float()
+    g = GraphedForward(model, x)
+    y_graph = g(x).float()
+    assert relerr(y_graph, y_eager) < 1e-5
+    x2 = synth.synth_images(2, seed=99).cuda()
+    with torch.no_grad():
+        assert relerr(g(x2).float(), model(x2).float()) < 1e-5
+    assert relerr(y_graph.cpu(), gold["logits"]) < 2e-2
+
+    def lat(fn, n=20):
+        fn(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / n * 1e3
+
+    with torch.no_grad():
+        t_eager, t_graph = lat(lambda: model(x)), lat(lambda: g(x))
+    print(f"batch-2 2-scale forward latency: eager {t_eager:.2f} ms, CUDA graph {t_graph:.2f} ms")
+    assert t_graph < t_eager
