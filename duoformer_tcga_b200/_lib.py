@@ -16,7 +16,7 @@ CSRC_DIR = os.path.join(_HERE, "csrc")
 
 # enums of include/duoformer_sm100.h
 EPI_BF16, EPI_GELU_BF16, EPI_RESIDUAL_F32, EPI_SCATTER_F32, EPI_F32, EPI_SPLIT_BF16, EPI_GELU_SPLIT_BF16 = range(7)
-ACT_BF16, ACT_SPLIT, ACT_F32 = range(3)
+ACT_BF16, ACT_SPLIT, ACT_F32, ACT_F16 = range(4)
 
 # every symbol include/duoformer_sm100.h declares
 EXPORTED_SYMBOLS = (
@@ -32,6 +32,8 @@ EXPORTED_SYMBOLS = (
     "duo_assemble_patch_tokens",
     "duo_head",
     "duo_convert",
+    "duo_im2col3x3",
+    "duo_pool_to_slice",
 )
 
 
@@ -58,6 +60,8 @@ class GemmArgs(Structure):
         ("dest_rows_per_group", c_int32),
         ("pos_period", c_int32),
         ("ln_eps", c_float),
+        ("relu", c_int32),
+        ("reserved", c_int32),
         ("ln_gamma", c_void_p),
         ("ln_beta", c_void_p),
         ("ln_out", c_void_p),
@@ -109,6 +113,10 @@ def load() -> ctypes.CDLL:
     lib.duo_head.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]
     lib.duo_convert.restype = c_int32
     lib.duo_convert.argtypes = [c_void_p, c_int64, c_void_p, c_int32, c_int64, c_int32, c_void_p]
+    lib.duo_im2col3x3.restype = c_int32
+    lib.duo_im2col3x3.argtypes = [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]
+    lib.duo_pool_to_slice.restype = c_int32
+    lib.duo_pool_to_slice.argtypes = [c_void_p, c_int32, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]
     _lib = lib
     return lib
 

@@ -77,6 +77,7 @@ struct GemmParams {
   const float* ln_gamma;  // fused LayerNorm (kEpiResidualLn)
   const float* ln_beta;
   float ln_eps;
+  int32_t relu;           // BF16 / F32 epilogues: clamp at zero
   const int32_t* row_map;
   const float* pos;
   int64_t M;
@@ -113,6 +114,12 @@ __device__ __forceinline__ void epilogue_math(const GemmParams& p, int col, cons
   if constexpr (EPI == DUO_EPI_GELU_BF16) {
 #pragma unroll
     for (int j = 0; j < 32; j += 2) gelu_erf_sigmoid_x2(f[j], f[j + 1]);
+  }
+  if constexpr (EPI == DUO_EPI_BF16 || EPI == DUO_EPI_F32) {
+    if (p.relu) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+    }
   }
   if constexpr (EPI == DUO_EPI_GELU_SPLIT_BF16) {
 #pragma unroll
@@ -1176,6 +1183,7 @@ extern "C" int duo_gemm(const duo_gemm_args* a, duo_stream_t stream) {
   p.ln_gamma = a->ln_gamma;
   p.ln_beta = a->ln_beta;
   p.ln_eps = a->ln_eps;
+  p.relu = a->relu;
   p.bias = a->bias;
   p.out = a->out;
   p.gamma = a->gamma;

@@ -17,6 +17,7 @@ from .multi_vision_transformer import MultiscaleTransformer
 from .projection_head import (Channel_Projector_All, Channel_Projector_layer1, Channel_Projector_layer2,
                               Channel_Projector_layer3, Projection)
 from .scale_attention import _check_eval
+from .channel_branch import ChannelBranch
 from .token_builder import TokenBuilder, TrunkRunner
 
 
@@ -67,6 +68,7 @@ class MyModel(nn.Module):
                 param.requires_grad = False
         self._trunk_runner = TrunkRunner()
         self._token_builder = TokenBuilder()
+        self._channel_branch = None
 
     @property
     def precision(self) -> str:
@@ -85,7 +87,12 @@ class MyModel(nn.Module):
 
     @torch.no_grad()
     def channel_branch(self, feats) -> torch.Tensor:
-        """[B, P, D] fp32 channel token (model.py:279-289; cuDNN convs)."""
+        """[B, P, D] fp32 channel token (model.py:279-289).  bf16 mode: im2col + tcgen05 GEMMs
+        (channel_branch.py); fp32 mode: the fp32 cuDNN modules with TF32 off."""
+        if self.precision == "bf16":
+            if self._channel_branch is None:
+                self._channel_branch = ChannelBranch(self.chann_proj1, self.chann_proj2, self.chann_proj_all)
+            return self._channel_branch(feats)
         dt = torch.float32
         old = torch.backends.cudnn.allow_tf32
         if self.precision == "fp32":

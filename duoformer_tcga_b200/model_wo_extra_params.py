@@ -17,6 +17,7 @@ from .projection_head import (Channel_Projector_All, Channel_Projector_layer1, C
                               Channel_Projector_layer3, Projection)
 from .resnet50ssl import resnet50FeatureExtractor
 from .scale_attention import MultiscaleFormer, _check_eval
+from .channel_branch import ChannelBranch
 from .token_builder import TokenBuilder, TrunkRunner
 
 
@@ -95,7 +96,7 @@ class MyModel_no_extra_params(nn.Module):
         # index tables are generated on device per patch grid (App. A D8, D15) — see index_tables.py
         self._trunk_runner = TrunkRunner()
         self._token_builder = TokenBuilder()
-        self._channel_runner = TrunkRunner()
+        self._channel_branch = None
 
     # ---- precision switch (additive API) ---------------------------------------------------
     @property
@@ -118,7 +119,12 @@ class MyModel_no_extra_params(nn.Module):
 
     @torch.no_grad()
     def channel_branch(self, feats) -> torch.Tensor:
-        """Channel token [B, P, D] fp32 from the four stage maps (model_wo_extra_params.py:236-248)."""
+        """Channel token [B, P, D] fp32 from the four stage maps (model_wo_extra_params.py:236-248).
+        bf16 mode: im2col + tcgen05 GEMMs (channel_branch.py); fp32 mode: fp32 cuDNN modules."""
+        if self.precision == "bf16":
+            if self._channel_branch is None:
+                self._channel_branch = ChannelBranch(self.chann_proj1, self.chann_proj2, self.chann_proj_all)
+            return self._channel_branch(feats)
         dt = torch.float32
         with torch.autocast("cuda", enabled=False):
             c0 = self.chann_proj1(feats[0].to(dt))

@@ -69,6 +69,7 @@ def gemm(
     ln_beta: Optional[torch.Tensor] = None,
     ln_out: Optional[torch.Tensor] = None,
     ln_eps: float = 1e-6,
+    relu: bool = False,
 ) -> torch.Tensor:
     """out = epilogue(A @ W.T + bias).  A [M,K] / W [N,K] bf16 (or [.,2K] split when split3).
     ln_out (bf16 [M,N], with EPI_RESIDUAL_F32): also LayerNorm(updated out rows) in the same kernel."""
@@ -86,6 +87,7 @@ def gemm(
     a.lda, a.ldw = A.stride(0), W.stride(0)
     a.ldo = out.stride(-2) if out.dim() >= 2 else out.shape[-1]
     a.split3 = split3
+    a.relu = 1 if relu else 0
     a.epilogue = epilogue
     a.rows_per_group, a.dest_rows_per_group, a.pos_period = rows_per_group, dest_rows_per_group, pos_period
     if ln_out is not None:
@@ -216,6 +218,33 @@ def convert(inp: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
         _lib.load().duo_convert(_ptr(inp), inp.stride(0), _ptr(out), kind, rows, cols, _stream()), "duo_convert"
     )
     return out
+
+
+_IN_KIND = {torch.bfloat16: _lib.ACT_BF16, torch.float16: _lib.ACT_F16, torch.float32: ACT_F32}
+
+
+def im2col3x3(x_nhwc: torch.Tensor, stride: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """NHWC [B,H,W,C] (bf16/f16/f32, contiguous) -> bf16 [B*Ho*Wo, 9*C] patches of a 3x3 / pad 1 / stride s conv."""
+    assert x_nhwc.dim() == 4 and x_nhwc.is_contiguous()
+    B, H, W, C = x_nhwc.shape
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    if out is None:
+        out = torch.empty(B * Ho * Wo, 9 * C, dtype=torch.bfloat16, device=x_nhwc.device)
+    assert out.is_contiguous() and out.shape == (B * Ho * Wo, 9 * C) and out.dtype == torch.bfloat16
+    _lib.check(_lib.load().duo_im2col3x3(_ptr(x_nhwc), _IN_KIND[x_nhwc.dtype], _ptr(out), B, H, W, C, stride, _stream()),
+               "duo_im2col3x3")
+    return out
+
+
+def pool_to_slice(x_nhwc: torch.Tensor, out_slice: torch.Tensor, pool: int) -> torch.Tensor:
+    """2x2 max-pool (pool=2) or copy (pool=1) of NHWC [B,H,W,C] into out_slice = wide[:, c0:c0+C]
+    (a bf16 [B*Ho*Wo, C] column slice of a wider contiguous matrix)."""
+    assert x_nhwc.dim() == 4 and x_nhwc.is_contiguous() and out_slice.dtype == torch.bfloat16
+    B, H, W, C = x_nhwc.shape
+    assert out_slice.shape == (B * (H // pool) * (W // pool), C) and out_slice.stride(1) == 1
+    _lib.check(_lib.load().duo_pool_to_slice(_ptr(x_nhwc), _IN_KIND[x_nhwc.dtype], _ptr(out_slice), out_slice.stride(0),
+                                             B, H, W, C, pool, _stream()), "duo_pool_to_slice")
+    return out_slice
 
 
 def launch_count() -> int:

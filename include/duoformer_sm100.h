@@ -56,7 +56,8 @@ enum {
 enum {
   DUO_ACT_BF16 = 0,  /* bf16 [rows, cols]        */
   DUO_ACT_SPLIT = 1, /* split bf16 [rows, 2*cols] */
-  DUO_ACT_F32 = 2    /* float [rows, cols]       */
+  DUO_ACT_F32 = 2,   /* float [rows, cols]       */
+  DUO_ACT_F16 = 3    /* __half [rows, cols] (input of the im2col / pool kernels: the fp16 cuDNN trunk) */
 };
 
 const char* duo_last_error(void);
@@ -95,6 +96,8 @@ typedef struct duo_gemm_args {
   int32_t dest_rows_per_group; /* SCATTER: token rows per image (P*S)                      */
   int32_t pos_period;          /* SCATTER: S                                               */
   float ln_eps;                /* fused LayerNorm epsilon                                  */
+  int32_t relu;                /* BF16 / F32 epilogues: out = max(acc + bias, 0) (conv + BN + ReLU of   */
+  int32_t reserved;            /* the channel-token branch, projection_head.py:242-254)               */
   /* RESIDUAL_F32 + fused LayerNorm (optional, ln_out != NULL, bf16 operands, N <= 1024):     */
   /* after out += gamma*(acc+bias), ln_out[M,N] (bf16, dense) = LayerNorm(out rows) — the      */
   /* x = x + f(x); norm(x) pair of scale_attention.py:91-92 in one kernel.                     */
@@ -166,6 +169,20 @@ int duo_assemble_patch_tokens(const float* X, const float* cls, const float* pos
 int duo_head(const float* in, int64_t row_stride, const float* ln_gamma, const float* ln_beta,
              float eps, const float* W, const float* bias, float* logits, int32_t B, int32_t D,
              int32_t num_classes, duo_stream_t stream);
+
+/*
+ * Channel-token branch (projection_head.py:152-268) on the GEMM kernel:
+ * duo_im2col3x3: NHWC in [B,H,W,C] (bf16 / f16 / f32) -> bf16 [B*Ho*Wo, 9*C], column order (ky,kx,c),
+ *   kernel 3, padding 1, stride 1 or 2 (Conv2d(k=3, s, p=1) == this + duo_gemm with the weight
+ *   permuted to [N, ky, kx, c]).
+ * duo_pool_to_slice: 2x2/2 max-pool (pool == 2) or copy (pool == 1) of an NHWC map into a channel
+ *   slice of a wider NHWC tensor (`out` = first channel of the slice, rows ld_out apart): the
+ *   MaxPool2d + torch.cat of model.py:279-286.
+ */
+int duo_im2col3x3(const void* in, int32_t in_kind, void* out, int32_t B, int32_t H, int32_t W, int32_t C,
+                  int32_t stride, duo_stream_t stream);
+int duo_pool_to_slice(const void* in, int32_t in_kind, void* out, int64_t ld_out, int32_t B, int32_t H,
+                      int32_t W, int32_t C, int32_t pool, duo_stream_t stream);
 
 /* fp32 [rows, cols] (leading dim ld) -> bf16 / split bf16 (contiguous). */
 int duo_convert(const float* in, int64_t ld, void* out, int32_t out_kind, int64_t rows,

@@ -27,9 +27,9 @@ def test_c_abi_library_loads_and_exports_every_declared_symbol():
 
 
 def test_gemm_args_struct_layout_matches_header():
-    # 7 pointers, 4 int64, 7 int32 + 1 float, 3 pointers -> 8*7 + 8*4 + 4*8 + 8*3 = 144 bytes
-    assert ctypes.sizeof(_lib.GemmArgs) == 144
-    assert _lib.GemmArgs.ln_gamma.offset == 120
+    # 7 pointers, 4 int64, 7 int32 + float + 2 int32, 3 pointers -> 8*7 + 8*4 + 4*10 + 8*3 = 152 bytes
+    assert ctypes.sizeof(_lib.GemmArgs) == 152
+    assert _lib.GemmArgs.ln_gamma.offset == 128
     assert _lib.GemmArgs.M.offset == 56 and _lib.GemmArgs.N.offset == 88
 
 

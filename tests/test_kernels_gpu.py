@@ -252,3 +252,41 @@ def test_gemm_split_mode_2_plain_A_split_W():
     out = torch.empty(M, N, dtype=torch.float32, device="cuda")
     ops.gemm(A, ops.split_weight(W), bias, out, ops.EPI_F32, split3=2)
     assert relerr(out, ref) < 2e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("H,C,N,stride", [(28, 256, 256, 2), (14, 512, 512, 2), (7, 768, 768, 1), (12, 256, 128, 1)])
+def test_conv3x3_as_im2col_plus_gemm(H, C, N, stride, dtype):
+    """Conv2d(k=3, pad=1, stride s) + bias (+ ReLU) == duo_im2col3x3 + duo_gemm with the weight permuted
+    to [N, ky, kx, c]  (channel-token branch, projection_head.py:152-268)."""
+    B = 3
+    x = _gen((B, C, H, H), 131).to(dtype)
+    w = _gen((N, C, 3, 3), 132, (2.0 / (9 * C)) ** 0.5)
+    bias = _gen((N,), 133, 0.1)
+    ref = torch.nn.functional.conv2d(x.float().to(torch.bfloat16).float(), w.to(torch.bfloat16).float(), bias, stride=stride, padding=1)
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous()
+    a = ops.im2col3x3(x_nhwc, stride)
+    Ho = ref.shape[2]
+    assert a.shape == (B * Ho * Ho, 9 * C)
+    wg = w.permute(0, 2, 3, 1).reshape(N, 9 * C).to(torch.bfloat16).contiguous()
+    out = torch.empty(B * Ho * Ho, N, dtype=torch.float32, device="cuda")
+    ops.gemm(a, wg, bias, out, ops.EPI_F32)
+    assert relerr(out.view(B, Ho, Ho, N).permute(0, 3, 1, 2), ref) < 2e-4
+    ops.gemm(a, wg, bias, out, ops.EPI_F32, relu=True)
+    assert relerr(out.view(B, Ho, Ho, N).permute(0, 3, 1, 2), ref.clamp_min(0)) < 2e-4
+    outb = torch.empty(B * Ho * Ho, N, dtype=torch.bfloat16, device="cuda")
+    ops.gemm(a, wg, bias, outb, ops.EPI_BF16, relu=True)
+    assert relerr(outb.view(B, Ho, Ho, N).permute(0, 3, 1, 2), ref.clamp_min(0)) < 1e-2
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16, torch.float32])
+def test_pool_to_slice_concatenates_like_maxpool_and_cat(dtype):
+    B, g = 2, 7
+    a = _gen((B, 2 * g, 2 * g, 256), 141).to(dtype)
+    b = _gen((B, g, g, 128), 142).to(dtype)
+    cat = torch.zeros(B * g * g, 384, dtype=torch.bfloat16, device="cuda")
+    ops.pool_to_slice(a, cat[:, :256], 2)
+    ops.pool_to_slice(b, cat[:, 256:], 1)
+    ra = torch.nn.functional.max_pool2d(a.float().permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1).reshape(B * g * g, 256)
+    ref = torch.cat([ra, b.float().reshape(B * g * g, 128)], dim=1).to(torch.bfloat16)
+    assert torch.equal(cat, ref)
