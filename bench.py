@@ -158,9 +158,12 @@ def main():
         run_reference_arm(args)
         return
 
-    # keep stdout to exactly one JSON line: NCCL prints its version banner to stdout at VERSION/INFO level
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # keep stdout to exactly ONE JSON line: libraries (NCCL prints its version banner to stdout at
+    # communicator creation) write to file descriptor 1 behind Python's back, so point fd 1 at stderr
+    # for the duration of the run and restore it just before the result line is printed.
+    sys.stdout.flush()
+    saved_stdout_fd = os.dup(1)
+    os.dup2(2, 1)
 
     import torch
     import torch.distributed as dist
@@ -276,7 +279,10 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             cb = oracle_cpu_throughput(steps=3, warmup=1)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        sys.stdout.flush()
+        os.dup2(saved_stdout_fd, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
