@@ -143,23 +143,26 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // (fp32 simulation, x in [-12, 12]) — about 300x below bf16 rounding of O(1) activations — with
 // 7 FMA-pipe operations + 2 MUFU (ex2, rcp) per element instead of ~18 + 1 for the rational erf.
 // The coefficients below are -log2(e) * c_k so that exp(-L) = ex2(x * r(x^2)).
-__device__ __forceinline__ void gelu_erf_sigmoid_x2(float& a, float& b) {
+// Only u = x^2 is clamped (one FMNMX per element): beyond |x| = 5.5 the exponent continues linearly,
+// x * r(30.25), so Phi still saturates to 0 / 1 (ex2 overflow -> rcp(inf) = 0 -> gelu = -0).
+__device__ __forceinline__ uint64_t gelu_erf_sigmoid_p2(uint64_t x) {
 #define DUO_C2(v) pack2((v), (v))
-  const uint64_t x = pack2(a, b);
-  const float ca = fminf(fmaxf(a, -5.5f), 5.5f);
-  const float cb = fminf(fmaxf(b, -5.5f), 5.5f);
-  const uint64_t xc = pack2(ca, cb);
-  const uint64_t u = mul2(xc, xc);
+  float ua, ub;
+  unpack2(mul2(x, x), ua, ub);
+  const uint64_t u = pack2(fminf(ua, 30.25f), fminf(ub, 30.25f));
   uint64_t r = fma2(DUO_C2(2.4836352167767473e-05f), u, DUO_C2(7.360616000369191e-04f));
   r = fma2(r, u, DUO_C2(-1.0598272830247879e-01f));
   r = fma2(r, u, DUO_C2(-2.301647186279297f));
   float ea, eb;
-  unpack2(mul2(xc, r), ea, eb);
+  unpack2(mul2(x, r), ea, eb);
   const uint64_t d = add2(pack2(ex2_approx(ea), ex2_approx(eb)), DUO_C2(1.0f));
   float da, db;
   unpack2(d, da, db);
-  unpack2(mul2(x, pack2(rcp_approx(da), rcp_approx(db))), a, b);
+  return mul2(x, pack2(rcp_approx(da), rcp_approx(db)));
 #undef DUO_C2
+}
+__device__ __forceinline__ void gelu_erf_sigmoid_x2(float& a, float& b) {
+  unpack2(gelu_erf_sigmoid_p2(pack2(a, b)), a, b);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {

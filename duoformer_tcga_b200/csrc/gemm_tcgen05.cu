@@ -104,16 +104,22 @@ __device__ __forceinline__ void epilogue_bias_load(const GemmParams& p, int col,
 template <int EPI>
 __device__ __forceinline__ void epilogue_math(const GemmParams& p, int col, const uint32_t (&v)[32],
                                               const float4 (&b)[8], float (&f)[32]) {
+  if constexpr (EPI == DUO_EPI_GELU_BF16) {  // bias add and GELU on packed fp32 pairs
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint64_t lo = add2(pack2(__uint_as_float(v[4 * j + 0]), __uint_as_float(v[4 * j + 1])), pack2(b[j].x, b[j].y));
+      const uint64_t hi = add2(pack2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), pack2(b[j].z, b[j].w));
+      unpack2(gelu_erf_sigmoid_p2(lo), f[4 * j + 0], f[4 * j + 1]);
+      unpack2(gelu_erf_sigmoid_p2(hi), f[4 * j + 2], f[4 * j + 3]);
+    }
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b[j].x;
     f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b[j].y;
     f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b[j].z;
     f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b[j].w;
-  }
-  if constexpr (EPI == DUO_EPI_GELU_BF16) {
-#pragma unroll
-    for (int j = 0; j < 32; j += 2) gelu_erf_sigmoid_x2(f[j], f[j + 1]);
   }
   if constexpr (EPI == DUO_EPI_BF16 || EPI == DUO_EPI_F32) {
     if (p.relu) {
@@ -318,12 +324,29 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
     const int sub_row = lane >> 3;  // row inside a group of four handled by one store instruction
     const int chunk = lane & 7;     // 16-byte chunk of the 128-byte row
     const uint32_t buf0 = stg + stg_buf * (32u * 128u);
+    // after the transpose lane (sub_row, chunk) stores rows 4i + sub_row, i = 0..7: their destination
+    // and positional rows are fixed for the whole tile
+    float* orow[8];
+    const float* prow[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = 4 * i + sub_row;
+      const int64_t d = __shfl_sync(0xffffffffu, dst_row, r);
+      const int32_t ds = __shfl_sync(0xffffffffu, dst_s, r);
+      orow[i] = d >= 0 ? reinterpret_cast<float*>(p.out) + d * p.ldo + n0 + 4 * chunk : nullptr;
+      prow[i] = p.pos != nullptr ? p.pos + static_cast<int64_t>(ds) * p.N + n0 + 4 * chunk : nullptr;
+    }
 #pragma unroll 1
     for (int c = c_begin; c < c_end; c += 32) {
       uint32_t v[32];
       float4 bia[8];
+      float4 q[8];
       ptx::tmem_ld_32x32(taddr + static_cast<uint32_t>(c), v);
       epilogue_bias_load(p, n0 + c, bia);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)  // positional slices issued together, ahead of the transpose
+        q[i] = prow[i] != nullptr ? __ldg(reinterpret_cast<const float4*>(prow[i] + c))
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
       ptx::tmem_ld_wait();
       if (c + 32 >= c_end) {
         ptx::tc_fence_before();
@@ -331,17 +354,6 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
       }
       float f[32];
       epilogue_math<EPI>(p, n0 + c, v, bia, f);
-      if (valid && p.pos != nullptr) {
-        const float4* q4 = reinterpret_cast<const float4*>(p.pos + static_cast<int64_t>(dst_s) * p.N + n0 + c);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 q = __ldg(q4 + j);
-          f[4 * j + 0] += q.x;
-          f[4 * j + 1] += q.y;
-          f[4 * j + 2] += q.z;
-          f[4 * j + 3] += q.w;
-        }
-      }
       __syncwarp();  // previous chunk's reads of the staging tile are done
 #pragma unroll
       for (int j = 0; j < 8; ++j)
@@ -352,15 +364,14 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int r = 4 * i + sub_row;  // row of the warp slab this lane now stores
-        const int64_t d = __shfl_sync(0xffffffffu, dst_row, r);
         uint32_t w0, w1, w2, w3;
         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                      : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
                      : "r"(buf0 + static_cast<uint32_t>(r) * 128u + (static_cast<uint32_t>(chunk ^ (r & 7)) << 4)));
-        if (d >= 0) {
-          uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<float*>(p.out) + d * p.ldo + n0 + c) + chunk;
-          *o = make_uint4(w0, w1, w2, w3);
-        }
+        if (orow[i] != nullptr)
+          *reinterpret_cast<float4*>(orow[i] + c) =
+              make_float4(__uint_as_float(w0) + q[i].x, __uint_as_float(w1) + q[i].y, __uint_as_float(w2) + q[i].z,
+                          __uint_as_float(w3) + q[i].w);
       }
     }
   } else {
@@ -1081,7 +1092,11 @@ int dispatch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
     }
     case DUO_EPI_RESIDUAL_F32: return launch_pair<DUO_EPI_RESIDUAL_F32, 4>(ta, tb, to, to, p, st);
     case kEpiResidualTma: return launch_pair<kEpiResidualTma, 4>(ta, tb, to, to, p, st);
-    case DUO_EPI_SCATTER_F32: return launch_pair<DUO_EPI_SCATTER_F32, 4>(ta, tb, to, to, p, st);
+    case DUO_EPI_SCATTER_F32: {  // short K, store-bound epilogue: 8 warps (DUO_GEMM_SCATTER_WARPS=4 for the A/B)
+      static const int w = [] { const char* e = getenv("DUO_GEMM_SCATTER_WARPS"); return (e && e[0] == '4') ? 4 : 8; }();
+      return w == 8 ? launch_pair<DUO_EPI_SCATTER_F32, 8>(ta, tb, to, to, p, st)
+                    : launch_pair<DUO_EPI_SCATTER_F32, 4>(ta, tb, to, to, p, st);
+    }
     case DUO_EPI_F32: return launch_pair<DUO_EPI_F32, 4>(ta, tb, to, to, p, st);
     case DUO_EPI_SPLIT_BF16: return launch_pair<DUO_EPI_SPLIT_BF16, 4>(ta, tb, to, to, p, st);
     case DUO_EPI_GELU_SPLIT_BF16: return launch_pair<DUO_EPI_GELU_SPLIT_BF16, 8>(ta, tb, to, to, p, st);

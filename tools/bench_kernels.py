@@ -84,6 +84,24 @@ def main():
         emit("cublas_" + name, ms2, best2, flops=2.0 * M * N * K)
         del A, W, out
 
+    # token scatter GEMMs (projection of one trunk stage straight into token rows + positional add)
+    if not a.only or "scatter" in a.only or "gemm" in a.only:
+        from duoformer_tcga_b200.index_tables import token_row_maps
+        maps = token_row_maps(4, 7)
+        pos = torch.randn(S, D, device=dev)
+        for k, (C, hw) in {0: (256, 56), 1: (512, 28), 2: (1024, 14), 3: (2048, 7)}.items():
+            if k not in maps or S != 86:
+                continue
+            rows = a.images * hw * hw
+            A = (torch.randn(rows, C, device=dev) * 0.5).to(torch.bfloat16)
+            W = (torch.randn(D, C, device=dev) * 0.02).to(torch.bfloat16)
+            bias = torch.zeros(D, device=dev)
+            rm = maps[k].to(dev)
+            ms, best = timeit(lambda: ops.gemm(A, W, bias, x, ops.EPI_SCATTER_F32, row_map=rm, rows_per_group=hw * hw,
+                                               dest_rows_per_group=P * S, pos=pos, pos_period=S))
+            emit(f"gemm_scatter_K{C}", ms, best, flops=2.0 * rows * D * C, nbytes=rows * (C * 2 + D * 4))
+            del A, W
+
     qkv = (torch.randn(M, 3 * D, device=dev)).to(torch.bfloat16)
     ao = torch.empty(M, D, dtype=torch.bfloat16, device=dev)
     for algo in (2, 1):
