@@ -65,6 +65,7 @@ class GemmArgs(Structure):
         ("ln_gamma", c_void_p),
         ("ln_beta", c_void_p),
         ("ln_out", c_void_p),
+        ("ln_sync", c_void_p),
     ]
 
 

@@ -38,6 +38,6 @@ int device_sm_count() {
 }  // namespace duo
 
 extern "C" const char* duo_last_error(void) { return duo::g_err; }
-extern "C" int duo_abi_version(void) { return 1; }
+extern "C" int duo_abi_version(void) { return 2; }  // 2: duo_gemm_args.ln_sync
 extern "C" int64_t duo_launch_count(void) { return duo::g_launches; }
 extern "C" void duo_launch_count_reset(void) { duo::g_launches = 0; }

@@ -76,6 +76,8 @@ struct GemmParams {
   const float* gamma;
   const float* ln_gamma;  // fused LayerNorm (kEpiResidualLn)
   const float* ln_beta;
+  void* ln_out;
+  uint32_t* ln_sync;  // [num_m_blocks][2 CTAs][4 quarters] finished N tiles per 32-row slab
   float ln_eps;
   int32_t relu;           // BF16 / F32 epilogues: clamp at zero
   const int32_t* row_map;
@@ -580,194 +582,91 @@ constexpr int kPairBlockN = 256;
 // EPI_WARPS epilogue warps: 4 (one per TMEM lane quarter, all 256 columns, double-buffered
 // staging) or 8 (two per quarter, 128 columns each, single-buffered staging — used when the
 // epilogue math is heavy, i.e. GELU).
-// FUSED_LN: the residual+LayerNorm epilogue needs four 4 KB staging buffers per warp (three for
-// the TMA-load -> modify -> TMA-store pipeline of X chunks, one for the bf16 LayerNorm output)
-// and three load mbarriers per warp; it gives up one ring stage for them.
+// FUSED_LN: four extra LayerNorm warps (one per epilogue warp) and a panel counter each.
+constexpr int kLnWarps = 4;
 template <int EPI_WARPS, bool FUSED_LN = false>
 struct PairCfg {
-  static constexpr int kStages = FUSED_LN ? 5 : 6;
-  static constexpr int kThreads = 64 + 32 * EPI_WARPS;
-  static constexpr int kStagingBufs = FUSED_LN ? 4 : 8 / EPI_WARPS;
+  static constexpr int kStages = 6;
+  static constexpr int kThreads = 64 + 32 * EPI_WARPS + (FUSED_LN ? 32 * kLnWarps : 0);
+  static constexpr int kStagingBufs = 8 / EPI_WARPS;
   static constexpr uint32_t kABytes = kBlockM * kBlockK * 2;          // 16 KB (this CTA's 128 rows)
   static constexpr uint32_t kBBytes = (kPairBlockN / 2) * kBlockK * 2;  // 16 KB (this CTA's N half)
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
   static constexpr uint32_t kTmemCols = 2 * kPairBlockN;
-  static constexpr uint32_t kStagingBytes = EPI_WARPS * kStagingBufs * 32 * 128;  // 32 KB (64 KB fused LN)
-  static constexpr uint32_t kBarrierBytes = (2 * kStages + 4) * 8 + 8 + (FUSED_LN ? EPI_WARPS * 3 * 8 : 0);
+  static constexpr uint32_t kStagingBytes = EPI_WARPS * kStagingBufs * 32 * 128;  // 32 KB
+  static constexpr uint32_t kBarrierBytes = (2 * kStages + 4) * 8 + 8 + (FUSED_LN ? kLnWarps * 4 : 0);
   static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kStagingBytes + kBarrierBytes + 1024;
 };
 
 // ---- residual update + fused LayerNorm (kEpiResidualLn, pair kernel, row-panel tile order) ------
-// Per-thread statistics of the row this thread owns, accumulated across the N tiles of the panel
-// (shifted by the row's first value to avoid cancellation in E[d^2] - E[d]^2), plus the parity
-// bits of the warp's three X-load mbarriers.
-struct LnRowStats {
-  float pivot = 0.f, s1 = 0.f, s2 = 0.f;
-  uint32_t ld_phase = 0;
-};
-
-__device__ __forceinline__ void ld_shared_v4(uint32_t addr, float4& r) {
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+// The residual update is the ordinary TMA reduce-add epilogue in the ordinary tile order (the N
+// tiles of a 256-row panel run on neighbouring pairs at the same time, which keeps the A panel
+// in L2).  When an epilogue warp knows the reduce-adds of a tile have completed
+// (cp.async.bulk.wait_group, checked one tile late so the store pipeline never drains) it bumps
+// the global counter of its 32-row slab, p.ln_sync[m_blk][cta][quarter].  The pair that owns the
+// panel's LAST N tile runs the LayerNorm: its LN warp waits until the slab's counter reaches the
+// number of N tiles, resets it, re-reads the finished rows (L2 hits: they were just written
+// there), normalises them exactly like layernorm.cu (two-pass statistics in registers) and
+// writes the bf16 operand of the next GEMM.  LN warps never touch TMEM or the smem ring, so the
+// GEMM pipeline does not wait on them; every CTA of the persistent grid is resident, so the
+// producers of a counter are always running (a bounded spin traps instead of hanging).
+__device__ __forceinline__ float4 ld_l2_f4(const float4* ptr) {
+  float4 r;
+  asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];"
                : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
-               : "r"(addr));
+               : "l"(ptr)
+               : "memory");
+  return r;
 }
 
-// X moves only through TMA (coalesced 128-byte lines): a 32-row x 32-column fp32 chunk is loaded
-// into one of three swizzled 4 KB buffers (two chunks ahead), updated IN PLACE by the thread that
-// owns each row, and stored back from the same buffer.
-//   pass 1 (every N tile):  x_new = x_old + gamma * (acc + bias); row statistics in registers.
-//   pass 2 (after the panel's last N tile): the freshly written rows are re-loaded (L2 hits),
-//   normalised and stored as the bf16 operand of the next GEMM (fourth buffer, 64 columns/store).
-template <typename ReleaseFn>
-__device__ __forceinline__ void epilogue_residual_ln(const GemmParams& p, const CUtensorMap* tmap_x,
-                                                     const CUtensorMap* tmap_ln, uint32_t taddr, int row0,
-                                                     int lane, int n0, bool last_n_tile, uint32_t stg,
-                                                     uint32_t ldbar, LnRowStats& st, ReleaseFn release) {
-  const uint32_t my_row_off = static_cast<uint32_t>(lane) * 128u;
-  const uint32_t x7 = static_cast<uint32_t>(lane & 7);
-  auto buf_addr = [&](int b) { return stg + static_cast<uint32_t>(b) * 4096u; };
-  auto issue_load = [&](int b, int col) {  // lane 0 only
-    ptx::mbar_arrive_expect_tx(ldbar + 8u * b, 4096u);
-    ptx::tma_load_2d(buf_addr(b), tmap_x, ldbar + 8u * b, col, row0);
-  };
-  auto wait_load = [&](int b) {
-    ptx::mbar_wait(ldbar + 8u * b, (st.ld_phase >> b) & 1u);
-    st.ld_phase ^= (1u << b);
-  };
+template <int NV>
+__device__ __forceinline__ void ln_row_store(const float4 (&v)[NV], const float4 (&g)[NV], const float4 (&b)[NV],
+                                             float eps, int lane, __nv_bfloat16* yrow) {
+  constexpr int D = NV * 128;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const float mean = warp_sum(s) * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float a0 = v[i].x - mean, a1 = v[i].y - mean, a2 = v[i].z - mean, a3 = v[i].w - mean;
+    q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    uint2 w;
+    w.x = pack_bf16x2((v[i].x - mean) * rstd * g[i].x + b[i].x, (v[i].y - mean) * rstd * g[i].y + b[i].y);
+    w.y = pack_bf16x2((v[i].z - mean) * rstd * g[i].z + b[i].z, (v[i].w - mean) * rstd * g[i].w + b[i].w);
+    reinterpret_cast<uint2*>(yrow)[lane + 32 * i] = w;
+  }
+}
 
-  // ---------------- pass 1 ----------------
-  if (lane == 0) {
-    ptx::tma_store_wait_read<0>();  // buffers 0 / 1 free (previous N tile's stores have read them)
-    issue_load(0, n0);
-    issue_load(1, n0 + 32);
+// rows [row_begin, row_begin + nrows) of X (= p.out, fp32, leading dim p.ldo) -> p.ln_out (bf16 [M, N])
+template <int NV>
+__device__ __forceinline__ void ln_rows_from_l2(const GemmParams& p, int64_t row_begin, int nrows, int lane) {
+  constexpr int D = NV * 128;
+  float4 g[NV], b[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    g[i] = __ldg(reinterpret_cast<const float4*>(p.ln_gamma) + lane + 32 * i);
+    b[i] = __ldg(reinterpret_cast<const float4*>(p.ln_beta) + lane + 32 * i);
   }
+  const float* x0 = reinterpret_cast<const float*>(p.out) + row_begin * p.ldo;
+  __nv_bfloat16* y0 = reinterpret_cast<__nv_bfloat16*>(p.ln_out) + row_begin * D;
 #pragma unroll 1
-  for (int c8 = 0; c8 < kPairBlockN / 32; ++c8) {
-    const int b = c8 % 3;
-    const int c = c8 * 32;
-    uint32_t v[32];
-    float4 bia[8];
-    ptx::tmem_ld_32x32(taddr + static_cast<uint32_t>(c), v);
-    epilogue_bias_load(p, n0 + c, bia);
-    wait_load(b);
-    ptx::tmem_ld_wait();
-    if (c8 == kPairBlockN / 32 - 1) {
-      ptx::tc_fence_before();
-      release();
-    }
-    const uint32_t rowbuf = buf_addr(b) + my_row_off;
-    float f[32];
+  for (int r = 0; r < nrows; r += 2) {  // two rows in flight per warp
+    const int r1 = (r + 1 < nrows) ? r + 1 : r;
+    const float4* xa = reinterpret_cast<const float4*>(x0 + static_cast<int64_t>(r) * p.ldo);
+    const float4* xb = reinterpret_cast<const float4*>(x0 + static_cast<int64_t>(r1) * p.ldo);
+    float4 va[NV], vb[NV];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + bia[j].x;
-      f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bia[j].y;
-      f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bia[j].z;
-      f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bia[j].w;
-    }
-    if (p.gamma != nullptr) {
-      const float4* g4 = reinterpret_cast<const float4*>(p.gamma + n0 + c);
+    for (int i = 0; i < NV; ++i) va[i] = ld_l2_f4(xa + lane + 32 * i);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 g = __ldg(g4 + j);
-        f[4 * j + 0] *= g.x;
-        f[4 * j + 1] *= g.y;
-        f[4 * j + 2] *= g.z;
-        f[4 * j + 3] *= g.w;
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float4 xo;
-      ld_shared_v4(rowbuf + ((static_cast<uint32_t>(j) ^ x7) << 4), xo);
-      f[4 * j + 0] += xo.x;
-      f[4 * j + 1] += xo.y;
-      f[4 * j + 2] += xo.z;
-      f[4 * j + 3] += xo.w;
-    }
-    if (n0 == 0 && c8 == 0) {
-      st.pivot = f[0];
-      st.s1 = 0.f;
-      st.s2 = 0.f;
-    }
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float d = f[j] - st.pivot;
-      st.s1 += d;
-      st.s2 = fmaf(d, d, st.s2);
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      st_shared_v4(rowbuf + ((static_cast<uint32_t>(j) ^ x7) << 4), __float_as_uint(f[4 * j + 0]),
-                   __float_as_uint(f[4 * j + 1]), __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3]));
-    ptx::fence_proxy_async();
-    __syncwarp();
-    if (lane == 0) {
-      ptx::tma_store_2d(tmap_x, buf_addr(b), n0 + c, row0);
-      ptx::tma_store_commit();
-      if (c8 + 2 < kPairBlockN / 32) {
-        ptx::tma_store_wait_read<1>();  // chunk c8-1's store (buffer (c8+2)%3) has read its buffer
-        issue_load((c8 + 2) % 3, n0 + c + 64);
-      }
-    }
-  }
-  if (!last_n_tile) return;
-
-  // ---------------- pass 2: LayerNorm of the updated rows ----------------
-  if (lane == 0) ptx::tma_store_wait<0>();  // this warp's X stores have completed (visible in L2)
-  __syncwarp();
-  const float inv_n = 1.0f / static_cast<float>(p.N);
-  const float m1 = st.s1 * inv_n;
-  const float mean = st.pivot + m1;
-  const float var = fmaxf(st.s2 * inv_n - m1 * m1, 0.f);
-  const float rstd = rsqrtf(var + p.ln_eps);
-  const float shift = -mean * rstd;
-  if (lane == 0) {
-    issue_load(0, 0);
-    issue_load(1, 32);
-  }
-  const int nchunks = p.N / 32;
-#pragma unroll 1
-  for (int q = 0; q < nchunks; ++q) {
-    const int b = q % 3;
-    const int h = q & 1;
-    const int col = q * 32;
-    wait_load(b);
-    const uint32_t rowbuf = buf_addr(b) + my_row_off;
-    const float4* g4 = reinterpret_cast<const float4*>(p.ln_gamma + col);
-    const float4* b4 = reinterpret_cast<const float4*>(p.ln_beta + col);
-    float y[32];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float4 xo;
-      ld_shared_v4(rowbuf + ((static_cast<uint32_t>(j) ^ x7) << 4), xo);
-      const float4 g = __ldg(g4 + j);
-      const float4 be = __ldg(b4 + j);
-      y[4 * j + 0] = fmaf(fmaf(xo.x, rstd, shift), g.x, be.x);
-      y[4 * j + 1] = fmaf(fmaf(xo.y, rstd, shift), g.y, be.y);
-      y[4 * j + 2] = fmaf(fmaf(xo.z, rstd, shift), g.z, be.z);
-      y[4 * j + 3] = fmaf(fmaf(xo.w, rstd, shift), g.w, be.w);
-    }
-    if (h == 0) {
-      if (lane == 0) ptx::tma_store_wait_read<0>();  // previous bf16 store has read buffer 3
-    }
-    __syncwarp();  // all lanes finished reading buffer b (it may be re-filled) / buffer 3 is free
-    const uint32_t obuf = buf_addr(3) + my_row_off;
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      st_shared_v4(obuf + ((static_cast<uint32_t>(4 * h + j) ^ x7) << 4),
-                   pack_bf16x2(y[8 * j + 0], y[8 * j + 1]), pack_bf16x2(y[8 * j + 2], y[8 * j + 3]),
-                   pack_bf16x2(y[8 * j + 4], y[8 * j + 5]), pack_bf16x2(y[8 * j + 6], y[8 * j + 7]));
-    if (h == 1) {
-      ptx::fence_proxy_async();
-      __syncwarp();
-    }
-    if (lane == 0) {
-      if (h == 1) {
-        ptx::tma_store_2d(tmap_ln, buf_addr(3), col - 32, row0);
-        ptx::tma_store_commit();
-      }
-      if (q + 2 < nchunks) issue_load((q + 2) % 3, col + 64);
-    }
+    for (int i = 0; i < NV; ++i) vb[i] = ld_l2_f4(xb + lane + 32 * i);
+    ln_row_store<NV>(va, g, b, p.ln_eps, lane, y0 + static_cast<int64_t>(r) * D);
+    if (r1 != r) ln_row_store<NV>(vb, g, b, p.ln_eps, lane, y0 + static_cast<int64_t>(r1) * D);
   }
 }
 
@@ -794,12 +693,13 @@ __device__ __forceinline__ bool pair_tile(int64_t it, int64_t pair_idx, int64_t 
 }
 
 template <int EPI, int EPI_WARPS>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg<EPI_WARPS>::kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1)
+__launch_bounds__(PairCfg<EPI_WARPS, EPI == kEpiResidualLn>::kThreads, 1)
 gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
                          const __grid_constant__ CUtensorMap tmap_b,
                          const __grid_constant__ CUtensorMap tmap_out,
                          const __grid_constant__ CUtensorMap tmap_ln, const GemmParams p) {
-  constexpr bool kRowPanel = (EPI == kEpiResidualLn);
+  constexpr bool kRowPanel = false;
   using C = PairCfg<EPI_WARPS, EPI == kEpiResidualLn>;
   using ET = EpiTraits<EPI>;
   constexpr int kStages = C::kStages;
@@ -817,7 +717,8 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
   uint32_t* tmem_ptr_generic =
       reinterpret_cast<uint32_t*>(smem_raw + (tmem_ptr_smem - ptx::smem_u32(smem_raw)));
 
-  constexpr int kTmaWarp = EPI_WARPS, kMmaWarp = EPI_WARPS + 1;  // highest warp ids: never starved
+  constexpr int kExtraWarps = (EPI == kEpiResidualLn) ? kLnWarps : 0;  // LayerNorm warps sit after the epilogue warps
+  constexpr int kTmaWarp = EPI_WARPS + kExtraWarps, kMmaWarp = kTmaWarp + 1;  // highest warp ids: never starved
   const int warp_idx = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   const uint32_t cta_rank = ptx::cluster_ctarank();
@@ -828,8 +729,6 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
     ptx::prefetch_tmap(&tmap_b);
     if constexpr (ET::kStaged) ptx::prefetch_tmap(&tmap_out);
     if constexpr (EPI == kEpiResidualLn) {
-      ptx::prefetch_tmap(&tmap_ln);
-      for (int i = 0; i < EPI_WARPS * 3; ++i) ptx::mbar_init(tmem_ptr_smem + 8u + 8u * i, 1);  // X-load barriers
     }
 #pragma unroll
     for (int s = 0; s < kStages; ++s) {
@@ -932,6 +831,37 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
         }
       }
     }
+  } else if (EPI == kEpiResidualLn && warp_idx >= EPI_WARPS) {
+    // ===================== LayerNorm warps (fused LN only): warp j serves epilogue warp j =====================
+    const int j = warp_idx - EPI_WARPS;
+    const uint32_t want = static_cast<uint32_t>(p.num_n_blocks);
+    for (int64_t it = 0; pair_tile<kRowPanel>(it, pair_idx, pair_stride, p.num_m_blocks, p.num_n_blocks, m_blk, n_blk); ++it) {
+      if (n_blk != p.num_n_blocks - 1) continue;  // the owner of the last N tile normalises the panel
+      const int64_t mb = m_blk;
+      if (lane == 0) {
+        uint32_t* cnt = p.ln_sync + (mb * 8 + cta_rank * 4 + j);
+        uint32_t have = 0, spins = 0;
+        while (true) {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(have) : "l"(cnt) : "memory");
+          if (have >= want) break;
+          __nanosleep(256);
+          if (++spins > (1u << 23)) __trap();  // seconds without progress: fail instead of hanging
+        }
+        asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(cnt), "r"(0u) : "memory");  // ready for the next launch
+        asm volatile("fence.proxy.async;" ::: "memory");
+      }
+      __syncwarp();
+      const int64_t row_begin = mb * (2 * kBlockM) + static_cast<int64_t>(cta_rank) * kBlockM + j * 32;
+      const int64_t left = p.M - row_begin;
+      const int nrows = left >= 32 ? 32 : static_cast<int>(left);
+      if (nrows > 0) {
+        switch (p.N) {
+          case 384: ln_rows_from_l2<3>(p, row_begin, nrows, lane); break;
+          case 768: ln_rows_from_l2<6>(p, row_begin, nrows, lane); break;
+          default: ln_rows_from_l2<8>(p, row_begin, nrows, lane); break;  // 1024
+        }
+      }
+    }
   } else {
     // ===================== epilogue warps (0..EPI_WARPS-1, both CTAs) =====================
     const int quarter = warp_idx & 3;             // TMEM lane quarter (rows) of this warp
@@ -941,7 +871,12 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
     uint32_t stg_buf = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    LnRowStats ln_stats;
+    int ln_prev_m = -1;  // tile whose reduce-adds are issued but not yet known to be complete
+    auto ln_publish = [&](int mb) {  // lane 0: this warp's slab of tile (mb, *) is final in L2
+      asm volatile("fence.proxy.async;" ::: "memory");
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.ln_sync + (static_cast<int64_t>(mb) * 8 + cta_rank * 4 + quarter)) : "memory");
+    };
+    (void)ln_prev_m;
     for (int64_t it = 0; pair_tile<kRowPanel>(it, pair_idx, pair_stride, p.num_m_blocks, p.num_n_blocks, m_blk, n_blk); ++it) {
       const int row0 = m_blk * (2 * kBlockM) + static_cast<int>(cta_rank) * kBlockM + quarter * 32;
       const int n0 = n_blk * BLOCK_N;
@@ -950,19 +885,21 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const uint32_t taddr =
           tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
       const uint32_t leader_empty = ptx::mapa(tmem_empty_bar(acc), 0);
-      if constexpr (EPI == kEpiResidualLn) {
-        epilogue_residual_ln(p, &tmap_out, &tmap_ln, taddr, row0, lane, n0, n_blk == p.num_n_blocks - 1, stg,
-                             tmem_ptr_smem + 8u + 24u * static_cast<uint32_t>(warp_idx), ln_stats, [&]() {
-                               __syncwarp();
-                               if (lane == 0) ptx::mbar_arrive_cluster(leader_empty);
-                             });
-      } else
-      epilogue_tile<EPI, C::kStagingBufs>(p, &tmap_out, taddr, row0, lane, n0, col_part * kColsPerWarp,
-                                          (col_part + 1) * kColsPerWarp, stg, stg_buf,
+      constexpr int kTileEpi = (EPI == kEpiResidualLn) ? kEpiResidualTma : EPI;
+      epilogue_tile<kTileEpi, C::kStagingBufs>(p, &tmap_out, taddr, row0, lane, n0, col_part * kColsPerWarp,
+                                               (col_part + 1) * kColsPerWarp, stg, stg_buf,
                          [&]() {
                            __syncwarp();
                            if (lane == 0) ptx::mbar_arrive_cluster(leader_empty);
                          });
+      if constexpr (EPI == kEpiResidualLn) {
+        if (ln_prev_m >= 0 && lane == 0) {
+          // everything older than this tile's BLOCK_N / 32 reduce-add groups has completed
+          ptx::tma_store_wait<BLOCK_N / 32>();
+          ln_publish(ln_prev_m);
+        }
+        ln_prev_m = m_blk;
+      }
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1u;
@@ -970,6 +907,9 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
     if constexpr (ET::kStaged) {
       if (lane == 0) ptx::tma_store_wait<0>();
+    }
+    if constexpr (EPI == kEpiResidualLn) {
+      if (ln_prev_m >= 0 && lane == 0) ln_publish(ln_prev_m);
     }
   }
 
@@ -1070,10 +1010,11 @@ int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
                                   static_cast<int>(C::kSmemBytes)));
     configured = true;
   }
-  // work units: tiles (round-robin) or whole row panels (fused LayerNorm)
-  const int64_t units = EPI == kEpiResidualLn ? static_cast<int64_t>(p.num_m_blocks)
-                                              : static_cast<int64_t>(p.num_m_blocks) * p.num_n_blocks;
-  const int pairs_max = device_sm_count() / 2;
+  const int64_t units = static_cast<int64_t>(p.num_m_blocks) * p.num_n_blocks;  // tiles, round-robin over pairs
+  // DUO_GEMM_MAX_SMS caps the persistent grid (leaves SMs to kernels running beside the GEMM)
+  static const int sm_cap = [] { const char* e = getenv("DUO_GEMM_MAX_SMS"); return e ? atoi(e) : 0; }();
+  const int sms_avail = device_sm_count();
+  const int pairs_max = ((sm_cap > 1 && sm_cap < sms_avail) ? sm_cap : sms_avail) / 2;
   const int pairs = static_cast<int>(units < pairs_max ? units : pairs_max);
   kfn<<<2 * pairs, C::kThreads, C::kSmemBytes, st>>>(ta, tb, to, tl, p);
   DUO_LAUNCH_CHECK("gemm_tcgen05_pair_kernel");
@@ -1177,7 +1118,7 @@ extern "C" int duo_gemm(const duo_gemm_args* a, duo_stream_t stream) {
     DUO_CHECK_ARG(a->N % 128 == 0 && a->N <= 1024, "duo_gemm: fused LayerNorm needs N %% 128 == 0, N <= 1024");
     DUO_CHECK_ARG((reinterpret_cast<uintptr_t>(a->ln_out) & 15) == 0, "duo_gemm: ln_out must be 16-byte aligned");
   }
-  const bool fused_ln = want_ln && use_pair;
+  const bool fused_ln = want_ln && use_pair && a->ln_sync != nullptr && (a->N == 384 || a->N == 768 || a->N == 1024);
   if (fused_ln) epi = kEpiResidualLn;
   if (epi == DUO_EPI_RESIDUAL_F32 && residual_via_tma()) epi = kEpiResidualTma;
   if (epi == DUO_EPI_BF16 || epi == DUO_EPI_GELU_BF16) {
@@ -1197,6 +1138,8 @@ extern "C" int duo_gemm(const duo_gemm_args* a, duo_stream_t stream) {
   GemmParams p;
   p.ln_gamma = a->ln_gamma;
   p.ln_beta = a->ln_beta;
+  p.ln_out = a->ln_out;
+  p.ln_sync = a->ln_sync;
   p.ln_eps = a->ln_eps;
   p.relu = a->relu;
   p.bias = a->bias;

@@ -74,12 +74,28 @@ def _align(n: int, a: int = 1024) -> int:
     return (n + a - 1) // a * a
 
 
-# bf16 mode: fuse each LayerNorm into the epilogue of the preceding residual GEMM (duo_gemm's ln_out).
-# Correct (tests/test_kernels_gpu.py, parity suite with the flag on) but OFF by default: the fused
-# epilogue must move X through a TMA-load -> modify -> TMA-store pipeline that the 32-64 KB of
-# staging shared memory cannot keep deep enough — measured 3.40 ms (proj+LN2) / 4.77 ms (fc2+LN1)
-# per launch against 1.35+0.76 / 3.62+0.76 ms unfused (profiles/r01_notes.md).
+# bf16 mode: run each LayerNorm inside the preceding residual GEMM (duo_gemm's ln_out: extra LayerNorm
+# warps re-read every finished 256-row panel and write the bf16 operand of the next GEMM).
+# Correct (tests/test_kernels_gpu.py, parity suite with the flag on) but OFF by default: on the
+# power-capped B200 the LayerNorm's traffic costs the same time inside the GEMM as beside it —
+# per 64 images fc2+LN1 1.13 ms fused vs 1.15 ms as two launches, proj+LN2 0.60 vs 0.55 ms
+# (profiles/r01_notes.md; the first version, LN in the epilogue warps, was 2x slower still).
 FUSE_LAYERNORM = False
+
+
+_LN_SYNC = {}
+
+
+def _ln_sync(device, rows, slot):
+    """Zeroed row-panel counters for duo_gemm's fused LayerNorm (8 per 256 rows).  Every launch leaves
+    them zero, so one buffer per (device, concurrently running chunk) is allocated once and reused."""
+    need = 8 * ((rows + 255) // 256)
+    key = (device.index, slot)
+    t = _LN_SYNC.get(key)
+    if t is None or t.numel() < need:
+        t = torch.zeros(need, dtype=torch.int32, device=device)
+        _LN_SYNC[key] = t
+    return t
 
 
 def _scale_chunk_ops(X, b0, nb, buf, blocks, num_heads, scale, eps, precision, capture, attn_algo, live_only_last):
@@ -103,6 +119,7 @@ def _scale_chunk_ops(X, b0, nb, buf, blocks, num_heads, scale, eps, precision, c
     HID = Workspace.view(buf, 2 * hn_bytes, (T, kd * hidden), torch.bfloat16)  # aliases QKV (dead after attention)
     gelu = ops.EPI_GELU_SPLIT_BF16 if fp32 else ops.EPI_GELU_BF16
     L = len(blocks)
+    sync = _ln_sync(X.device, T, b0) if fuse else None
     for i, blk in enumerate(blocks):
         last = i == L - 1
         if i == 0 or not fuse:
@@ -123,7 +140,7 @@ def _scale_chunk_ops(X, b0, nb, buf, blocks, num_heads, scale, eps, precision, c
             yield
             if fuse:
                 ops.gemm(A0, blk["proj"][0], blk["proj"][1], X0, ops.EPI_RESIDUAL_F32, gamma=blk["g1"],
-                         ln_gamma=blk["n2w"], ln_beta=blk["n2b"], ln_out=N0, ln_eps=eps)
+                         ln_gamma=blk["n2w"], ln_beta=blk["n2b"], ln_out=N0, ln_eps=eps, ln_sync=sync)
                 yield
             else:
                 ops.gemm(A0, blk["proj"][0], blk["proj"][1], X0, ops.EPI_RESIDUAL_F32, gamma=blk["g1"], split3=fp32)
@@ -142,7 +159,7 @@ def _scale_chunk_ops(X, b0, nb, buf, blocks, num_heads, scale, eps, precision, c
         yield
         if fuse:
             ops.gemm(Hb, blk["proj"][0], blk["proj"][1], Xc, ops.EPI_RESIDUAL_F32, gamma=blk["g1"],
-                     ln_gamma=blk["n2w"], ln_beta=blk["n2b"], ln_out=Ha, ln_eps=eps)
+                     ln_gamma=blk["n2w"], ln_beta=blk["n2b"], ln_out=Ha, ln_eps=eps, ln_sync=sync)
             yield
         else:
             ops.gemm(Hb, blk["proj"][0], blk["proj"][1], Xc, ops.EPI_RESIDUAL_F32, gamma=blk["g1"], split3=fp32)
@@ -154,7 +171,7 @@ def _scale_chunk_ops(X, b0, nb, buf, blocks, num_heads, scale, eps, precision, c
         if fuse and not last:
             nxt = blocks[i + 1]
             ops.gemm(HID, blk["fc2"][0], blk["fc2"][1], Xc, ops.EPI_RESIDUAL_F32, gamma=blk["g2"],
-                     ln_gamma=nxt["n1w"], ln_beta=nxt["n1b"], ln_out=Ha, ln_eps=eps)
+                     ln_gamma=nxt["n1w"], ln_beta=nxt["n1b"], ln_out=Ha, ln_eps=eps, ln_sync=sync)
         else:
             ops.gemm(HID, blk["fc2"][0], blk["fc2"][1], Xc, ops.EPI_RESIDUAL_F32, gamma=blk["g2"], split3=fp32)
         yield

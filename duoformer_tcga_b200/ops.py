@@ -70,6 +70,7 @@ def gemm(
     ln_out: Optional[torch.Tensor] = None,
     ln_eps: float = 1e-6,
     relu: bool = False,
+    ln_sync: Optional[torch.Tensor] = None,
 ) -> torch.Tensor:
     """out = epilogue(A @ W.T + bias).  A [M,K] / W [N,K] bf16 (or [.,2K] split when split3).
     ln_out (bf16 [M,N], with EPI_RESIDUAL_F32): also LayerNorm(updated out rows) in the same kernel."""
@@ -93,6 +94,9 @@ def gemm(
     if ln_out is not None:
         assert ln_out.dtype == torch.bfloat16 and ln_out.is_contiguous() and ln_out.shape[-1] == N
         a.ln_gamma, a.ln_beta, a.ln_out, a.ln_eps = _ptr(ln_gamma), _ptr(ln_beta), _ptr(ln_out), float(ln_eps)
+        if ln_sync is not None:  # zeroed int32 scratch, 8 per 256-row panel; left zero by every launch
+            assert ln_sync.dtype == torch.int32 and ln_sync.is_contiguous() and ln_sync.numel() >= 8 * ((M + 255) // 256)
+            a.ln_sync = _ptr(ln_sync)
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() == N
     if row_map is not None:

@@ -104,6 +104,10 @@ typedef struct duo_gemm_args {
   const float* ln_gamma;
   const float* ln_beta;
   void* ln_out;
+  /* fused LayerNorm only: caller-owned scratch of 8 * ceil(M / 256) uint32, ZERO before the first */
+  /* use; every launch leaves it zero again (row-panel completion counters shared by the CTAs).    */
+  /* NULL -> the LayerNorm runs as a second launch.                                                */
+  uint32_t* ln_sync;
 } duo_gemm_args;
 int duo_gemm(const duo_gemm_args* args, duo_stream_t stream);
 

@@ -224,8 +224,9 @@ def test_invalid_arguments_raise():
 
 @pytest.mark.parametrize("M,K,with_gamma", [(256 * 60 + 77, 768, False), (256 * 60 + 77, 768, True), (256 * 52, 3072, False), (300, 768, True)])
 def test_gemm_residual_with_fused_layernorm(M, K, with_gamma):
-    """x = x + gamma*(A W^T + b); ln = LayerNorm(x) in one kernel (pair kernel, row-panel order);
-    small M falls back to GEMM + LayerNorm launches with the same result."""
+    """x = x + gamma*(A W^T + b); ln = LayerNorm(x) in one kernel (pair kernel: LayerNorm warps re-read
+    each finished row panel from L2); small M falls back to GEMM + LayerNorm launches with the same
+    result.  The panel counters (ln_sync) must be zero again after every launch."""
     N = 768
     A = _gen((M, K), 111).to(torch.bfloat16)
     W = _gen((N, K), 112, 0.05).to(torch.bfloat16)
@@ -237,9 +238,16 @@ def test_gemm_residual_with_fused_layernorm(M, K, with_gamma):
     Xr = X + (gamma * upd if with_gamma else upd)
     lnr = torch.nn.functional.layer_norm(Xr, (N,), lg, lb, 1e-6)
     ln = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
-    ops.gemm(A, W, bias, X, ops.EPI_RESIDUAL_F32, gamma=gamma, ln_gamma=lg, ln_beta=lb, ln_out=ln, ln_eps=1e-6)
-    assert relerr(X, Xr) < 1e-4
-    assert relerr(ln, lnr) < 8e-3
+    sync = torch.zeros(8 * ((M + 255) // 256), dtype=torch.int32, device="cuda")
+    X0 = X.clone()
+    for _ in range(2):  # second launch reuses the self-resetting counters
+        X.copy_(X0)
+        ln.zero_()
+        ops.gemm(A, W, bias, X, ops.EPI_RESIDUAL_F32, gamma=gamma, ln_gamma=lg, ln_beta=lb, ln_out=ln, ln_eps=1e-6,
+                 ln_sync=sync)
+        assert relerr(X, Xr) < 1e-4
+        assert relerr(ln, lnr) < 8e-3
+        assert int(sync.abs().max()) == 0
 
 
 def test_gemm_split_mode_2_plain_A_split_W():

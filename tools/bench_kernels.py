@@ -84,6 +84,25 @@ def main():
         emit("cublas_" + name, ms2, best2, flops=2.0 * M * N * K)
         del A, W, out
 
+    # residual GEMM + LayerNorm: fused (LN warps inside the GEMM) vs the two launches
+    if not a.only or "fusedln" in a.only:
+        for name, K in (("proj", D), ("fc2", 4 * D)):
+            A = (torch.randn(M, K, device=dev) * 0.5).to(torch.bfloat16)
+            W = (torch.randn(D, K, device=dev) * 0.02).to(torch.bfloat16)
+            bias = torch.zeros(D, device=dev)
+            sync = torch.zeros(8 * ((M + 255) // 256), dtype=torch.int32, device=dev)
+            ms, best = timeit(lambda: ops.gemm(A, W, bias, x, ops.EPI_RESIDUAL_F32, ln_gamma=g, ln_beta=b, ln_out=hn,
+                                               ln_sync=sync))
+            assert int(sync.abs().max()) == 0, "panel counters must be left zero"
+            emit(f"gemm_{name}_residual_fusedln", ms, best, flops=2.0 * M * D * K)
+
+            def two():
+                ops.gemm(A, W, bias, x, ops.EPI_RESIDUAL_F32)
+                ops.layernorm(x, g, b, hn, 1e-6)
+            ms, best = timeit(two)
+            emit(f"gemm_{name}_residual_then_ln", ms, best, flops=2.0 * M * D * K)
+            del A, W
+
     # token scatter GEMMs (projection of one trunk stage straight into token rows + positional add)
     if not a.only or "scatter" in a.only or "gemm" in a.only:
         from duoformer_tcga_b200.index_tables import token_row_maps
