@@ -583,7 +583,7 @@ constexpr int kPairBlockN = 256;
 // staging) or 8 (two per quarter, 128 columns each, single-buffered staging — used when the
 // epilogue math is heavy, i.e. GELU).
 // FUSED_LN: four extra LayerNorm warps (one per epilogue warp) and a panel counter each.
-constexpr int kLnWarps = 4;
+constexpr int kLnWarps = 4;  // one per epilogue warp (32 rows each, four in flight)
 template <int EPI_WARPS, bool FUSED_LN = false>
 struct PairCfg {
   static constexpr int kStages = 6;
@@ -620,7 +620,7 @@ __device__ __forceinline__ float4 ld_l2_f4(const float4* ptr) {
 }
 
 template <int NV>
-__device__ __forceinline__ void ln_row_store(const float4 (&v)[NV], const float4 (&g)[NV], const float4 (&b)[NV],
+__device__ __forceinline__ void ln_row_store(const float4 (&v)[NV], const float4* g4, const float4* b4,
                                              float eps, int lane, __nv_bfloat16* yrow) {
   constexpr int D = NV * 128;
   float s = 0.f;
@@ -636,60 +636,51 @@ __device__ __forceinline__ void ln_row_store(const float4 (&v)[NV], const float4
   const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
+    const float4 g = __ldg(g4 + lane + 32 * i);
+    const float4 b = __ldg(b4 + lane + 32 * i);
     uint2 w;
-    w.x = pack_bf16x2((v[i].x - mean) * rstd * g[i].x + b[i].x, (v[i].y - mean) * rstd * g[i].y + b[i].y);
-    w.y = pack_bf16x2((v[i].z - mean) * rstd * g[i].z + b[i].z, (v[i].w - mean) * rstd * g[i].w + b[i].w);
+    w.x = pack_bf16x2((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y);
+    w.y = pack_bf16x2((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
     reinterpret_cast<uint2*>(yrow)[lane + 32 * i] = w;
   }
 }
 
-// rows [row_begin, row_begin + nrows) of X (= p.out, fp32, leading dim p.ldo) -> p.ln_out (bf16 [M, N])
+// rows [row_begin, row_begin + nrows) of X (= p.out, fp32, leading dim p.ldo) -> p.ln_out (bf16 [M, N]);
+// four rows in flight per warp (the loads are L2 / HBM latency bound).
 template <int NV>
 __device__ __forceinline__ void ln_rows_from_l2(const GemmParams& p, int64_t row_begin, int nrows, int lane) {
   constexpr int D = NV * 128;
-  float4 g[NV], b[NV];
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    g[i] = __ldg(reinterpret_cast<const float4*>(p.ln_gamma) + lane + 32 * i);
-    b[i] = __ldg(reinterpret_cast<const float4*>(p.ln_beta) + lane + 32 * i);
-  }
+  constexpr int kRows = NV > 6 ? 2 : 4;
+  const float4* g4 = reinterpret_cast<const float4*>(p.ln_gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(p.ln_beta);
   const float* x0 = reinterpret_cast<const float*>(p.out) + row_begin * p.ldo;
   __nv_bfloat16* y0 = reinterpret_cast<__nv_bfloat16*>(p.ln_out) + row_begin * D;
 #pragma unroll 1
-  for (int r = 0; r < nrows; r += 2) {  // two rows in flight per warp
-    const int r1 = (r + 1 < nrows) ? r + 1 : r;
-    const float4* xa = reinterpret_cast<const float4*>(x0 + static_cast<int64_t>(r) * p.ldo);
-    const float4* xb = reinterpret_cast<const float4*>(x0 + static_cast<int64_t>(r1) * p.ldo);
-    float4 va[NV], vb[NV];
+  for (int r = 0; r < nrows; r += kRows) {
+    float4 v[kRows][NV];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) va[i] = ld_l2_f4(xa + lane + 32 * i);
+    for (int k = 0; k < kRows; ++k) {
+      const int rk = (r + k < nrows) ? r + k : nrows - 1;
+      const float4* xr = reinterpret_cast<const float4*>(x0 + static_cast<int64_t>(rk) * p.ldo);
 #pragma unroll
-    for (int i = 0; i < NV; ++i) vb[i] = ld_l2_f4(xb + lane + 32 * i);
-    ln_row_store<NV>(va, g, b, p.ln_eps, lane, y0 + static_cast<int64_t>(r) * D);
-    if (r1 != r) ln_row_store<NV>(vb, g, b, p.ln_eps, lane, y0 + static_cast<int64_t>(r1) * D);
+      for (int i = 0; i < NV; ++i) v[k][i] = ld_l2_f4(xr + lane + 32 * i);
+    }
+#pragma unroll
+    for (int k = 0; k < kRows; ++k)
+      if (r + k < nrows) ln_row_store<NV>(v[k], g4, b4, p.ln_eps, lane, y0 + static_cast<int64_t>(r + k) * D);
   }
 }
 
-// Tile order of the pair kernels.  Default: tiles round-robin over pairs, N fastest.  ROW_PANEL:
-// a pair owns whole 256-row panels and walks their N tiles consecutively (needed when the
-// epilogue accumulates per-row statistics across the full row — fused LayerNorm).
-template <bool ROW_PANEL>
-__device__ __forceinline__ bool pair_tile(int64_t it, int64_t pair_idx, int64_t pair_stride, int nmb,
-                                          int nnb, int& m_blk, int& n_blk) {
-  if constexpr (ROW_PANEL) {
-    const int64_t r = it / nnb;
-    const int64_t mb = pair_idx + r * pair_stride;
-    if (mb >= nmb) return false;
-    m_blk = static_cast<int>(mb);
-    n_blk = static_cast<int>(it - r * nnb);
-    return true;
-  } else {
-    const int64_t tile = pair_idx + it * pair_stride;
-    if (tile >= static_cast<int64_t>(nmb) * nnb) return false;
-    m_blk = static_cast<int>(tile / nnb);
-    n_blk = static_cast<int>(tile - static_cast<int64_t>(m_blk) * nnb);
-    return true;
-  }
+// Tile order of the pair kernels: tiles round-robin over pairs, N fastest — the N tiles of a row panel
+// run on neighbouring pairs at the same time and share the A panel through L2.  (Pair-owned row
+// panels were measured: fc2 0.92 -> 1.16 ms per 64 images, 74 x 1.5 MB of A panels do not fit L2.)
+__device__ __forceinline__ bool pair_tile(int64_t it, int64_t pair_idx, int64_t pair_stride, int nmb, int nnb,
+                                          int& m_blk, int& n_blk) {
+  const int64_t tile = pair_idx + it * pair_stride;
+  if (tile >= static_cast<int64_t>(nmb) * nnb) return false;
+  m_blk = static_cast<int>(tile / nnb);
+  n_blk = static_cast<int>(tile - static_cast<int64_t>(m_blk) * nnb);
+  return true;
 }
 
 template <int EPI, int EPI_WARPS>
@@ -699,7 +690,6 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
                          const __grid_constant__ CUtensorMap tmap_b,
                          const __grid_constant__ CUtensorMap tmap_out,
                          const __grid_constant__ CUtensorMap tmap_ln, const GemmParams p) {
-  constexpr bool kRowPanel = false;
   using C = PairCfg<EPI_WARPS, EPI == kEpiResidualLn>;
   using ET = EpiTraits<EPI>;
   constexpr int kStages = C::kStages;
@@ -761,7 +751,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int64_t it = 0; pair_tile<kRowPanel>(it, pair_idx, pair_stride, p.num_m_blocks, p.num_n_blocks, m_blk, n_blk); ++it) {
+      for (int64_t it = 0; pair_tile(it, pair_idx, pair_stride, p.num_m_blocks, p.num_n_blocks, m_blk, n_blk); ++it) {
         const int a_row = m_blk * (2 * kBlockM) + static_cast<int>(cta_rank) * kBlockM;
         const int b_row = n_blk * BLOCK_N + static_cast<int>(cta_rank) * (BLOCK_N / 2);
         for (int kb = 0; kb < num_k_blocks; ++kb) {
@@ -801,7 +791,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int64_t it = 0; pair_tile<kRowPanel>(it, pair_idx, pair_stride, p.num_m_blocks, p.num_n_blocks, m_blk, n_blk); ++it) {
+      for (int64_t it = 0; pair_tile(it, pair_idx, pair_stride, p.num_m_blocks, p.num_n_blocks, m_blk, n_blk); ++it) {
         ptx::mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
@@ -835,7 +825,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
     // ===================== LayerNorm warps (fused LN only): warp j serves epilogue warp j =====================
     const int j = warp_idx - EPI_WARPS;
     const uint32_t want = static_cast<uint32_t>(p.num_n_blocks);
-    for (int64_t it = 0; pair_tile<kRowPanel>(it, pair_idx, pair_stride, p.num_m_blocks, p.num_n_blocks, m_blk, n_blk); ++it) {
+    for (int64_t it = 0; pair_tile(it, pair_idx, pair_stride, p.num_m_blocks, p.num_n_blocks, m_blk, n_blk); ++it) {
       if (n_blk != p.num_n_blocks - 1) continue;  // the owner of the last N tile normalises the panel
       const int64_t mb = m_blk;
       if (lane == 0) {
@@ -877,7 +867,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
       asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.ln_sync + (static_cast<int64_t>(mb) * 8 + cta_rank * 4 + quarter)) : "memory");
     };
     (void)ln_prev_m;
-    for (int64_t it = 0; pair_tile<kRowPanel>(it, pair_idx, pair_stride, p.num_m_blocks, p.num_n_blocks, m_blk, n_blk); ++it) {
+    for (int64_t it = 0; pair_tile(it, pair_idx, pair_stride, p.num_m_blocks, p.num_n_blocks, m_blk, n_blk); ++it) {
       const int row0 = m_blk * (2 * kBlockM) + static_cast<int>(cta_rank) * kBlockM + quarter * 32;
       const int n0 = n_blk * BLOCK_N;
       ptx::mbar_wait(tmem_full_bar(acc), acc_phase);

@@ -7,6 +7,8 @@ import duoformer_tcga_b200 as duo
 from duoformer_tcga_b200 import engine, ops
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+if os.environ.get("CUDNN_BENCHMARK") == "1":
+    torch.backends.cudnn.benchmark = True
 torch.manual_seed(0)
 m = duo.MyModel_no_extra_params(depth=12, num_layers=4, pretrained=False, embed_dim=768, num_heads=12, num_classes=10, proj_dim=768).cuda().eval()
 x = torch.randn(B, 3, 224, 224, device="cuda")
