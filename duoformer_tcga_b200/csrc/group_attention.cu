@@ -478,6 +478,10 @@ int launch_mma(const void* qkv, void* out, int64_t groups, int S, int H, float s
 }  // namespace
 }  // namespace duo
 
+namespace duo {
+int launch_scale_attention_tc(const void* qkv, void* out, int64_t groups, int S, int H, float scale, cudaStream_t st);
+}
+
 extern "C" int duo_group_attention(const void* qkv, int32_t in_kind, void* out, int32_t out_kind,
                                    int64_t num_groups, int32_t S, int32_t num_heads, float scale,
                                    int32_t algo, int32_t q_rows, duo_stream_t stream) {
@@ -495,6 +499,11 @@ extern "C" int duo_group_attention(const void* qkv, int32_t in_kind, void* out, 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool mma_ok = in_kind == DUO_ACT_BF16 && out_kind == DUO_ACT_BF16 && S > 16 && S <= 96;
   if (algo == 0) algo = mma_ok ? 2 : 1;
+  if (algo == 3) {  // tcgen05 / TMEM kernel (scale_attention_tc.cu)
+    DUO_CHECK_ARG(mma_ok && S > 64 && q_rows == S,
+                  "duo_group_attention: algo 3 needs bf16 in/out, 64 < S <= 96 and q_rows == S (S=%d q_rows=%d)", S, q_rows);
+    return launch_scale_attention_tc(qkv, out, num_groups, S, num_heads, scale, st);
+  }
   if (algo == 2) {
     DUO_CHECK_ARG(mma_ok, "duo_group_attention: algo 2 needs bf16 in/out and 16 < S <= 96 (S=%d)", S);
     // the model's own sizes get compile-time S (masks / padded tiles pruned)

@@ -1,0 +1,300 @@
+// Scale attention on the 5th-generation tensor cores (tcgen05 + TMEM) for 64 < S <= 96 tokens per
+// group and head_dim 64 — the S = 86 case of the 4-scale model (scale_attention.py:28-45,
+// multiscale_attn.py:149-166: softmax(q k^T * scale) v inside every (patch, head)).
+//
+// One persistent CTA of four warps walks (group, head) problems; two CTAs share an SM.
+//   warp 3   : lane 0 issues TMA loads (Q, K, V head slices, one box of S rows x 128 B each,
+//              double-buffered) and all tcgen05.mma; the whole warp transposes V into the K-major
+//              V^T operand (ldmatrix.trans -> st.shared) while the scores are being computed.
+//   warps 0-2: thread = query row.  scores from TMEM (tcgen05.ld) -> softmax in registers (no
+//              shuffles) -> P (bf16) into shared memory over the dead Q|K tiles -> after the
+//              second MMA, O from TMEM, scaled by 1/sum, stored as bf16.
+//   MMA 1    : S[128 x 96] = Q[128 x 64] K^T          4 x UMMA 128x96x16, accumulator columns [0, 96)
+//   MMA 2    : O[128 x 64] = P[128 x 96] V^T^T        ceil(S/16) x UMMA 128x64x16, columns [128, 192)
+// Rows >= S of the M = 128 operands are whatever follows them in shared memory: they only feed
+// accumulator rows that are never read.  Key padding (S..95): P columns are written as zeros and
+// the V padding rows are zeroed once (TMA boxes never touch them), so no NaN can enter a real row.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace duo {
+namespace {
+
+constexpr int kDh = 64;
+constexpr int kKeysPad = 96;
+constexpr uint32_t kTile = kKeysPad * 128;       // one Q / K / V head slice: 96 rows x 128 B
+constexpr uint32_t kBuf = 3 * kTile;             // Q | K | V
+constexpr uint32_t kVtBlock = kDh * 128;         // V^T: 64 rows x (64 keys) per block
+constexpr uint32_t kSmemData = 2 * kBuf + 2 * kVtBlock;
+constexpr uint32_t kSmemBytes = kSmemData + 64 + 1024;
+constexpr uint32_t kTmemCols = 256;
+constexpr uint32_t kColS = 0, kColO = 128;
+
+__device__ __forceinline__ void ldmatrix_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+
+__global__ void __launch_bounds__(128, 2)
+scale_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __restrict__ out,
+                          int S, int H, int64_t problems, float scale_log2e) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t vt_base = base + 2 * kBuf;
+  const uint32_t bar_base = base + kSmemData;
+  const uint32_t full_bar0 = bar_base, s_full = bar_base + 16, p_ready = bar_base + 24, o_full = bar_base + 32;
+  const uint32_t tmem_slot = bar_base + 40;
+  uint32_t* tmem_slot_generic = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int D = H * kDh;
+  const uint32_t load_bytes = 3u * static_cast<uint32_t>(S) * 128u;
+  const int nk = (S + 15) >> 4;  // 16-key steps of the second MMA
+
+  // V padding rows of both buffers: zero once
+  for (int i = threadIdx.x; i < 2 * (kKeysPad - S) * 8; i += 128) {
+    const int b = i / ((kKeysPad - S) * 8);
+    const int j = i - b * (kKeysPad - S) * 8;
+    const uint32_t dst = base + b * kBuf + 2 * kTile + static_cast<uint32_t>((S + (j >> 3)) * 128 + ((j & 7) << 4));
+    asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0u) : "memory");
+  }
+  if (warp == 3) {
+    if (lane == 0) {
+      ptx::prefetch_tmap(&tmap_qkv);
+      ptx::mbar_init(full_bar0, 1);
+      ptx::mbar_init(full_bar0 + 8, 1);
+      ptx::mbar_init(s_full, 1);
+      ptx::mbar_init(p_ready, 3);  // one arrival per softmax warp
+      ptx::mbar_init(o_full, 1);
+      ptx::fence_barrier_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc<kTmemCols>(tmem_slot);
+  }
+  ptx::fence_proxy_async();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_generic;
+
+  auto issue_loads = [&](int b, int64_t prob) {  // warp 3, lane 0
+    const int64_t g = prob / H;
+    const int h = static_cast<int>(prob - g * H);
+    const uint32_t dst = base + b * kBuf;
+    const uint32_t bar = full_bar0 + 8u * b;
+    const int32_t row = static_cast<int32_t>(g * S);
+    ptx::mbar_arrive_expect_tx(bar, load_bytes);
+    ptx::tma_load_2d(dst, &tmap_qkv, bar, h * kDh, row);
+    ptx::tma_load_2d(dst + kTile, &tmap_qkv, bar, D + h * kDh, row);
+    ptx::tma_load_2d(dst + 2 * kTile, &tmap_qkv, bar, 2 * D + h * kDh, row);
+  };
+
+  const int64_t first = blockIdx.x;
+  const int64_t stride = gridDim.x;
+
+  if (warp == 3) {
+    // ===================== control warp: TMA, MMA issue, V transpose =====================
+    constexpr uint32_t idesc_s = ptx::make_idesc_bf16(128, kKeysPad);
+    constexpr uint32_t idesc_o = ptx::make_idesc_bf16(128, kDh);
+    if (lane == 0 && first < problems) issue_loads(0, first);
+    uint32_t full_phase = 0;  // bit b = parity to wait for on buffer b
+    int it = 0;
+    for (int64_t prob = first; prob < problems; prob += stride, ++it) {
+      const int b = it & 1;
+      const uint32_t buf = base + b * kBuf;
+      ptx::mbar_wait(full_bar0 + 8u * b, (full_phase >> b) & 1u);
+      full_phase ^= (1u << b);
+      if (lane == 0) {
+        ptx::tc_fence_after();
+        const uint64_t dq = ptx::make_smem_desc_sw128(buf);
+        const uint64_t dk = ptx::make_smem_desc_sw128(buf + kTile);
+#pragma unroll
+        for (int k = 0; k < kDh / 16; ++k)
+          ptx::umma_bf16(tmem_base + kColS, dq + static_cast<uint64_t>(2 * k), dk + static_cast<uint64_t>(2 * k),
+                         idesc_s, k > 0 ? 1u : 0u);
+        ptx::umma_commit(s_full);
+      }
+      // the previous problem's second MMA has consumed its P (other buffer's Q|K tiles) and V^T
+      if (it > 0) ptx::mbar_wait(o_full, static_cast<uint32_t>((it - 1) & 1));
+      if (lane == 0 && prob + stride < problems) issue_loads(b ^ 1, prob + stride);
+      // ---- V[key][d] -> V^T[d][key] (K-major, 128B swizzle, two blocks of 64 keys) ----
+      {
+        const uint32_t v_tile = buf + 2 * kTile;
+#pragma unroll 1
+        for (int kb = 0; kb < kKeysPad / 8; ++kb) {
+          const int key = 8 * kb + (lane & 7);
+          const uint32_t dst_blk = vt_base + static_cast<uint32_t>(kb >> 3) * kVtBlock;
+          const int kc = kb & 7;
+#pragma unroll
+          for (int cq = 0; cq < 2; ++cq) {
+            const int chunk = 4 * cq + (lane >> 3);
+            uint32_t r[4];
+            ldmatrix_x4_t(v_tile + static_cast<uint32_t>(key * 128 + ((chunk ^ (key & 7)) << 4)), r[0], r[1], r[2], r[3]);
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+              const int d = 8 * (4 * cq + m) + (lane >> 2);
+              const uint32_t dst = dst_blk + static_cast<uint32_t>(d * 128 + ((kc ^ (d & 7)) << 4) + 4 * (lane & 3));
+              asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst), "r"(r[m]) : "memory");
+            }
+          }
+        }
+      }
+      ptx::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        ptx::mbar_wait(p_ready, static_cast<uint32_t>(it & 1));
+        ptx::tc_fence_after();
+        const uint64_t dp0 = ptx::make_smem_desc_sw128(buf);           // P keys 0..63 (over the Q tile)
+        const uint64_t dp1 = ptx::make_smem_desc_sw128(buf + kTile);   // P keys 64..95 (over the K tile)
+        const uint64_t dv0 = ptx::make_smem_desc_sw128(vt_base);
+        const uint64_t dv1 = ptx::make_smem_desc_sw128(vt_base + kVtBlock);
+        for (int k = 0; k < nk; ++k) {
+          const uint64_t da = (k < 4 ? dp0 : dp1) + static_cast<uint64_t>(2 * (k & 3));
+          const uint64_t db = (k < 4 ? dv0 : dv1) + static_cast<uint64_t>(2 * (k & 3));
+          ptx::umma_bf16(tmem_base + kColO, da, db, idesc_o, k > 0 ? 1u : 0u);
+        }
+        ptx::umma_commit(o_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== softmax / output warps: thread = query row =====================
+    const int r = warp * 32 + lane;
+    const uint32_t x7 = static_cast<uint32_t>(r & 7);
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    int it = 0;
+    for (int64_t prob = first; prob < problems; prob += stride, ++it) {
+      const int b = it & 1;
+      const uint32_t buf = base + b * kBuf;
+      const int64_t g = prob / H;
+      const int h = static_cast<int>(prob - g * H);
+      ptx::mbar_wait(s_full, static_cast<uint32_t>(it & 1));
+      ptx::tc_fence_after();
+      uint32_t v0[32], v1[32], v2[32];
+      ptx::tmem_ld_32x32(taddr + kColS, v0);
+      ptx::tmem_ld_32x32(taddr + kColS + 32, v1);
+      ptx::tmem_ld_32x32(taddr + kColS + 64, v2);
+      ptx::tmem_ld_wait();
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaxf(__uint_as_float(v0[j]), __uint_as_float(v1[j])));
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (64 + j < S) mx = fmaxf(mx, __uint_as_float(v2[j]));
+      const float off = mx * scale_log2e;
+      float sum = 0.f;
+      // probabilities, 8 keys (one 16-byte chunk of the P row) at a time
+      auto emit = [&](const uint32_t (&v)[32], int key0, uint32_t tile) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float p[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int key = key0 + 8 * c + j;
+            p[j] = key < S ? exp2f(fmaf(__uint_as_float(v[8 * c + j]), scale_log2e, -off)) : 0.f;
+            sum += p[j];
+          }
+          const uint32_t kc = static_cast<uint32_t>(((key0 & 63) >> 3) + c);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile + static_cast<uint32_t>(r) * 128u + ((kc ^ x7) << 4)),
+                       "r"(pack_bf16x2(p[0], p[1])), "r"(pack_bf16x2(p[2], p[3])), "r"(pack_bf16x2(p[4], p[5])),
+                       "r"(pack_bf16x2(p[6], p[7]))
+                       : "memory");
+        }
+      };
+      emit(v0, 0, buf);
+      emit(v1, 32, buf);
+      emit(v2, 64, buf + kTile);
+      ptx::fence_proxy_async();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(p_ready);
+
+      ptx::mbar_wait(o_full, static_cast<uint32_t>(it & 1));
+      ptx::tc_fence_after();
+      ptx::tmem_ld_32x32(taddr + kColO, v0);
+      ptx::tmem_ld_32x32(taddr + kColO + 32, v1);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      if (r < S) {
+        const float inv = 1.0f / sum;
+        uint4* o4 = reinterpret_cast<uint4*>(out + (g * S + r) * D + h * kDh);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          o4[c] = make_uint4(pack_bf16x2(__uint_as_float(v0[8 * c + 0]) * inv, __uint_as_float(v0[8 * c + 1]) * inv),
+                             pack_bf16x2(__uint_as_float(v0[8 * c + 2]) * inv, __uint_as_float(v0[8 * c + 3]) * inv),
+                             pack_bf16x2(__uint_as_float(v0[8 * c + 4]) * inv, __uint_as_float(v0[8 * c + 5]) * inv),
+                             pack_bf16x2(__uint_as_float(v0[8 * c + 6]) * inv, __uint_as_float(v0[8 * c + 7]) * inv));
+          o4[4 + c] = make_uint4(pack_bf16x2(__uint_as_float(v1[8 * c + 0]) * inv, __uint_as_float(v1[8 * c + 1]) * inv),
+                                 pack_bf16x2(__uint_as_float(v1[8 * c + 2]) * inv, __uint_as_float(v1[8 * c + 3]) * inv),
+                                 pack_bf16x2(__uint_as_float(v1[8 * c + 4]) * inv, __uint_as_float(v1[8 * c + 5]) * inv),
+                                 pack_bf16x2(__uint_as_float(v1[8 * c + 6]) * inv, __uint_as_float(v1[8 * c + 7]) * inv));
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 3) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+}  // namespace
+
+// qkv [groups * S, 3 * H * 64] bf16 -> out [groups * S, H * 64] bf16; 64 < S <= 96.
+int launch_scale_attention_tc(const void* qkv, void* out, int64_t groups, int S, int H, float scale, cudaStream_t st) {
+  static PFN_encodeTiled encode = nullptr;
+  if (encode == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess) {
+      set_error("cuTensorMapEncodeTiled entry point not available");
+      return DUO_ERR_CUDA;
+    }
+    encode = reinterpret_cast<PFN_encodeTiled>(ptr);
+  }
+  const int64_t rows = groups * S;
+  const int64_t cols = 3LL * H * kDh;
+  if (rows >= (int64_t(1) << 31)) {
+    set_error("duo_group_attention: too many rows for the tcgen05 kernel");
+    return DUO_ERR_INVALID;
+  }
+  CUtensorMap tm;
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(cols) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kDh), static_cast<cuuint32_t>(S)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(qkv), gdim, gstride, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) for the qkv tensor", static_cast<int>(r));
+    return DUO_ERR_CUDA;
+  }
+  static bool configured = false;
+  if (!configured) {
+    DUO_CUDA(cudaFuncSetAttribute(scale_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(kSmemBytes)));
+    configured = true;
+  }
+  const int64_t problems = groups * H;
+  const int64_t max_ctas = 2LL * device_sm_count();
+  const unsigned grid = static_cast<unsigned>(problems < max_ctas ? problems : max_ctas);
+  scale_attention_tc_kernel<<<grid, 128, kSmemBytes, st>>>(tm, reinterpret_cast<__nv_bfloat16*>(out), S, H, problems,
+                                                           scale * 1.4426950408889634f);
+  DUO_LAUNCH_CHECK("scale_attention_tc_kernel");
+  return DUO_OK;
+}
+
+}  // namespace duo

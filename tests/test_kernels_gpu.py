@@ -124,14 +124,15 @@ def _attn_ref(qkv, S, H, scale):
     return (a @ v).transpose(1, 2).reshape(rows, D)
 
 
-@pytest.mark.parametrize("S,G,algo", [(6, 98, 1), (22, 50, 1), (22, 50, 2), (86, 49, 1), (86, 49, 2), (50, 7, 1), (50, 7, 2), (145, 3, 1), (17, 5, 2), (96, 4, 2)])
+@pytest.mark.parametrize("S,G,algo", [(6, 98, 1), (22, 50, 1), (22, 50, 2), (86, 49, 1), (86, 49, 2), (50, 7, 1), (50, 7, 2), (145, 3, 1), (17, 5, 2), (96, 4, 2),
+                                          (86, 49, 3), (86, 700, 3), (96, 4, 3), (80, 6, 3), (71, 5, 3), (65, 3, 3)])
 def test_group_attention_bf16(S, G, algo):
     H = 12
     qkv = _gen((G * S, 3 * H * 64), 41 + S, 2.0).to(torch.bfloat16)
     ref = _attn_ref(qkv, S, H, 0.125)
     out = torch.empty(G * S, H * 64, dtype=torch.bfloat16, device="cuda")
     ops.group_attention(qkv, out, S, H, 0.125, algo=algo)
-    assert relerr(out, ref) < (1.5e-2 if algo == 2 else 8e-3)
+    assert relerr(out, ref) < (1.5e-2 if algo >= 2 else 8e-3)
 
 
 @pytest.mark.parametrize("S,G,algo,q_rows", [(86, 49, 2, 1), (86, 49, 1, 1), (22, 10, 2, 3), (6, 30, 1, 1), (50, 5, 2, 17)])

@@ -123,10 +123,12 @@ def main():
 
     qkv = (torch.randn(M, 3 * D, device=dev)).to(torch.bfloat16)
     ao = torch.empty(M, D, dtype=torch.bfloat16, device=dev)
-    for algo in (2, 1):
+    for algo in (3, 2, 1):
         if a.only and "attn" not in a.only:
             continue
         if algo == 2 and not (16 < S <= 96):
+            continue
+        if algo == 3 and not (64 < S <= 96):
             continue
         ms, best = timeit(lambda: ops.group_attention(qkv, ao, S, 12, 0.125, algo=algo), iters=5, warmup=2)
         emit(f"scale_attention_algo{algo}_S{S}", ms, best, flops=4.0 * (M // S) * S * S * D, nbytes=M * D * 8)
