@@ -498,7 +498,8 @@ extern "C" int duo_group_attention(const void* qkv, int32_t in_kind, void* out, 
   DUO_CHECK_ARG(q_rows >= 1 && q_rows <= S, "duo_group_attention: q_rows=%d must be in [1, S=%d]", q_rows, S);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool mma_ok = in_kind == DUO_ACT_BF16 && out_kind == DUO_ACT_BF16 && S > 16 && S <= 96;
-  if (algo == 0) algo = mma_ok ? 2 : 1;
+  // auto: tcgen05 kernel for the 4-scale group size, mma.sync kernel for the other tensor-core sizes
+  if (algo == 0) algo = (mma_ok && S > 64 && q_rows == S) ? 3 : (mma_ok ? 2 : 1);
   if (algo == 3) {  // tcgen05 / TMEM kernel (scale_attention_tc.cu)
     DUO_CHECK_ARG(mma_ok && S > 64 && q_rows == S,
                   "duo_group_attention: algo 3 needs bf16 in/out, 64 < S <= 96 and q_rows == S (S=%d q_rows=%d)", S, q_rows);

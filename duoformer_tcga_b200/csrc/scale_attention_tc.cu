@@ -7,8 +7,11 @@
 //              double-buffered) and all tcgen05.mma; the whole warp transposes V into the K-major
 //              V^T operand (ldmatrix.trans -> st.shared) while the scores are being computed.
 //   warps 0-2: thread = query row.  scores from TMEM (tcgen05.ld) -> softmax in registers (no
-//              shuffles) -> P (bf16) into shared memory over the dead Q|K tiles -> after the
-//              second MMA, O from TMEM, scaled by 1/sum, stored as bf16.
+//              shuffles) -> P (bf16) into shared memory -> after the second MMA, O from TMEM,
+//              scaled by 1/sum, transposed through the warp's (dead) P rows and stored as full
+//              128-byte lines.
+// Loads run two problems ahead: a buffer is refilled as soon as its Q/K have been multiplied and
+// its V transposed.
 //   MMA 1    : S[128 x 96] = Q[128 x 64] K^T          4 x UMMA 128x96x16, accumulator columns [0, 96)
 //   MMA 2    : O[128 x 64] = P[128 x 96] V^T^T        ceil(S/16) x UMMA 128x64x16, columns [128, 192)
 // Rows >= S of the M = 128 operands are whatever follows them in shared memory: they only feed
@@ -27,8 +30,9 @@ constexpr int kKeysPad = 96;
 constexpr uint32_t kTile = kKeysPad * 128;       // one Q / K / V head slice: 96 rows x 128 B
 constexpr uint32_t kBuf = 3 * kTile;             // Q | K | V
 constexpr uint32_t kVtBlock = kDh * 128;         // V^T: 64 rows x (64 keys) per block
-constexpr uint32_t kSmemData = 2 * kBuf + 2 * kVtBlock;
-constexpr uint32_t kSmemBytes = kSmemData + 64 + 1024;
+constexpr uint32_t kPBytes = 2 * kTile;          // P: keys 0..63 | keys 64..95, 96 rows x 128 B each
+constexpr uint32_t kSmemData = 2 * kBuf + kPBytes + 2 * kVtBlock;
+constexpr uint32_t kSmemBytes = kSmemData + 64;  // 112 KB + barriers: two CTAs per SM (no alignment slack to spare)
 constexpr uint32_t kTmemCols = 256;
 constexpr uint32_t kColS = 0, kColO = 128;
 
@@ -38,12 +42,17 @@ __device__ __forceinline__ void ldmatrix_x4_t(uint32_t addr, uint32_t& r0, uint3
                : "r"(addr));
 }
 
+// S_CT > 0: S known at compile time (the model's 86); 0: runtime S.
+template <int S_CT>
 __global__ void __launch_bounds__(128, 2)
 scale_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __restrict__ out,
-                          int S, int H, int64_t problems, float scale_log2e) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t vt_base = base + 2 * kBuf;
+                          int S_rt, int H, int64_t problems, float scale_log2e) {
+  const int S = S_CT > 0 ? S_CT : S_rt;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = ptx::smem_u32(smem_raw);
+  if ((base & 1023u) != 0) __trap();  // the 128-byte swizzle patterns of TMA and UMMA assume 1024-byte aligned tiles
+  const uint32_t p_base = base + 2 * kBuf;
+  const uint32_t vt_base = p_base + kPBytes;
   const uint32_t bar_base = base + kSmemData;
   const uint32_t full_bar0 = bar_base, s_full = bar_base + 16, p_ready = bar_base + 24, o_full = bar_base + 32;
   const uint32_t tmem_slot = bar_base + 40;
@@ -100,7 +109,10 @@ scale_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfl
     // ===================== control warp: TMA, MMA issue, V transpose =====================
     constexpr uint32_t idesc_s = ptx::make_idesc_bf16(128, kKeysPad);
     constexpr uint32_t idesc_o = ptx::make_idesc_bf16(128, kDh);
-    if (lane == 0 && first < problems) issue_loads(0, first);
+    if (lane == 0) {
+      if (first < problems) issue_loads(0, first);
+      if (first + stride < problems) issue_loads(1, first + stride);
+    }
     uint32_t full_phase = 0;  // bit b = parity to wait for on buffer b
     int it = 0;
     for (int64_t prob = first; prob < problems; prob += stride, ++it) {
@@ -118,13 +130,12 @@ scale_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfl
                          idesc_s, k > 0 ? 1u : 0u);
         ptx::umma_commit(s_full);
       }
-      // the previous problem's second MMA has consumed its P (other buffer's Q|K tiles) and V^T
+      // the previous problem's second MMA has consumed V^T
       if (it > 0) ptx::mbar_wait(o_full, static_cast<uint32_t>((it - 1) & 1));
-      if (lane == 0 && prob + stride < problems) issue_loads(b ^ 1, prob + stride);
       // ---- V[key][d] -> V^T[d][key] (K-major, 128B swizzle, two blocks of 64 keys) ----
       {
         const uint32_t v_tile = buf + 2 * kTile;
-#pragma unroll 1
+#pragma unroll 2
         for (int kb = 0; kb < kKeysPad / 8; ++kb) {
           const int key = 8 * kb + (lane & 7);
           const uint32_t dst_blk = vt_base + static_cast<uint32_t>(kb >> 3) * kVtBlock;
@@ -146,10 +157,15 @@ scale_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfl
       ptx::fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
+        // this buffer is free once Q K^T has completed (V is already transposed): refill it two problems ahead
+        if (prob + 2 * stride < problems) {
+          ptx::mbar_wait(s_full, static_cast<uint32_t>(it & 1));
+          issue_loads(b, prob + 2 * stride);
+        }
         ptx::mbar_wait(p_ready, static_cast<uint32_t>(it & 1));
         ptx::tc_fence_after();
-        const uint64_t dp0 = ptx::make_smem_desc_sw128(buf);           // P keys 0..63 (over the Q tile)
-        const uint64_t dp1 = ptx::make_smem_desc_sw128(buf + kTile);   // P keys 64..95 (over the K tile)
+        const uint64_t dp0 = ptx::make_smem_desc_sw128(p_base);           // P keys 0..63
+        const uint64_t dp1 = ptx::make_smem_desc_sw128(p_base + kTile);   // P keys 64..95
         const uint64_t dv0 = ptx::make_smem_desc_sw128(vt_base);
         const uint64_t dv1 = ptx::make_smem_desc_sw128(vt_base + kVtBlock);
         for (int k = 0; k < nk; ++k) {
@@ -168,8 +184,6 @@ scale_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfl
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
     int it = 0;
     for (int64_t prob = first; prob < problems; prob += stride, ++it) {
-      const int b = it & 1;
-      const uint32_t buf = base + b * kBuf;
       const int64_t g = prob / H;
       const int h = static_cast<int>(prob - g * H);
       ptx::mbar_wait(s_full, static_cast<uint32_t>(it & 1));
@@ -195,7 +209,7 @@ scale_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfl
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int key = key0 + 8 * c + j;
-            p[j] = key < S ? exp2f(fmaf(__uint_as_float(v[8 * c + j]), scale_log2e, -off)) : 0.f;
+            p[j] = key < S ? ex2_approx(fmaf(__uint_as_float(v[8 * c + j]), scale_log2e, -off)) : 0.f;
             sum += p[j];
           }
           const uint32_t kc = static_cast<uint32_t>(((key0 & 63) >> 3) + c);
@@ -205,9 +219,9 @@ scale_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfl
                        : "memory");
         }
       };
-      emit(v0, 0, buf);
-      emit(v1, 32, buf);
-      emit(v2, 64, buf + kTile);
+      emit(v0, 0, p_base);
+      emit(v1, 32, p_base);
+      emit(v2, 64, p_base + kTile);
       ptx::fence_proxy_async();
       ptx::tc_fence_before();
       __syncwarp();
@@ -219,20 +233,37 @@ scale_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfl
       ptx::tmem_ld_32x32(taddr + kColO + 32, v1);
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
-      if (r < S) {
+      {
+        // O row -> this thread's (dead) P row, then the warp stores four complete 128-byte rows per instruction
         const float inv = 1.0f / sum;
-        uint4* o4 = reinterpret_cast<uint4*>(out + (g * S + r) * D + h * kDh);
+        const uint32_t my_row = p_base + static_cast<uint32_t>(r) * 128u;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          o4[c] = make_uint4(pack_bf16x2(__uint_as_float(v0[8 * c + 0]) * inv, __uint_as_float(v0[8 * c + 1]) * inv),
-                             pack_bf16x2(__uint_as_float(v0[8 * c + 2]) * inv, __uint_as_float(v0[8 * c + 3]) * inv),
-                             pack_bf16x2(__uint_as_float(v0[8 * c + 4]) * inv, __uint_as_float(v0[8 * c + 5]) * inv),
-                             pack_bf16x2(__uint_as_float(v0[8 * c + 6]) * inv, __uint_as_float(v0[8 * c + 7]) * inv));
-          o4[4 + c] = make_uint4(pack_bf16x2(__uint_as_float(v1[8 * c + 0]) * inv, __uint_as_float(v1[8 * c + 1]) * inv),
-                                 pack_bf16x2(__uint_as_float(v1[8 * c + 2]) * inv, __uint_as_float(v1[8 * c + 3]) * inv),
-                                 pack_bf16x2(__uint_as_float(v1[8 * c + 4]) * inv, __uint_as_float(v1[8 * c + 5]) * inv),
-                                 pack_bf16x2(__uint_as_float(v1[8 * c + 6]) * inv, __uint_as_float(v1[8 * c + 7]) * inv));
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + ((static_cast<uint32_t>(c) ^ x7) << 4)),
+                       "r"(pack_bf16x2(__uint_as_float(v0[8 * c + 0]) * inv, __uint_as_float(v0[8 * c + 1]) * inv)),
+                       "r"(pack_bf16x2(__uint_as_float(v0[8 * c + 2]) * inv, __uint_as_float(v0[8 * c + 3]) * inv)),
+                       "r"(pack_bf16x2(__uint_as_float(v0[8 * c + 4]) * inv, __uint_as_float(v0[8 * c + 5]) * inv)),
+                       "r"(pack_bf16x2(__uint_as_float(v0[8 * c + 6]) * inv, __uint_as_float(v0[8 * c + 7]) * inv))
+                       : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + ((static_cast<uint32_t>(4 + c) ^ x7) << 4)),
+                       "r"(pack_bf16x2(__uint_as_float(v1[8 * c + 0]) * inv, __uint_as_float(v1[8 * c + 1]) * inv)),
+                       "r"(pack_bf16x2(__uint_as_float(v1[8 * c + 2]) * inv, __uint_as_float(v1[8 * c + 3]) * inv)),
+                       "r"(pack_bf16x2(__uint_as_float(v1[8 * c + 4]) * inv, __uint_as_float(v1[8 * c + 5]) * inv)),
+                       "r"(pack_bf16x2(__uint_as_float(v1[8 * c + 6]) * inv, __uint_as_float(v1[8 * c + 7]) * inv))
+                       : "memory");
         }
+        __syncwarp();
+        __nv_bfloat16* obase = out + (g * S) * D + h * kDh + (lane & 7) * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = warp * 32 + 4 * i + (lane >> 3);
+          uint32_t w0, w1, w2, w3;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                       : "r"(p_base + static_cast<uint32_t>(rr * 128 + (((lane & 7) ^ (rr & 7)) << 4))));
+          if (rr < S) *reinterpret_cast<uint4*>(obase + static_cast<int64_t>(rr) * D) = make_uint4(w0, w1, w2, w3);
+        }
+        __syncwarp();  // rows are free for the next problem's P
       }
     }
   }
@@ -284,15 +315,21 @@ int launch_scale_attention_tc(const void* qkv, void* out, int64_t groups, int S,
   }
   static bool configured = false;
   if (!configured) {
-    DUO_CUDA(cudaFuncSetAttribute(scale_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    DUO_CUDA(cudaFuncSetAttribute(scale_attention_tc_kernel<86>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(kSmemBytes)));
+    DUO_CUDA(cudaFuncSetAttribute(scale_attention_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(kSmemBytes)));
     configured = true;
   }
   const int64_t problems = groups * H;
   const int64_t max_ctas = 2LL * device_sm_count();
   const unsigned grid = static_cast<unsigned>(problems < max_ctas ? problems : max_ctas);
-  scale_attention_tc_kernel<<<grid, 128, kSmemBytes, st>>>(tm, reinterpret_cast<__nv_bfloat16*>(out), S, H, problems,
-                                                           scale * 1.4426950408889634f);
+  if (S == 86)
+    scale_attention_tc_kernel<86><<<grid, 128, kSmemBytes, st>>>(tm, reinterpret_cast<__nv_bfloat16*>(out), S, H, problems,
+                                                                 scale * 1.4426950408889634f);
+  else
+    scale_attention_tc_kernel<0><<<grid, 128, kSmemBytes, st>>>(tm, reinterpret_cast<__nv_bfloat16*>(out), S, H, problems,
+                                                                scale * 1.4426950408889634f);
   DUO_LAUNCH_CHECK("scale_attention_tc_kernel");
   return DUO_OK;
 }
