@@ -579,16 +579,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 // the "slot free" / "accumulator full" arrivals to both CTAs; each CTA runs its own epilogue.
 // ===========================================================================================
 constexpr int kPairBlockN = 256;
-// EPI_WARPS epilogue warps: 4 (one per TMEM lane quarter, all 256 columns, double-buffered
-// staging) or 8 (two per quarter, 128 columns each, single-buffered staging — used when the
-// epilogue math is heavy, i.e. GELU).
+// EPI_WARPS epilogue warps: 4 (one per TMEM lane quarter, all 256 columns, 6 operand stages) or 8
+// (two per quarter, 128 columns each, 5 operand stages — used when the epilogue is heavy: GELU,
+// token scatter; both only occur with short K).  Staging is double-buffered per warp either way.
 // FUSED_LN: four extra LayerNorm warps (one per epilogue warp) and a panel counter each.
 constexpr int kLnWarps = 4;  // one per epilogue warp (32 rows each, four in flight)
 template <int EPI_WARPS, bool FUSED_LN = false>
 struct PairCfg {
-  static constexpr int kStages = 6;
+  static constexpr int kStages = EPI_WARPS == 8 ? 5 : 6;
   static constexpr int kThreads = 64 + 32 * EPI_WARPS + (FUSED_LN ? 32 * kLnWarps : 0);
-  static constexpr int kStagingBufs = 8 / EPI_WARPS;
+  static constexpr int kStagingBufs = 2;
   static constexpr uint32_t kABytes = kBlockM * kBlockK * 2;          // 16 KB (this CTA's 128 rows)
   static constexpr uint32_t kBBytes = (kPairBlockN / 2) * kBlockK * 2;  // 16 KB (this CTA's N half)
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
