@@ -61,7 +61,7 @@ class GemmArgs(Structure):
         ("pos_period", c_int32),
         ("ln_eps", c_float),
         ("relu", c_int32),
-        ("reserved", c_int32),
+        ("fp16_operands", c_int32),
         ("ln_gamma", c_void_p),
         ("ln_beta", c_void_p),
         ("ln_out", c_void_p),

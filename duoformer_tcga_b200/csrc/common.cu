@@ -35,6 +35,15 @@ int device_sm_count() {
   return cached_sms;
 }
 
+bool first_use_on_device(uint64_t& mask) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+  const uint64_t bit = uint64_t(1) << dev;
+  if (mask & bit) return false;
+  mask |= bit;
+  return true;
+}
+
 }  // namespace duo
 
 extern "C" const char* duo_last_error(void) { return duo::g_err; }

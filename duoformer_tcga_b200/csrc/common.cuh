@@ -38,6 +38,9 @@ void count_launch();
   } while (0)
 
 int device_sm_count();
+// true the first time it is called with `mask` on the current device (per-device one-time setup such as
+// cudaFuncSetAttribute: function attributes are per device); false afterwards.
+bool first_use_on_device(uint64_t& mask);
 
 // ---- small device helpers --------------------------------------------------------------
 #ifdef __CUDACC__

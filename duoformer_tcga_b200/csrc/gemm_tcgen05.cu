@@ -88,6 +88,7 @@ struct GemmParams {
   int32_t split3;
   int32_t rows_per_group, dest_rows_per_group, pos_period;
   int32_t num_m_blocks, num_n_blocks;
+  uint32_t idesc_mask;  // ~0, or with the a_format / b_format bits cleared (fp16 operands instead of bf16)
 };
 
 // acc[32] (fp32 bits) -> f[32] = acc + bias (optionally GELU'd / scaled by LayerScale gamma)
@@ -493,7 +494,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   } else if (warp_idx == kMmaWarp) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(kBlockM, BLOCK_N);
+      const uint32_t idesc = ptx::make_idesc_bf16(kBlockM, BLOCK_N) & p.idesc_mask;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -786,7 +787,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
   } else if (warp_idx == kMmaWarp) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (is_leader && lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(2 * kBlockM, BLOCK_N);
+      const uint32_t idesc = ptx::make_idesc_bf16(2 * kBlockM, BLOCK_N) & p.idesc_mask;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -958,13 +959,11 @@ template <int BLOCK_N, int EPI>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const GemmParams& p,
            cudaStream_t st) {
   using C = Cfg<BLOCK_N>;
-  static bool configured = false;
+  static uint64_t configured = 0;  // per device
   auto kfn = gemm_tcgen05_kernel<BLOCK_N, EPI>;
-  if (!configured) {
+  if (first_use_on_device(configured))
     DUO_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(C::kSmemBytes)));
-    configured = true;
-  }
   const int64_t tiles = static_cast<int64_t>(p.num_m_blocks) * p.num_n_blocks;
   const int sms = device_sm_count();
   const int grid = static_cast<int>(tiles < sms ? tiles : sms);
@@ -993,13 +992,11 @@ template <int EPI, int EPI_WARPS>
 int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tl,
                 const GemmParams& p, cudaStream_t st) {
   using C = PairCfg<EPI_WARPS, EPI == kEpiResidualLn>;
-  static bool configured = false;
+  static uint64_t configured = 0;  // per device
   auto kfn = gemm_tcgen05_pair_kernel<EPI, EPI_WARPS>;
-  if (!configured) {
+  if (first_use_on_device(configured))
     DUO_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(C::kSmemBytes)));
-    configured = true;
-  }
   const int64_t units = static_cast<int64_t>(p.num_m_blocks) * p.num_n_blocks;  // tiles, round-robin over pairs
   // DUO_GEMM_MAX_SMS caps the persistent grid (leaves SMs to kernels running beside the GEMM)
   static const int sm_cap = [] { const char* e = getenv("DUO_GEMM_MAX_SMS"); return e ? atoi(e) : 0; }();
@@ -1067,6 +1064,7 @@ extern "C" int duo_gemm(const duo_gemm_args* a, duo_stream_t stream) {
   DUO_CHECK_ARG(a->N % 128 == 0, "duo_gemm: N=%d must be a multiple of 128", a->N);
   DUO_CHECK_ARG(a->K % kBlockK == 0, "duo_gemm: K=%d must be a multiple of 64", a->K);
   DUO_CHECK_ARG(a->split3 >= 0 && a->split3 <= 2, "duo_gemm: split3=%d", a->split3);
+  DUO_CHECK_ARG(a->fp16_operands == 0 || (a->fp16_operands == 1 && a->split3 == 0), "duo_gemm: fp16_operands=%d needs split3 == 0", a->fp16_operands);
   const int kcols = a->split3 ? 2 * a->K : a->K;         // W columns
   const int acols = a->split3 == 1 ? 2 * a->K : a->K;    // A columns
   DUO_CHECK_ARG(a->lda >= acols && a->ldw >= kcols && a->lda % 8 == 0 && a->ldw % 8 == 0,
@@ -1146,6 +1144,7 @@ extern "C" int duo_gemm(const duo_gemm_args* a, duo_stream_t stream) {
   p.dest_rows_per_group = a->dest_rows_per_group;
   p.pos_period = a->pos_period;
   p.num_m_blocks = static_cast<int32_t>(m_blocks);
+  p.idesc_mask = a->fp16_operands ? ~((1u << 7) | (1u << 10)) : ~0u;  // a_format / b_format: 1 = BF16, 0 = F16
   p.num_n_blocks = use_pair ? a->N / kPairBlockN : a->N / block_n;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (use_pair) return dispatch_pair(ta, tb, to, tl, p, epi, st);

@@ -313,13 +313,12 @@ int launch_scale_attention_tc(const void* qkv, void* out, int64_t groups, int S,
     set_error("cuTensorMapEncodeTiled failed (%d) for the qkv tensor", static_cast<int>(r));
     return DUO_ERR_CUDA;
   }
-  static bool configured = false;
-  if (!configured) {
+  static uint64_t configured = 0;  // per device
+  if (first_use_on_device(configured)) {
     DUO_CUDA(cudaFuncSetAttribute(scale_attention_tc_kernel<86>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(kSmemBytes)));
     DUO_CUDA(cudaFuncSetAttribute(scale_attention_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(kSmemBytes)));
-    configured = true;
   }
   const int64_t problems = groups * H;
   const int64_t max_ctas = 2LL * device_sm_count();

@@ -36,10 +36,11 @@ def param_signature(module: nn.Module, precision: str) -> tuple:
     return tuple(sig)
 
 
-def pack_linear(weight: torch.Tensor, bias: Optional[torch.Tensor], precision: str) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
-    """[N, K] fp32 master weight -> bf16 (or split hi|lo bf16) K-major TMA operand + fp32 bias."""
+def pack_linear(weight: torch.Tensor, bias: Optional[torch.Tensor], precision: str,
+                dtype: torch.dtype = torch.bfloat16) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """[N, K] fp32 master weight -> bf16 (or fp16, or split hi|lo bf16) K-major TMA operand + fp32 bias."""
     w = weight.detach().reshape(weight.shape[0], -1).to(torch.float32)
-    wp = ops.split_weight(w) if precision == "fp32" else w.to(torch.bfloat16).contiguous()
+    wp = ops.split_weight(w) if precision == "fp32" else w.to(dtype).contiguous()
     b = None if bias is None else bias.detach().to(torch.float32).contiguous()
     return wp, b
 

@@ -74,11 +74,12 @@ def gemm(
 ) -> torch.Tensor:
     """out = epilogue(A @ W.T + bias).  A [M,K] / W [N,K] bf16 (or [.,2K] split when split3).
     ln_out (bf16 [M,N], with EPI_RESIDUAL_F32): also LayerNorm(updated out rows) in the same kernel."""
-    assert A.dim() == 2 and W.dim() == 2 and A.dtype == torch.bfloat16 and W.dtype == torch.bfloat16
+    split3 = int(split3)  # 0 plain, 1 both operands split (hi|lo), 2 only W split (A exact bf16)
+    assert A.dim() == 2 and W.dim() == 2 and W.dtype == A.dtype, "A and W must share one 16-bit format"
+    assert A.dtype == torch.bfloat16 or (A.dtype == torch.float16 and split3 == 0), "operands must be bf16 (or fp16 in plain mode)"
     assert A.stride(1) == 1 and W.stride(1) == 1 and out.stride(-1) == 1
     M = A.shape[0]
     N = W.shape[0]
-    split3 = int(split3)  # 0 plain, 1 both operands split (hi|lo), 2 only W split (A exact bf16)
     K = W.shape[1] // 2 if split3 else W.shape[1]
     assert A.shape[1] == (2 * K if split3 == 1 else K), (A.shape, W.shape, split3)
     a = _lib.GemmArgs()
@@ -89,6 +90,7 @@ def gemm(
     a.ldo = out.stride(-2) if out.dim() >= 2 else out.shape[-1]
     a.split3 = split3
     a.relu = 1 if relu else 0
+    a.fp16_operands = 1 if A.dtype == torch.float16 else 0
     a.epilogue = epilogue
     a.rows_per_group, a.dest_rows_per_group, a.pos_period = rows_per_group, dest_rows_per_group, pos_period
     if ln_out is not None:

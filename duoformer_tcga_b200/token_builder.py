@@ -167,12 +167,13 @@ class TokenBuilder(engine.PackCache):
             self._maps[key] = {k: m.to(device) for k, m in token_row_maps(num_layers, g).items()}
         return self._maps[key]
 
-    def pack(self, projection: nn.Module, num_layers: int, precision: str) -> Dict[int, Tuple]:
+    def pack(self, projection: nn.Module, num_layers: int, precision: str,
+             dtype: torch.dtype = torch.bfloat16) -> Dict[int, Tuple]:
         def build():
-            return {k: engine.pack_linear(projection.head(k).weight, projection.head(k).bias, precision)
+            return {k: engine.pack_linear(projection.head(k).weight, projection.head(k).bias, precision, dtype)
                     for k in stages_used(num_layers)}
 
-        return self.packed(build, projection, precision)
+        return self.packed(build, projection, precision + str(dtype))
 
     @torch.no_grad()
     def build(
@@ -197,14 +198,16 @@ class TokenBuilder(engine.PackCache):
         X = torch.empty(B, P, S, D, dtype=torch.float32, device=dev)
         ops.fill_scale_token(X, scale_tok, pos_scale[0])
         maps = self.row_maps(num_layers, g, dev)
-        packs = self.pack(projection, num_layers, precision)
+        # fp16 trunk maps feed the GEMM as they are, against fp16 copies of the 1x1-conv weights
+        op_dtype = torch.float16 if (precision == "bf16" and feats[3].dtype == torch.float16) else torch.bfloat16
+        packs = self.pack(projection, num_layers, precision, op_dtype)
         for k in stages_used(num_layers):
             f = feats[k]
             Bk, C, H, W = f.shape
             assert H == g * 2 ** (3 - k) and W == H, f"stage {k}: expected {g * 2 ** (3 - k)}^2, got {H}x{W}"
             rows = f.permute(0, 2, 3, 1)  # NHWC view; contiguous when f is channels-last
             if precision == "bf16":
-                A = rows.to(torch.bfloat16).contiguous().view(Bk * H * W, C)
+                A = rows.to(op_dtype).contiguous().view(Bk * H * W, C)
             else:
                 a32 = rows.to(torch.float32).contiguous().view(Bk * H * W, C)
                 A = torch.empty(Bk * H * W, 2 * C, dtype=torch.bfloat16, device=dev)

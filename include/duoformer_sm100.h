@@ -97,7 +97,10 @@ typedef struct duo_gemm_args {
   int32_t pos_period;          /* SCATTER: S                                               */
   float ln_eps;                /* fused LayerNorm epsilon                                  */
   int32_t relu;                /* BF16 / F32 epilogues: out = max(acc + bias, 0) (conv + BN + ReLU of   */
-  int32_t reserved;            /* the channel-token branch, projection_head.py:242-254)               */
+  int32_t fp16_operands;       /* the channel-token branch, projection_head.py:242-254).               */
+                               /* fp16_operands = 1: A and W hold IEEE fp16 instead of bf16 (the cuDNN */
+                               /* trunk maps are fed as they are; plain mode only, split3 == 0; one    */
+                               /* tcgen05.mma takes A and B of the same 16-bit format)                 */
   /* RESIDUAL_F32 + fused LayerNorm (optional, ln_out != NULL, bf16 operands, N <= 1024):     */
   /* after out += gamma*(acc+bias), ln_out[M,N] (bf16, dense) = LayerNorm(out rows) — the      */
   /* x = x + f(x); norm(x) pair of scale_attention.py:91-92 in one kernel.                     */

@@ -251,6 +251,18 @@ def test_gemm_residual_with_fused_layernorm(M, K, with_gamma):
         assert int(sync.abs().max()) == 0
 
 
+@pytest.mark.parametrize("M,N,K", [(300, 768, 256), (256 * 150 + 3, 768, 512)])
+def test_gemm_fp16_operands(M, N, K):
+    """fp16_operands: A (the cuDNN trunk maps) and W in IEEE fp16, tcgen05.mma kind::f16 (1-CTA and pair kernels)."""
+    A = _gen((M, K), 131).to(torch.float16)
+    W = _gen((N, K), 132, 0.05).to(torch.float16)
+    bias = _gen((N,), 133)
+    ref = A.float() @ W.float().t() + bias
+    out = torch.empty(M, N, dtype=torch.float32, device="cuda")
+    ops.gemm(A, W, bias, out, ops.EPI_F32)
+    assert relerr(out, ref) < 2e-5  # exact products, fp32 accumulation
+
+
 def test_gemm_split_mode_2_plain_A_split_W():
     """split3 == 2: exact bf16 activations times hi|lo-split weights (A*Wh + A*Wl)."""
     M, N, K = 700, 768, 768
