@@ -34,6 +34,7 @@ EXPORTED_SYMBOLS = (
     "duo_convert",
     "duo_im2col3x3",
     "duo_pool_to_slice",
+    "duo_maxpool3x3s2",
 )
 
 
@@ -118,6 +119,8 @@ def load() -> ctypes.CDLL:
     lib.duo_im2col3x3.argtypes = [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]
     lib.duo_pool_to_slice.restype = c_int32
     lib.duo_pool_to_slice.argtypes = [c_void_p, c_int32, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]
+    lib.duo_maxpool3x3s2.restype = c_int32
+    lib.duo_maxpool3x3s2.argtypes = [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]
     _lib = lib
     return lib
 

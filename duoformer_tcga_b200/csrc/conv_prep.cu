@@ -110,6 +110,47 @@ __global__ void pool_to_slice_kernel(const T* __restrict__ in, __nv_bfloat16* __
   }
 }
 
+// MaxPool2d(kernel 3, stride 2, padding 1) on NHWC, same 16-bit type in and out (max of representable
+// values is exact).  One thread per (output pixel, 8 channels): the 3x3 window is 9 coalesced 16-byte loads.
+template <typename T2>  // __half2 or __nv_bfloat162
+__global__ void maxpool3x3s2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W,
+                                    int C, int Ho, int Wo) {
+  const int c8n = C >> 3;
+  const int64_t total = static_cast<int64_t>(B) * Ho * Wo * c8n;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % c8n);
+    const int64_t r = i / c8n;
+    const int xo = static_cast<int>(r % Wo);
+    const int yo = static_cast<int>((r / Wo) % Ho);
+    const int64_t b = r / (static_cast<int64_t>(Wo) * Ho);
+    const int y0 = 2 * yo - 1, x0 = 2 * xo - 1;
+    bool have = false;
+    uint4 m = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int y = y0 + dy;
+      if (y < 0 || y >= H) continue;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int x = x0 + dx;
+        if (x < 0 || x >= W) continue;
+        const uint4 v = __ldg(in + ((b * H + y) * W + x) * c8n + c8);
+        if (!have) {
+          m = v;
+          have = true;
+        } else {
+          T2* mm = reinterpret_cast<T2*>(&m);
+          const T2* vv = reinterpret_cast<const T2*>(&v);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) mm[j] = __hmax2(mm[j], vv[j]);
+        }
+      }
+    }
+    out[r * c8n + c8] = m;
+  }
+}
+
 inline unsigned grid_for(int64_t total) {
   const int64_t want = (total + 255) / 256;
   const int64_t cap = static_cast<int64_t>(device_sm_count()) * 16;
@@ -142,6 +183,27 @@ extern "C" int duo_im2col3x3(const void* in, int32_t in_kind, void* out, int32_t
     default: set_error("duo_im2col3x3: in_kind=%d", in_kind); return DUO_ERR_INVALID;
   }
   DUO_LAUNCH_CHECK("im2col3x3_kernel");
+  return DUO_OK;
+}
+
+extern "C" int duo_maxpool3x3s2(const void* in, int32_t kind, void* out, int32_t B, int32_t H, int32_t W,
+                                int32_t C, duo_stream_t stream) {
+  using namespace duo;
+  DUO_CHECK_ARG(in && out, "duo_maxpool3x3s2: NULL pointer");
+  DUO_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "duo_maxpool3x3s2: bad dims B=%d H=%d W=%d C=%d", B, H, W, C);
+  DUO_CHECK_ARG(((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+                "duo_maxpool3x3s2: pointers must be 16-byte aligned");
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;  // kernel 3, stride 2, padding 1
+  const int64_t total = static_cast<int64_t>(B) * Ho * Wo * (C / 8);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const uint4* i4 = reinterpret_cast<const uint4*>(in);
+  uint4* o4 = reinterpret_cast<uint4*>(out);
+  switch (kind) {
+    case DUO_ACT_BF16: maxpool3x3s2_kernel<__nv_bfloat162><<<grid_for(total), 256, 0, st>>>(i4, o4, B, H, W, C, Ho, Wo); break;
+    case DUO_ACT_F16: maxpool3x3s2_kernel<__half2><<<grid_for(total), 256, 0, st>>>(i4, o4, B, H, W, C, Ho, Wo); break;
+    default: set_error("duo_maxpool3x3s2: kind=%d (bf16 or f16 only)", kind); return DUO_ERR_INVALID;
+  }
+  DUO_LAUNCH_CHECK("maxpool3x3s2_kernel");
   return DUO_OK;
 }
 

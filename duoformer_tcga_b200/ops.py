@@ -253,6 +253,18 @@ def pool_to_slice(x_nhwc: torch.Tensor, out_slice: torch.Tensor, pool: int) -> t
     return out_slice
 
 
+def maxpool3x3s2(x: torch.Tensor) -> torch.Tensor:
+    """nn.MaxPool2d(3, 2, 1) of a channels-last fp16 / bf16 NCHW tensor; returns a channels-last tensor."""
+    assert x.dim() == 4 and x.dtype in (torch.float16, torch.bfloat16)
+    assert x.is_contiguous(memory_format=torch.channels_last), "channels-last input expected"
+    B, C, H, W = x.shape
+    out = torch.empty(B, C, (H - 1) // 2 + 1, (W - 1) // 2 + 1, dtype=x.dtype, device=x.device,
+                      memory_format=torch.channels_last)
+    _lib.check(_lib.load().duo_maxpool3x3s2(_ptr(x), _IN_KIND[x.dtype], _ptr(out), B, H, W, C, _stream()),
+               "duo_maxpool3x3s2")
+    return out
+
+
 def launch_count() -> int:
     return int(_lib.load().duo_launch_count())
 

@@ -64,6 +64,19 @@ def _fused_bottleneck(blk: nn.Module, x: torch.Tensor) -> torch.Tensor:
                                             *_conv_args(blk.conv3))
 
 
+def _stem_pool(pool: nn.Module, x: torch.Tensor) -> torch.Tensor:
+    """The stem's MaxPool2d(3, 2, 1): own NHWC kernel (torch's channels-last max-pool runs at ~10 % of the
+    HBM roofline: 0.75 ms per 256 images); any other pooling configuration goes through the module."""
+    def pair(v):
+        return tuple(v) if isinstance(v, (tuple, list)) else (v, v)
+    std = (isinstance(pool, nn.MaxPool2d) and pair(pool.kernel_size) == (3, 3) and pair(pool.stride) == (2, 2)
+           and pair(pool.padding) == (1, 1) and pair(pool.dilation) == (1, 1) and not pool.ceil_mode)
+    if (std and x.is_cuda and x.dtype in (torch.float16, torch.bfloat16) and x.shape[1] % 8 == 0
+            and x.is_contiguous(memory_format=torch.channels_last)):
+        return ops.maxpool3x3s2(x)
+    return pool(x)
+
+
 def _fused_trunk_forward(t: nn.Module, x: torch.Tensor, by_scale: bool) -> Dict[int, torch.Tensor]:
     """Forward of a BN-folded ResNet-50 trunk with fused cuDNN epilogues; returns the four stage maps."""
     if by_scale:
@@ -74,7 +87,7 @@ def _fused_trunk_forward(t: nn.Module, x: torch.Tensor, by_scale: bool) -> Dict[
         stem, pool = ch["0"], ch["3"]
         layers = [ch["4"], ch["5"], ch["6"], ch["7"]]
     x = torch.cudnn_convolution_relu(x, stem.weight, stem.bias, *_conv_args(stem))
-    x = pool(x)
+    x = _stem_pool(pool, x)
     feats: Dict[int, torch.Tensor] = {}
     for i, layer in enumerate(layers):
         for blk in layer:

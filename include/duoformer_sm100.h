@@ -193,6 +193,14 @@ int duo_im2col3x3(const void* in, int32_t in_kind, void* out, int32_t B, int32_t
 int duo_pool_to_slice(const void* in, int32_t in_kind, void* out, int64_t ld_out, int32_t B, int32_t H,
                       int32_t W, int32_t C, int32_t pool, duo_stream_t stream);
 
+/*
+ * Trunk stem pooling: nn.MaxPool2d(kernel_size=3, stride=2, padding=1) of torchvision's ResNet
+ * (resnet50ssl.py:35-45 / torchvision resnet.py, between conv1 and layer1) on an NHWC map,
+ * bf16 or f16 (`kind`), same type out: [B,H,W,C] -> [B,ceil(H/2),ceil(W/2),C].  C % 8 == 0.
+ */
+int duo_maxpool3x3s2(const void* in, int32_t kind, void* out, int32_t B, int32_t H, int32_t W, int32_t C,
+                     duo_stream_t stream);
+
 /* fp32 [rows, cols] (leading dim ld) -> bf16 / split bf16 (contiguous). */
 int duo_convert(const float* in, int64_t ld, void* out, int32_t out_kind, int64_t rows,
                 int32_t cols, duo_stream_t stream);

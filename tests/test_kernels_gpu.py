@@ -263,6 +263,16 @@ def test_gemm_fp16_operands(M, N, K):
     assert relerr(out, ref) < 2e-5  # exact products, fp32 accumulation
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("B,C,H,W", [(3, 64, 112, 112), (2, 8, 7, 9), (1, 16, 1, 1)])
+def test_maxpool3x3s2_nhwc_matches_torch(B, C, H, W, dtype):
+    """duo_maxpool3x3s2 == nn.MaxPool2d(3, 2, 1) bit for bit (the ResNet stem pool), odd sizes included."""
+    x = _gen((B, C, H, W), 141).to(dtype).contiguous(memory_format=torch.channels_last)
+    ref = torch.nn.functional.max_pool2d(x, 3, 2, 1)
+    out = ops.maxpool3x3s2(x)
+    assert out.shape == ref.shape and torch.equal(out, ref)
+
+
 def test_gemm_split_mode_2_plain_A_split_W():
     """split3 == 2: exact bf16 activations times hi|lo-split weights (A*Wh + A*Wl)."""
     M, N, K = 700, 768, 768
