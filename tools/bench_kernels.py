@@ -69,7 +69,8 @@ def main():
 
     shapes = [("qkv", 3 * D, D, ops.EPI_BF16), ("proj_residual", D, D, ops.EPI_RESIDUAL_F32),
               ("fc1_gelu", 4 * D, D, ops.EPI_GELU_BF16), ("fc1_nogelu", 4 * D, D, ops.EPI_BF16),
-              ("fc2_residual", D, 4 * D, ops.EPI_RESIDUAL_F32)]
+              ("fc2_residual", D, 4 * D, ops.EPI_RESIDUAL_F32), ("fc2_shape_bf16out", D, 4 * D, ops.EPI_BF16),
+              ("proj_shape_bf16out", D, D, ops.EPI_BF16)]
     for name, N, K, epi in shapes:
         if a.only and "gemm" not in a.only and not any(tok in name for tok in a.only.split(",")):
             continue
