@@ -19,6 +19,8 @@ EPI_BF16, EPI_GELU_BF16, EPI_RESIDUAL_F32, EPI_SCATTER_F32, EPI_F32, EPI_SPLIT_B
 ACT_BF16, ACT_SPLIT, ACT_F32, ACT_F16 = range(4)
 
 # every symbol include/duoformer_sm100.h declares
+ABI_VERSION = 2  # duo_abi_version() of the library this binding was written against
+
 EXPORTED_SYMBOLS = (
     "duo_last_error",
     "duo_abi_version",
@@ -97,6 +99,9 @@ def load() -> ctypes.CDLL:
     lib.duo_last_error.restype = c_char_p
     lib.duo_last_error.argtypes = []
     lib.duo_abi_version.restype = c_int32
+    if lib.duo_abi_version() != ABI_VERSION:  # a stale build: struct layouts would not match
+        raise RuntimeError(f"{LIB_PATH} has ABI version {lib.duo_abi_version()}, this package needs {ABI_VERSION}: "
+                           "rebuild with `python -c 'import __graft_entry__ as g; g.build()'`")
     lib.duo_launch_count.restype = c_int64
     lib.duo_launch_count_reset.restype = None
     lib.duo_gemm.restype = c_int32

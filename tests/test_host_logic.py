@@ -22,7 +22,7 @@ def test_c_abi_library_loads_and_exports_every_declared_symbol():
     lib = _lib.load()  # built by __graft_entry__.build(); fails loudly if missing
     for name in declared:
         assert hasattr(lib, name), f"{name} not exported"
-    assert lib.duo_abi_version() == 2
+    assert lib.duo_abi_version() == _lib.ABI_VERSION == 2
     assert lib.duo_last_error() is not None
 
 
