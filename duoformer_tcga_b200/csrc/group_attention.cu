@@ -41,10 +41,9 @@ __host__ __device__ constexpr int fma_smem_words_per_warp(int S, int kpl) {
   return (words + 3) & ~3;
 }
 
-// COOP = false: one warp per (group, head), several problems per CTA (small S).
-// COOP = true : the whole CTA works on ONE (group, head): K/V are staged once for all warps and the
-//               query rows are dealt round-robin to the warps (S >= 32: 4x the warps per staged byte).
-template <typename Tin, int OUT_KIND, int KPL, bool COOP>
+// One warp per (group, head), several problems per CTA: small S, or a single query row.
+// (S >= 32 with more than one query row goes to the cooperative, query-blocked kernel below.)
+template <typename Tin, int OUT_KIND, int KPL>
 __global__ void group_attention_fma_kernel(const Tin* __restrict__ qkv, void* __restrict__ out,
                                            int64_t num_problems, int S, int H, float scale,
                                            int q_rows) {
@@ -57,33 +56,22 @@ __global__ void group_attention_fma_kernel(const Tin* __restrict__ qkv, void* __
   const int warps_per_cta = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int64_t prob = COOP ? static_cast<int64_t>(blockIdx.x)
-                            : static_cast<int64_t>(blockIdx.x) * warps_per_cta + warp;
-  if (prob >= num_problems) return;  // (COOP: never true — grid == num_problems)
+  const int64_t prob = static_cast<int64_t>(blockIdx.x) * warps_per_cta + warp;
+  if (prob >= num_problems) return;
   const int64_t g = prob / H;
   const int h = static_cast<int>(prob - g * H);
   const int D = H * kHeadDim;
   const int64_t ld = 3 * static_cast<int64_t>(D);
 
-  uint32_t *Vs, *Ks;
-  float *qs, *ps;
-  if constexpr (COOP) {
-    Vs = smem_words;
-    Ks = Vs + S * WPR;
-    float* scratch = reinterpret_cast<float*>(smem_words + ((S * WPR + S * (WPR + 1) + 3) & ~3));
-    qs = scratch + warp * (64 + KPL * 32);
-    ps = qs + 64;
-  } else {
-    Vs = smem_words + static_cast<size_t>(warp) * fma_smem_words_per_warp<Tin>(S, KPL);
-    qs = reinterpret_cast<float*>(Vs + S * WPR);
-    ps = qs + 64;
-    Ks = reinterpret_cast<uint32_t*>(ps + KPL * 32);
-  }
+  uint32_t* Vs = smem_words + static_cast<size_t>(warp) * fma_smem_words_per_warp<Tin>(S, KPL);
+  float* qs = reinterpret_cast<float*>(Vs + S * WPR);
+  float* ps = qs + 64;
+  uint32_t* Ks = reinterpret_cast<uint32_t*>(ps + KPL * 32);
 
   const Tin* base = qkv + (g * S) * ld + h * kHeadDim;
   // ---- stage K and V of this head ----
-  const int stage_tid = COOP ? static_cast<int>(threadIdx.x) : lane;
-  const int stage_rows = (COOP ? static_cast<int>(blockDim.x) : 32) / VPR;
+  const int stage_tid = lane;
+  const int stage_rows = 32 / VPR;
   for (int r0 = 0; r0 < S; r0 += stage_rows) {
     const int r = r0 + stage_tid / VPR;
     const int vec = stage_tid % VPR;
@@ -96,7 +84,7 @@ __global__ void group_attention_fma_kernel(const Tin* __restrict__ qkv, void* __
       vd[0] = vv.x; vd[1] = vv.y; vd[2] = vv.z; vd[3] = vv.w;
     }
   }
-  if constexpr (COOP) __syncthreads(); else __syncwarp();
+  __syncwarp();
 
   int krow[KPL];
 #pragma unroll
@@ -105,7 +93,7 @@ __global__ void group_attention_fma_kernel(const Tin* __restrict__ qkv, void* __
     krow[kk] = (j < S ? j : S - 1) * (WPR + 1);
   }
 
-  for (int i = COOP ? warp : 0; i < q_rows; i += COOP ? warps_per_cta : 1) {
+  for (int i = 0; i < q_rows; ++i) {
     // q row -> shared (fp32)
     {
       const Tin* qp = base + i * ld + 2 * lane;
@@ -208,24 +196,223 @@ __global__ void group_attention_fma_kernel(const Tin* __restrict__ qkv, void* __
   }
 }
 
+// ---- cooperative variant with query blocking (S >= 32, more than one query row) -------------
+// The single-query loop above is bound by shared-memory wavefronts (every K / V word is re-read for
+// every query: ~300 wavefronts per query at S = 50).  Here a warp takes kQB queries at a time, so a
+// K row or V row read from shared memory feeds kQB dot products, and the probabilities are fetched
+// four keys per broadcast load: ~85 wavefronts per query.
+constexpr int kQB = 4;
+
+template <typename Tin, int OUT_KIND, int KPL>
+__global__ void group_attention_fma_qb_kernel(const Tin* __restrict__ qkv, void* __restrict__ out,
+                                              int S, int H, float scale, int q_rows) {
+  constexpr int WPR = ElemTraits<Tin>::kWordsPerRow;
+  constexpr int VPR = WPR / 4;
+  constexpr bool kIsBf16 = (WPR == 32);
+  constexpr int kPS = KPL * 32;  // probability row length
+  extern __shared__ uint32_t smem_words[];
+
+  const int warps_per_cta = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t prob = blockIdx.x;
+  const int64_t g = prob / H;
+  const int h = static_cast<int>(prob - g * H);
+  const int D = H * kHeadDim;
+  const int64_t ld = 3 * static_cast<int64_t>(D);
+
+  uint32_t* Vs = smem_words;
+  uint32_t* Ks = Vs + S * WPR;
+  float* scratch = reinterpret_cast<float*>(smem_words + ((S * WPR + S * (WPR + 1) + 3) & ~3));
+  float* qs = scratch + warp * (kQB * 64 + kQB * kPS);
+  float* ps = qs + kQB * 64;
+
+  const Tin* base = qkv + (g * S) * ld + h * kHeadDim;
+  {
+    const int stage_rows = static_cast<int>(blockDim.x) / VPR;
+    for (int r0 = 0; r0 < S; r0 += stage_rows) {
+      const int r = r0 + static_cast<int>(threadIdx.x) / VPR;
+      const int vec = static_cast<int>(threadIdx.x) % VPR;
+      if (r < S) {
+        const uint4 kv = __ldg(reinterpret_cast<const uint4*>(base + r * ld + D) + vec);
+        const uint4 vv = __ldg(reinterpret_cast<const uint4*>(base + r * ld + 2 * D) + vec);
+        uint32_t* kd = Ks + r * (WPR + 1) + vec * 4;
+        kd[0] = kv.x; kd[1] = kv.y; kd[2] = kv.z; kd[3] = kv.w;
+        uint32_t* vd = Vs + r * WPR + vec * 4;
+        vd[0] = vv.x; vd[1] = vv.y; vd[2] = vv.z; vd[3] = vv.w;
+      }
+    }
+  }
+  __syncthreads();
+
+  int krow[KPL];
+#pragma unroll
+  for (int kk = 0; kk < KPL; ++kk) {
+    const int j = lane + 32 * kk;
+    krow[kk] = (j < S ? j : S - 1) * (WPR + 1);
+  }
+
+  for (int i0 = warp * kQB; i0 < q_rows; i0 += warps_per_cta * kQB) {
+    // kQB query rows -> shared (fp32); rows past q_rows repeat the last one (results discarded)
+#pragma unroll
+    for (int qb = 0; qb < kQB; ++qb) {
+      const int i = (i0 + qb < q_rows) ? i0 + qb : q_rows - 1;
+      const Tin* qp = base + i * ld + 2 * lane;
+      float q0, q1;
+      if constexpr (kIsBf16) {
+        const __nv_bfloat162 q2 = *reinterpret_cast<const __nv_bfloat162*>(qp);
+        q0 = __bfloat162float(q2.x);
+        q1 = __bfloat162float(q2.y);
+      } else {
+        const float2 q2 = *reinterpret_cast<const float2*>(qp);
+        q0 = q2.x;
+        q1 = q2.y;
+      }
+      qs[qb * 64 + 2 * lane] = q0;
+      qs[qb * 64 + 2 * lane + 1] = q1;
+    }
+    __syncwarp();
+
+    float acc[KPL][kQB];
+#pragma unroll
+    for (int kk = 0; kk < KPL; ++kk)
+#pragma unroll
+      for (int qb = 0; qb < kQB; ++qb) acc[kk][qb] = 0.f;
+#pragma unroll 4
+    for (int e = 0; e < 64; e += 4) {  // four head-dim elements per step
+      float4 q4[kQB];
+#pragma unroll
+      for (int qb = 0; qb < kQB; ++qb) q4[qb] = *reinterpret_cast<const float4*>(qs + qb * 64 + e);
+#pragma unroll
+      for (int kk = 0; kk < KPL; ++kk) {
+        float k0, k1, k2, k3;
+        if constexpr (kIsBf16) {
+          const uint32_t k01 = Ks[krow[kk] + (e >> 1)];
+          const uint32_t k23 = Ks[krow[kk] + (e >> 1) + 1];
+          k0 = __uint_as_float(k01 << 16);
+          k1 = __uint_as_float(k01 & 0xffff0000u);
+          k2 = __uint_as_float(k23 << 16);
+          k3 = __uint_as_float(k23 & 0xffff0000u);
+        } else {
+          const float* kr = reinterpret_cast<const float*>(Ks) + krow[kk] + e;
+          k0 = kr[0]; k1 = kr[1]; k2 = kr[2]; k3 = kr[3];
+        }
+#pragma unroll
+        for (int qb = 0; qb < kQB; ++qb) {
+          acc[kk][qb] = fmaf(q4[qb].x, k0, acc[kk][qb]);
+          acc[kk][qb] = fmaf(q4[qb].y, k1, acc[kk][qb]);
+          acc[kk][qb] = fmaf(q4[qb].z, k2, acc[kk][qb]);
+          acc[kk][qb] = fmaf(q4[qb].w, k3, acc[kk][qb]);
+        }
+      }
+    }
+
+#pragma unroll
+    for (int qb = 0; qb < kQB; ++qb) {
+      float m = -INFINITY;
+#pragma unroll
+      for (int kk = 0; kk < KPL; ++kk) {
+        acc[kk][qb] = (lane + 32 * kk < S) ? acc[kk][qb] * scale : -INFINITY;
+        m = fmaxf(m, acc[kk][qb]);
+      }
+      m = warp_max(m);
+      float sum = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < KPL; ++kk) {
+        acc[kk][qb] = (lane + 32 * kk < S) ? __expf(acc[kk][qb] - m) : 0.f;
+        sum += acc[kk][qb];
+      }
+      sum = warp_sum(sum);
+      const float inv = 1.0f / sum;
+#pragma unroll
+      for (int kk = 0; kk < KPL; ++kk) ps[qb * kPS + lane + 32 * kk] = acc[kk][qb] * inv;
+    }
+    __syncwarp();
+
+    float o0[kQB], o1[kQB];
+#pragma unroll
+    for (int qb = 0; qb < kQB; ++qb) o0[qb] = o1[qb] = 0.f;
+    auto v_pair = [&](int j, float& v0, float& v1) {
+      if constexpr (kIsBf16) {
+        const uint32_t v01 = Vs[j * WPR + lane];
+        v0 = __uint_as_float(v01 << 16);
+        v1 = __uint_as_float(v01 & 0xffff0000u);
+      } else {
+        const float2 v01 = *reinterpret_cast<const float2*>(Vs + j * WPR + 2 * lane);
+        v0 = v01.x;
+        v1 = v01.y;
+      }
+    };
+    const int S4 = S & ~3;
+    for (int j = 0; j < S4; j += 4) {
+      float4 p4[kQB];
+#pragma unroll
+      for (int qb = 0; qb < kQB; ++qb) p4[qb] = *reinterpret_cast<const float4*>(ps + qb * kPS + j);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        float v0, v1;
+        v_pair(j + t, v0, v1);
+#pragma unroll
+        for (int qb = 0; qb < kQB; ++qb) {
+          const float pj = t == 0 ? p4[qb].x : (t == 1 ? p4[qb].y : (t == 2 ? p4[qb].z : p4[qb].w));
+          o0[qb] = fmaf(pj, v0, o0[qb]);
+          o1[qb] = fmaf(pj, v1, o1[qb]);
+        }
+      }
+    }
+    for (int j = S4; j < S; ++j) {
+      float v0, v1;
+      v_pair(j, v0, v1);
+#pragma unroll
+      for (int qb = 0; qb < kQB; ++qb) {
+        const float pj = ps[qb * kPS + j];
+        o0[qb] = fmaf(pj, v0, o0[qb]);
+        o1[qb] = fmaf(pj, v1, o1[qb]);
+      }
+    }
+
+    const int ocol = h * kHeadDim + 2 * lane;
+#pragma unroll
+    for (int qb = 0; qb < kQB; ++qb) {
+      if (i0 + qb >= q_rows) break;
+      const int64_t orow = g * q_rows + i0 + qb;
+      if constexpr (OUT_KIND == DUO_ACT_BF16) {
+        reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(out) + orow * D + ocol)[0] =
+            pack_bf16x2(o0[qb], o1[qb]);
+      } else if constexpr (OUT_KIND == DUO_ACT_SPLIT) {
+        uint32_t hi, lo;
+        pack_split2(o0[qb], o1[qb], hi, lo);
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + orow * (2 * D) + ocol;
+        reinterpret_cast<uint32_t*>(o)[0] = hi;
+        reinterpret_cast<uint32_t*>(o + D)[0] = lo;
+      } else {
+        reinterpret_cast<float2*>(reinterpret_cast<float*>(out) + orow * D + ocol)[0] =
+            make_float2(o0[qb], o1[qb]);
+      }
+    }
+    __syncwarp();
+  }
+}
+
 template <typename Tin, int OUT_KIND, int KPL>
 int launch_fma(const void* qkv, void* out, int64_t groups, int S, int H, float scale, int q_rows,
                cudaStream_t st) {
   const int64_t problems = groups * H;
   if (S >= 32 && q_rows > 1) {
-    // cooperative CTA per problem: one K/V copy shared by four warps
+    // cooperative CTA per problem: one K/V copy shared by four warps, kQB queries per warp pass
     constexpr int WPR = ElemTraits<Tin>::kWordsPerRow;
     const int warps = 4;
-    const size_t smem = (static_cast<size_t>((S * WPR + S * (WPR + 1) + 3) & ~3) + warps * (64 + KPL * 32)) * 4;
+    const size_t smem =
+        (static_cast<size_t>((S * WPR + S * (WPR + 1) + 3) & ~3) + warps * (kQB * 64 + kQB * KPL * 32)) * 4;
     if (smem > 220 * 1024 || problems >= (int64_t(1) << 31)) {
       set_error("duo_group_attention: S=%d / %lld problems unsupported", S, (long long)problems);
       return DUO_ERR_INVALID;
     }
-    auto kfn = group_attention_fma_kernel<Tin, OUT_KIND, KPL, true>;
+    auto kfn = group_attention_fma_qb_kernel<Tin, OUT_KIND, KPL>;
     DUO_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    kfn<<<static_cast<unsigned>(problems), warps * 32, smem, st>>>(reinterpret_cast<const Tin*>(qkv), out,
-                                                                   problems, S, H, scale, q_rows);
-    DUO_LAUNCH_CHECK("group_attention_fma_kernel");
+    kfn<<<static_cast<unsigned>(problems), warps * 32, smem, st>>>(reinterpret_cast<const Tin*>(qkv), out, S, H, scale,
+                                                                   q_rows);
+    DUO_LAUNCH_CHECK("group_attention_fma_qb_kernel");
     return DUO_OK;
   }
   const size_t per_warp = static_cast<size_t>(fma_smem_words_per_warp<Tin>(S, KPL)) * 4;
@@ -236,7 +423,7 @@ int launch_fma(const void* qkv, void* out, int64_t groups, int S, int H, float s
     set_error("duo_group_attention: S=%d needs %zu B of shared memory", S, smem);
     return DUO_ERR_INVALID;
   }
-  auto kfn = group_attention_fma_kernel<Tin, OUT_KIND, KPL, false>;
+  auto kfn = group_attention_fma_kernel<Tin, OUT_KIND, KPL>;
   DUO_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(smem)));
   const int64_t grid = (problems + warps - 1) / warps;
