@@ -521,7 +521,8 @@ group_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16*
 #pragma unroll
       for (int r = r_first; r < S_PAD; r += kRowsPerPass) {
         const uint32_t dst = dst0 + static_cast<uint32_t>(r * 128 + ((c ^ (r & 7)) << 4));
-        if (r < S) {
+        // Q rows are only needed up to the last computed 16-row query tile (q_rows = 1: 16 of 86 rows)
+        if (r < S && (which != 0 || r < ((q_rows + 15) & ~15))) {
           cp_async_16(dst, s0 + static_cast<int64_t>(r) * ld);
         } else {
           asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0u) : "memory");
