@@ -690,7 +690,7 @@ __launch_bounds__(PairCfg<EPI_WARPS, EPI == kEpiResidualLn>::kThreads, 1)
 gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
                          const __grid_constant__ CUtensorMap tmap_b,
                          const __grid_constant__ CUtensorMap tmap_out,
-                         const __grid_constant__ CUtensorMap tmap_ln, const GemmParams p) {
+                         const GemmParams p) {
   using C = PairCfg<EPI_WARPS, EPI == kEpiResidualLn>;
   using ET = EpiTraits<EPI>;
   constexpr int kStages = C::kStages;
@@ -989,7 +989,7 @@ int dispatch_epi(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap
 }
 
 template <int EPI, int EPI_WARPS>
-int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tl,
+int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
                 const GemmParams& p, cudaStream_t st) {
   using C = PairCfg<EPI_WARPS, EPI == kEpiResidualLn>;
   static uint64_t configured = 0;  // per device
@@ -1003,31 +1003,31 @@ int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
   const int sms_avail = device_sm_count();
   const int pairs_max = ((sm_cap > 1 && sm_cap < sms_avail) ? sm_cap : sms_avail) / 2;
   const int pairs = static_cast<int>(units < pairs_max ? units : pairs_max);
-  kfn<<<2 * pairs, C::kThreads, C::kSmemBytes, st>>>(ta, tb, to, tl, p);
+  kfn<<<2 * pairs, C::kThreads, C::kSmemBytes, st>>>(ta, tb, to, p);
   DUO_LAUNCH_CHECK("gemm_tcgen05_pair_kernel");
   return DUO_OK;
 }
 
-int dispatch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tl,
+int dispatch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
                   const GemmParams& p, int epi, cudaStream_t st) {
   switch (epi) {
-    case kEpiResidualLn: return launch_pair<kEpiResidualLn, 4>(ta, tb, to, tl, p, st);
-    case DUO_EPI_BF16: return launch_pair<DUO_EPI_BF16, 4>(ta, tb, to, to, p, st);
+    case kEpiResidualLn: return launch_pair<kEpiResidualLn, 4>(ta, tb, to, p, st);
+    case DUO_EPI_BF16: return launch_pair<DUO_EPI_BF16, 4>(ta, tb, to, p, st);
     case DUO_EPI_GELU_BF16: {
       static const int gelu_warps = [] { const char* e = getenv("DUO_GEMM_GELU_WARPS"); return (e && e[0] == '4') ? 4 : 8; }();
-      return gelu_warps == 8 ? launch_pair<DUO_EPI_GELU_BF16, 8>(ta, tb, to, to, p, st)
-                             : launch_pair<DUO_EPI_GELU_BF16, 4>(ta, tb, to, to, p, st);
+      return gelu_warps == 8 ? launch_pair<DUO_EPI_GELU_BF16, 8>(ta, tb, to, p, st)
+                             : launch_pair<DUO_EPI_GELU_BF16, 4>(ta, tb, to, p, st);
     }
-    case DUO_EPI_RESIDUAL_F32: return launch_pair<DUO_EPI_RESIDUAL_F32, 4>(ta, tb, to, to, p, st);
-    case kEpiResidualTma: return launch_pair<kEpiResidualTma, 4>(ta, tb, to, to, p, st);
+    case DUO_EPI_RESIDUAL_F32: return launch_pair<DUO_EPI_RESIDUAL_F32, 4>(ta, tb, to, p, st);
+    case kEpiResidualTma: return launch_pair<kEpiResidualTma, 4>(ta, tb, to, p, st);
     case DUO_EPI_SCATTER_F32: {  // short K, store-bound epilogue: 8 warps (DUO_GEMM_SCATTER_WARPS=4 for the A/B)
       static const int w = [] { const char* e = getenv("DUO_GEMM_SCATTER_WARPS"); return (e && e[0] == '4') ? 4 : 8; }();
-      return w == 8 ? launch_pair<DUO_EPI_SCATTER_F32, 8>(ta, tb, to, to, p, st)
-                    : launch_pair<DUO_EPI_SCATTER_F32, 4>(ta, tb, to, to, p, st);
+      return w == 8 ? launch_pair<DUO_EPI_SCATTER_F32, 8>(ta, tb, to, p, st)
+                    : launch_pair<DUO_EPI_SCATTER_F32, 4>(ta, tb, to, p, st);
     }
-    case DUO_EPI_F32: return launch_pair<DUO_EPI_F32, 4>(ta, tb, to, to, p, st);
-    case DUO_EPI_SPLIT_BF16: return launch_pair<DUO_EPI_SPLIT_BF16, 4>(ta, tb, to, to, p, st);
-    case DUO_EPI_GELU_SPLIT_BF16: return launch_pair<DUO_EPI_GELU_SPLIT_BF16, 8>(ta, tb, to, to, p, st);
+    case DUO_EPI_F32: return launch_pair<DUO_EPI_F32, 4>(ta, tb, to, p, st);
+    case DUO_EPI_SPLIT_BF16: return launch_pair<DUO_EPI_SPLIT_BF16, 4>(ta, tb, to, p, st);
+    case DUO_EPI_GELU_SPLIT_BF16: return launch_pair<DUO_EPI_GELU_SPLIT_BF16, 8>(ta, tb, to, p, st);
     default: set_error("duo_gemm: unknown epilogue %d", epi); return DUO_ERR_INVALID;
   }
 }
@@ -1117,12 +1117,6 @@ extern "C" int duo_gemm(const duo_gemm_args* a, duo_stream_t stream) {
     to = ta;  // unused by the direct-store epilogues
   }
   if (rc != DUO_OK) return rc;
-  CUtensorMap tl = to;
-  if (fused_ln) {
-    rc = make_tmap(&tl, a->ln_out, a->M, a->N, a->N, 32, 2);
-    if (rc != DUO_OK) return rc;
-  }
-
   GemmParams p;
   p.ln_gamma = a->ln_gamma;
   p.ln_beta = a->ln_beta;
@@ -1147,7 +1141,7 @@ extern "C" int duo_gemm(const duo_gemm_args* a, duo_stream_t stream) {
   p.idesc_mask = a->fp16_operands ? ~((1u << 7) | (1u << 10)) : ~0u;  // a_format / b_format: 1 = BF16, 0 = F16
   p.num_n_blocks = use_pair ? a->N / kPairBlockN : a->N / block_n;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (use_pair) return dispatch_pair(ta, tb, to, tl, p, epi, st);
+  if (use_pair) return dispatch_pair(ta, tb, to, p, epi, st);
   rc = block_n == 256 ? dispatch_epi<256>(ta, tb, to, p, epi, st) : dispatch_epi<128>(ta, tb, to, p, epi, st);
   if (rc != DUO_OK || !want_ln) return rc;
   // small problems: unfused — LayerNorm of the updated rows as a second launch
