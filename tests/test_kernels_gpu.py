@@ -135,6 +135,16 @@ def test_group_attention_bf16(S, G, algo):
     assert relerr(out, ref) < (1.5e-2 if algo >= 2 else 8e-3)
 
 
+@pytest.mark.parametrize("H,S,G,algo", [(6, 86, 33, 3), (6, 86, 33, 2), (1, 90, 7, 3), (16, 70, 5, 3), (6, 50, 9, 1)])
+def test_group_attention_other_head_counts(H, S, G, algo):
+    """embed_dim = 64 * H for H != 12 (e.g. the 384-wide model): column offsets which*D + h*64 must follow H."""
+    qkv = _gen((G * S, 3 * H * 64), 71 + S + H, 2.0).to(torch.bfloat16)
+    ref = _attn_ref(qkv, S, H, 0.125)
+    out = torch.empty(G * S, H * 64, dtype=torch.bfloat16, device="cuda")
+    ops.group_attention(qkv, out, S, H, 0.125, algo=algo)
+    assert relerr(out, ref) < 1.5e-2
+
+
 @pytest.mark.parametrize("S,G,algo,q_rows", [(86, 49, 2, 1), (86, 49, 1, 1), (22, 10, 2, 3), (6, 30, 1, 1), (50, 5, 2, 17)])
 def test_group_attention_leading_query_rows(S, G, algo, q_rows):
     H = 12
