@@ -1,5 +1,8 @@
+"""Diagnostic (run by hand on a GPU box): which stage breaks batch-permutation invariance bit for bit
+(finding: only the cuDNN trunk, by one fp16 ulp in layer4; the own kernels are bit-exact)."""
 import os, sys
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
+_here = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(_here)); sys.path.insert(0, _here)
 import torch
 from common import build_product, load_golden
 from oracle import synth
