@@ -84,3 +84,76 @@ class ShardedDuoFormer(torch.nn.Module):
         if y.dim() == 1:
             y = y.unsqueeze(0)
         return all_gather_logits(y, x.shape[0])
+
+
+class HostPipeline:
+    """Feeds host batches to a DuoFormer model and returns host logits: the host->device copy of batch
+    i+1 runs on its own stream while batch i is computed (two device input buffers); the logits of every
+    batch are copied to pinned host memory as soon as they exist and handed out one step late, so the
+    launch queue of the GPU never drains between batches.  On several GPUs every rank feeds its own
+    shard and receives the gathered logits of the whole step.
+
+        pipe = HostPipeline(model)            # model: cuda, eval
+        for logits in pipe.run(batches):      # batches: iterable of (ideally pinned) host tensors [b,3,H,W]
+            ...                               # logits: host fp32 [b * world, num_classes]
+    """
+
+    def __init__(self, model: torch.nn.Module, device: Optional[torch.device] = None, gather: bool = True):
+        self.model = model
+        self.device = device if device is not None else next(model.parameters()).device
+        assert self.device.type == "cuda", "HostPipeline feeds a CUDA model"
+        self.gather = gather
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self._bufs = [None, None]
+        self._consumed = [None, None]  # event: the forward that read buffer k has been enqueued and finished
+
+    def _stage(self, k: int, host: torch.Tensor):
+        """Enqueue the copy of `host` into device buffer k on the copy stream; returns (tensor, ready event)."""
+        buf = self._bufs[k]
+        if buf is None or buf.shape != host.shape or buf.dtype != host.dtype:
+            buf = torch.empty(host.shape, dtype=host.dtype, device=self.device)
+            self._bufs[k] = buf
+        with torch.cuda.stream(self.copy_stream):
+            if self._consumed[k] is not None:
+                self.copy_stream.wait_event(self._consumed[k])  # the previous user of this buffer is done
+            buf.copy_(host, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(self.copy_stream)
+        return buf, ready
+
+    @torch.no_grad()
+    def run(self, host_batches):
+        it = iter(host_batches)
+        first = next(it, None)
+        if first is None:
+            return
+        k = 0
+        staged = self._stage(k, first)
+        compute = torch.cuda.current_stream(self.device)
+        pending = None  # (pinned host logits, event) of the previous batch
+        while staged is not None:
+            x, ready = staged
+            nxt = next(it, None)
+            staged_next = self._stage(k ^ 1, nxt) if nxt is not None else None  # overlaps the forward below
+            compute.wait_event(ready)
+            y = self.model(x)
+            done = torch.cuda.Event()
+            done.record(compute)
+            self._consumed[k] = done
+            if y.dim() == 1:
+                y = y.unsqueeze(0)
+            if self.gather and dist.is_initialized() and dist.get_world_size() > 1:
+                y = all_gather_logits(y)
+            y = y.float()
+            y_host = torch.empty(y.shape, dtype=y.dtype, pin_memory=True)
+            y_host.copy_(y, non_blocking=True)  # device -> host read of this step's result
+            landed = torch.cuda.Event()
+            landed.record(compute)
+            if pending is not None:
+                pending[1].synchronize()
+                yield pending[0]
+            pending = (y_host, landed)
+            staged, k = staged_next, k ^ 1
+        if pending is not None:
+            pending[1].synchronize()
+            yield pending[0]

@@ -268,3 +268,25 @@ def test_cuda_graph_replay_matches_eager_and_is_faster_at_small_batch():
         t_eager, t_graph = lat(lambda: model(x)), lat(lambda: g(x))
     print(f"batch-2 2-scale forward latency: eager {t_eager:.2f} ms, CUDA graph {t_graph:.2f} ms")
     assert t_graph < t_eager
+
+
+def test_host_pipeline_feeds_batches_and_matches_direct_calls():
+    """parallel.HostPipeline (H2D of the next batch on a copy stream, two device buffers, logits read
+    back every step) returns the same logits, in order, as calling the model on each batch."""
+    from duoformer_tcga_b200 import parallel
+
+    gold = load_golden("wo4_d2")
+    case = gold["case"]
+    model = build_product(case)
+    model.load_state_dict(synth.synth_state_dict(model.state_dict(), seed=0))
+    model = model.cuda().eval()
+    batches = [synth.synth_images(n, seed=20 + i).pin_memory() for i, n in enumerate([2, 3, 2, 1, 2])]
+    with torch.no_grad():
+        direct = [model(b.cuda()).float().cpu().reshape(b.shape[0], -1) for b in batches]
+    pipe = parallel.HostPipeline(model)
+    piped = list(pipe.run(batches))
+    assert len(piped) == len(direct)
+    for a, b in zip(piped, direct):
+        assert a.shape == b.shape and not a.is_cuda
+        assert torch.equal(a, b)
+    assert list(pipe.run([])) == []
