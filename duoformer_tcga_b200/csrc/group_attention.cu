@@ -668,6 +668,7 @@ int launch_mma(const void* qkv, void* out, int64_t groups, int S, int H, float s
 
 namespace duo {
 int launch_scale_attention_tc(const void* qkv, void* out, int64_t groups, int S, int H, float scale, cudaStream_t st);
+int launch_patch_attention_tc(const void* qkv, void* out, int64_t groups, int N, int H, float scale, cudaStream_t st);
 }
 
 extern "C" int duo_group_attention(const void* qkv, int32_t in_kind, void* out, int32_t out_kind,
@@ -676,7 +677,7 @@ extern "C" int duo_group_attention(const void* qkv, int32_t in_kind, void* out, 
   using namespace duo;
   DUO_CHECK_ARG(qkv && out, "duo_group_attention: NULL pointer");
   DUO_CHECK_ARG(num_groups > 0 && S > 0 && num_heads > 0, "duo_group_attention: empty problem");
-  DUO_CHECK_ARG(in_kind == DUO_ACT_BF16 || in_kind == DUO_ACT_F32,
+  DUO_CHECK_ARG(in_kind == DUO_ACT_BF16 || in_kind == DUO_ACT_F32 || in_kind == DUO_ACT_SPLIT,
                 "duo_group_attention: in_kind=%d", in_kind);
   DUO_CHECK_ARG(out_kind == DUO_ACT_BF16 || out_kind == DUO_ACT_SPLIT || out_kind == DUO_ACT_F32,
                 "duo_group_attention: out_kind=%d", out_kind);
@@ -685,6 +686,12 @@ extern "C" int duo_group_attention(const void* qkv, int32_t in_kind, void* out, 
                 "duo_group_attention: pointers must be 16-byte aligned");
   DUO_CHECK_ARG(q_rows >= 1 && q_rows <= S, "duo_group_attention: q_rows=%d must be in [1, S=%d]", q_rows, S);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (in_kind == DUO_ACT_SPLIT) {  // hi | lo bf16 pairs in and out: the split-precision tcgen05 kernel only
+    DUO_CHECK_ARG(out_kind == DUO_ACT_SPLIT && S <= 64 && q_rows == S && (algo == 0 || algo == 3),
+                  "duo_group_attention: split input needs split output, S <= 64, q_rows == S (S=%d q_rows=%d algo=%d)", S,
+                  q_rows, algo);
+    return launch_patch_attention_tc(qkv, out, num_groups, S, num_heads, scale, st);
+  }
   const bool mma_ok = in_kind == DUO_ACT_BF16 && out_kind == DUO_ACT_BF16 && S > 16 && S <= 96;
   // auto: tcgen05 kernel for the 4-scale group size, mma.sync kernel for the other tensor-core sizes
   if (algo == 0) algo = (mma_ok && S > 64 && q_rows == S) ? 3 : (mma_ok ? 2 : 1);

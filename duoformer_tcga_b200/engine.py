@@ -285,7 +285,9 @@ def region_attention(
     Z <- proj(softmax(q k^T * scale) v)   (scale_attention.py:195-209, multiscale_attn.py:205-219).
 
     precision "bf16":  Z bf16 [B*N, D], everything bf16.
-              "fp32":  Z split [B*N, 2D]; 3-pass split GEMMs, fp32 qkv, fp32 FMA attention.
+              "fp32":  Z split [B*N, 2D]; 3-pass split GEMMs; attention in split precision on tcgen05 (N <= 64:
+                       q, k, v as hi | lo pairs, three UMMAs per product) or fp32 qkv + fp32 FMA attention
+                       (N > 64, and the CLS-only query of the last block).
               "mixed": Z split [B*N, 2D] (the tensor handed from block to block keeps ~16 mantissa
                        bits, weights are split too), but qkv and the attention output are bf16 so the
                        attention runs on the mma.sync kernel; proj multiplies the exact bf16
@@ -298,9 +300,19 @@ def region_attention(
     rows = Z.shape[0]
     D = Z.shape[1] // kd_io
     dev = Z.device
-    QKV = torch.empty(rows, 3 * D, dtype=torch.float32 if fp32 else torch.bfloat16, device=dev)
-    ops.gemm(Z, blk["qkv"][0], blk["qkv"][1], QKV, ops.EPI_F32 if fp32 else ops.EPI_BF16, split3=1 if split_io else 0)
-    if cls_only:
+    if fp32 and not cls_only and N <= 64:
+        # global attention on tcgen05 / TMEM in split precision: q, k, v stay hi | lo bf16 pairs end to end
+        QKV = torch.empty(rows, 6 * D, dtype=torch.bfloat16, device=dev)
+        ops.gemm(Z, blk["qkv"][0], blk["qkv"][1], QKV, ops.EPI_SPLIT_BF16, split3=1)
+        AO = torch.empty(rows, 2 * D, dtype=torch.bfloat16, device=dev)
+        ops.group_attention(QKV, AO, N, num_heads, scale, split_in=True)
+    else:
+        QKV = torch.empty(rows, 3 * D, dtype=torch.float32 if fp32 else torch.bfloat16, device=dev)
+        ops.gemm(Z, blk["qkv"][0], blk["qkv"][1], QKV, ops.EPI_F32 if fp32 else ops.EPI_BF16, split3=1 if split_io else 0)
+        AO = None
+    if AO is not None:
+        pass
+    elif cls_only:
         # last patch block: only the CLS query row of every image reaches the head (scale_attention.py:341)
         rows = rows // N
         AO = torch.empty(rows, kd_ao * D, dtype=torch.bfloat16, device=dev)

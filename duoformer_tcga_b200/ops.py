@@ -134,15 +134,20 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out: tor
 
 
 def group_attention(
-    qkv: torch.Tensor, out: torch.Tensor, S: int, num_heads: int, scale: float, algo: int = 0, q_rows: int = 0
+    qkv: torch.Tensor, out: torch.Tensor, S: int, num_heads: int, scale: float, algo: int = 0, q_rows: int = 0,
+    split_in: bool = False,
 ) -> torch.Tensor:
     """softmax(q k^T * scale) v per (group of S rows, head); qkv [rows, 3*D], out [rows, D | 2D].
-    q_rows > 0: only the first q_rows query rows per group; out is [groups * q_rows, D | 2D]."""
+    q_rows > 0: only the first q_rows query rows per group; out is [groups * q_rows, D | 2D].
+    split_in: qkv is split bf16 [rows, 2*3*D] (hi | lo, duo_gemm's SPLIT epilogue), out split [rows, 2D]:
+    the split-precision tcgen05 kernel (S <= 64)."""
     assert qkv.is_contiguous() and out.is_contiguous()
-    D = qkv.shape[-1] // 3
-    rows = qkv.numel() // (3 * D)
+    D = qkv.shape[-1] // (6 if split_in else 3)
+    rows = qkv.numel() // ((6 if split_in else 3) * D)
     assert rows % S == 0 and D == 64 * num_heads
-    in_kind = ACT_F32 if qkv.dtype == torch.float32 else ACT_BF16
+    if split_in:
+        assert qkv.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and out.shape[-1] == 2 * D
+    in_kind = ACT_SPLIT if split_in else (ACT_F32 if qkv.dtype == torch.float32 else ACT_BF16)
     out_kind = _act_kind(out, D)
     _lib.check(
         _lib.load().duo_group_attention(

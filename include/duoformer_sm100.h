@@ -132,6 +132,9 @@ int duo_layernorm(const float* x, const float* gamma, const float* beta, void* o
  * S = 6/22/86), scale_attention.py:195-207 / multiscale_attn.py:205-216 (patch attention,
  * group = one image, S = P+1).  head_dim must be 64.
  * in_kind: DUO_ACT_BF16 or DUO_ACT_F32; out_kind: DUO_ACT_BF16 / DUO_ACT_SPLIT / DUO_ACT_F32.
+ * in_kind DUO_ACT_SPLIT (qkv rows = [hi: q k v | lo: q k v], the SPLIT epilogue of duo_gemm) with out_kind
+ * DUO_ACT_SPLIT, S <= 64, q_rows == S: the global patch attention in split-bf16 precision on tcgen05 / TMEM
+ * (three bf16 UMMAs per product: hi*hi + hi*lo + lo*hi; fp32-grade result).
  * algo: 0 = auto, 1 = warp-per-(group,head) register/shuffle FMA kernel (any S <= 160),
  *       2 = warp-level tensor-core (mma.sync) kernel (bf16 in, bf16 out, 16 < S <= 96),
  *       3 = tcgen05 / TMEM kernel (bf16 in, bf16 out, 64 < S <= 96, q_rows == S: the 4-scale

@@ -145,6 +145,29 @@ def test_group_attention_other_head_counts(H, S, G, algo):
     assert relerr(out, ref) < 1.5e-2
 
 
+@pytest.mark.parametrize("N,G,H", [(50, 7, 12), (50, 300, 12), (64, 3, 12), (17, 5, 6), (33, 4, 1)])
+def test_patch_attention_split_precision_tcgen05(N, G, H):
+    """Global patch attention on tcgen05 in split-bf16 precision: qkv as hi | lo pairs (what duo_gemm's SPLIT epilogue
+    writes), out as a hi | lo pair; fp32-grade agreement with the reference on the same (split-rounded) inputs."""
+    D = 64 * H
+    x = _gen((G * N, 3 * D), 401 + N, 2.0)
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+    qkv_split = torch.cat([hi, lo], dim=1).contiguous()
+    xs = hi.float() + lo.float()  # what the kernel sees
+    t = xs.reshape(G, N, 3, H, 64).permute(2, 0, 3, 1, 4).double()
+    a = torch.softmax((t[0] @ t[1].transpose(-2, -1)) * 0.125, dim=-1)
+    ref = (a @ t[2]).transpose(1, 2).reshape(G * N, D).float()
+    out = torch.empty(G * N, 2 * D, dtype=torch.bfloat16, device="cuda")
+    ops.group_attention(qkv_split, out, N, H, 0.125, split_in=True)
+    got = out[:, :D].float() + out[:, D:].float()
+    assert relerr(got, ref) < 1e-4
+    # and against the fp32 FMA kernel it replaces
+    out2 = torch.empty(G * N, 2 * D, dtype=torch.bfloat16, device="cuda")
+    ops.group_attention(xs.contiguous(), out2, N, H, 0.125, algo=1)
+    assert relerr(got, out2[:, :D].float() + out2[:, D:].float()) < 1e-4
+
+
 @pytest.mark.parametrize("algo", [2, 3])
 def test_group_attention_peaked_softmax_stays_finite(algo):
     """Scores of a few hundred (one key dominates every row): exp2 underflows to exactly 0 for the others,

@@ -22,6 +22,9 @@ AOs = torch.empty(rows, 2 * D, dtype=torch.bfloat16, device=dev)
 Zo = torch.empty(rows, 2 * D, dtype=torch.bfloat16, device=dev)
 print("qkv split3 -> f32      ", t(lambda: ops.gemm(Zs, Wq, bq, QKV32, ops.EPI_F32, split3=True)))
 print("attn fp32 in, split out", t(lambda: ops.group_attention(QKV32, AOs, N, H, 0.125)))
+QKVs = torch.empty(rows, 6 * D, dtype=torch.bfloat16, device=dev)
+print("qkv split3 -> split    ", t(lambda: ops.gemm(Zs, Wq, bq, QKVs, ops.EPI_SPLIT_BF16, split3=True)))
+print("attn split tcgen05     ", t(lambda: ops.group_attention(QKVs, AOs, N, H, 0.125, split_in=True)))
 print("proj split3 -> split   ", t(lambda: ops.gemm(AOs, Wp, bp, Zo, ops.EPI_SPLIT_BF16, split3=True)))
 Zb = Zs[:, :D].contiguous(); Wqb = Wq[:, :D].contiguous(); Wpb = Wp[:, :D].contiguous()
 QKVb = torch.empty(rows, 3 * D, dtype=torch.bfloat16, device=dev); AOb = torch.empty(rows, D, dtype=torch.bfloat16, device=dev)
