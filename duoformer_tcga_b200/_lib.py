@@ -19,7 +19,7 @@ EPI_BF16, EPI_GELU_BF16, EPI_RESIDUAL_F32, EPI_SCATTER_F32, EPI_F32, EPI_SPLIT_B
 ACT_BF16, ACT_SPLIT, ACT_F32, ACT_F16 = range(4)
 
 # every symbol include/duoformer_sm100.h declares
-ABI_VERSION = 2  # duo_abi_version() of the library this binding was written against
+ABI_VERSION = 3  # duo_abi_version() of the library this binding was written against
 
 EXPORTED_SYMBOLS = (
     "duo_last_error",
@@ -65,10 +65,10 @@ class GemmArgs(Structure):
         ("ln_eps", c_float),
         ("relu", c_int32),
         ("fp16_operands", c_int32),
-        ("ln_gamma", c_void_p),
-        ("ln_beta", c_void_p),
-        ("ln_out", c_void_p),
-        ("ln_sync", c_void_p),
+        ("xb_out", c_void_p),
+        ("stats_out", c_void_p),
+        ("ln_stats", c_void_p),
+        ("ln_colsum", c_void_p),
     ]
 
 

@@ -47,15 +47,24 @@ constexpr int kNumThreads = 192;
 constexpr int kNumEpilogueThreads = 128;
 constexpr uint32_t kStagingBytesPerWarp = 2 * 32 * 128;  // two 32-row x 128 B buffers
 
-// Internal epilogue variants (superset of the ABI's DUO_EPI_*): staged TMA paths.
-constexpr int kEpiResidualTma = 100;  // DUO_EPI_RESIDUAL_F32 through TMA reduce-add
-constexpr int kEpiResidualLn = 101;   // residual update + fused LayerNorm of the updated rows (pair kernel)
+// Internal epilogue variants (superset of the ABI's DUO_EPI_*).
+constexpr int kEpiResidualTma = 100;  // DUO_EPI_RESIDUAL_F32: TMA reduce-add into the fp32 stream
+constexpr int kEpiResidualFwd = 101;  // residual update + statistics forwarding (pair kernel): X is TMA-loaded,
+                                      // updated in shared memory and stored back together with its bf16 copy and
+                                      // per-row LayerNorm partial statistics (duo_gemm_args.xb_out / stats_out)
+constexpr int kEpiBf16Ln = 102;       // DUO_EPI_BF16 with the forwarded LayerNorm applied in the epilogue
+constexpr int kEpiGeluBf16Ln = 103;   // DUO_EPI_GELU_BF16 with the forwarded LayerNorm applied in the epilogue
+
+constexpr int kStatCols = 128;  // columns covered by one forwarded (mean, M2) pair
 
 template <int EPI>
 struct EpiTraits {
-  static constexpr bool kStagedBf16 = (EPI == DUO_EPI_BF16 || EPI == DUO_EPI_GELU_BF16);
-  static constexpr bool kStagedF32 = (EPI == kEpiResidualTma || EPI == kEpiResidualLn);
-  static constexpr bool kStaged = kStagedBf16 || kStagedF32;
+  static constexpr bool kLnApply = (EPI == kEpiBf16Ln || EPI == kEpiGeluBf16Ln);
+  static constexpr bool kGelu = (EPI == DUO_EPI_GELU_BF16 || EPI == kEpiGeluBf16Ln);
+  static constexpr bool kStagedBf16 = (EPI == DUO_EPI_BF16 || EPI == DUO_EPI_GELU_BF16 || kLnApply);
+  static constexpr bool kStagedF32 = (EPI == kEpiResidualTma);
+  static constexpr bool kFwd = (EPI == kEpiResidualFwd);
+  static constexpr bool kStaged = kStagedBf16 || kStagedF32 || kFwd;
 };
 
 template <int BLOCK_N>
@@ -74,10 +83,11 @@ struct GemmParams {
   const float* bias;
   void* out;
   const float* gamma;
-  const float* ln_gamma;  // fused LayerNorm (kEpiResidualLn)
-  const float* ln_beta;
-  void* ln_out;
-  uint32_t* ln_sync;  // [num_m_blocks][2 CTAs][4 quarters] finished N tiles per 32-row slab
+  // statistics forwarding, producer side (kEpiResidualFwd)
+  float2* stats_out;        // [M, N / 128] (mean, M2) of the updated rows, per 128-column part
+  // statistics forwarding, consumer side (kEpiBf16Ln / kEpiGeluBf16Ln)
+  const float2* ln_stats;   // [M, K / 128]
+  const float* ln_colsum;   // [N] sum_k W'[n, k]
   float ln_eps;
   int32_t relu;           // BF16 / F32 epilogues: clamp at zero
   const int32_t* row_map;
@@ -90,6 +100,31 @@ struct GemmParams {
   int32_t num_m_blocks, num_n_blocks;
   uint32_t idesc_mask;  // ~0, or with the a_format / b_format bits cleared (fp16 operands instead of bf16)
 };
+
+// Forwarded LayerNorm, consumer side.  The A operand of this GEMM is the UN-normalised bf16 copy of the
+// residual stream and W' = W * diag(ln_gamma); with (mean, rstd) of the row,
+//   LN(x) W^T + b = rstd * (x W'^T - mean * colsum(W')) + (W ln_beta + b)
+// so the epilogue computes  ln_a * acc + (ln_c * colsum[n] + bias'[n])  with ln_a = rstd, ln_c = -mean * rstd.
+// The (mean, M2) pairs of the row's K / 128 column parts (written by the producing residual GEMM from the
+// fp32 row) are merged with Chan's formula.
+__device__ __forceinline__ void ln_row_coeffs(const GemmParams& p, int64_t row, bool valid, float& ln_a, float& ln_c) {
+  ln_a = 1.f;
+  ln_c = 0.f;
+  if (!valid) return;
+  const int parts = p.K / kStatCols;
+  const float2* st = p.ln_stats + row * parts;
+  float mean = 0.f, m2 = 0.f;
+  for (int i = 0; i < parts; ++i) mean += __ldg(st + i).x;
+  mean *= 1.0f / static_cast<float>(parts);
+  for (int i = 0; i < parts; ++i) {
+    const float2 s = __ldg(st + i);
+    const float d = s.x - mean;
+    m2 += s.y + static_cast<float>(kStatCols) * d * d;
+  }
+  const float rstd = rsqrtf(m2 / static_cast<float>(p.K) + p.ln_eps);
+  ln_a = rstd;
+  ln_c = -mean * rstd;
+}
 
 // acc[32] (fp32 bits) -> f[32] = acc + bias (optionally GELU'd / scaled by LayerScale gamma)
 // Bias slice [col, col+32) -> registers; issued BEFORE waiting on the TMEM load so both latencies overlap.
@@ -104,16 +139,52 @@ __device__ __forceinline__ void epilogue_bias_load(const GemmParams& p, int col,
   }
 }
 
+// colsum(W') slice [col, col+32) (forwarded LayerNorm only)
+__device__ __forceinline__ void epilogue_colsum_load(const GemmParams& p, int col, float4 (&cs)[8]) {
+  const float4* c4 = reinterpret_cast<const float4*>(p.ln_colsum + col);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) cs[j] = __ldg(c4 + j);
+}
+
+// Forwarded LayerNorm: b <- ln_c * colsum + b  (the per-row, per-column additive term)
+__device__ __forceinline__ void epilogue_ln_fold_bias(float ln_c, const float4 (&cs)[8], float4 (&b)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    uint64_t lo = fma2(pack2(ln_c, ln_c), pack2(cs[j].x, cs[j].y), pack2(b[j].x, b[j].y));
+    uint64_t hi = fma2(pack2(ln_c, ln_c), pack2(cs[j].z, cs[j].w), pack2(b[j].z, b[j].w));
+    unpack2(lo, b[j].x, b[j].y);
+    unpack2(hi, b[j].z, b[j].w);
+  }
+}
+
+// f = ln_a * acc + b  (ln_a == 1 without a forwarded LayerNorm: plain bias add), then the epilogue's function
 template <int EPI>
 __device__ __forceinline__ void epilogue_math(const GemmParams& p, int col, const uint32_t (&v)[32],
-                                              const float4 (&b)[8], float (&f)[32]) {
-  if constexpr (EPI == DUO_EPI_GELU_BF16) {  // bias add and GELU on packed fp32 pairs
+                                              const float4 (&b)[8], float (&f)[32], float ln_a) {
+  using ET = EpiTraits<EPI>;
+  if constexpr (ET::kGelu) {  // bias add and GELU on packed fp32 pairs
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const uint64_t lo = add2(pack2(__uint_as_float(v[4 * j + 0]), __uint_as_float(v[4 * j + 1])), pack2(b[j].x, b[j].y));
-      const uint64_t hi = add2(pack2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), pack2(b[j].z, b[j].w));
+      uint64_t lo, hi;
+      if constexpr (ET::kLnApply) {
+        lo = fma2(pack2(ln_a, ln_a), pack2(__uint_as_float(v[4 * j + 0]), __uint_as_float(v[4 * j + 1])), pack2(b[j].x, b[j].y));
+        hi = fma2(pack2(ln_a, ln_a), pack2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), pack2(b[j].z, b[j].w));
+      } else {
+        lo = add2(pack2(__uint_as_float(v[4 * j + 0]), __uint_as_float(v[4 * j + 1])), pack2(b[j].x, b[j].y));
+        hi = add2(pack2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), pack2(b[j].z, b[j].w));
+      }
       unpack2(gelu_erf_sigmoid_p2(lo), f[4 * j + 0], f[4 * j + 1]);
       unpack2(gelu_erf_sigmoid_p2(hi), f[4 * j + 2], f[4 * j + 3]);
+    }
+    return;
+  }
+  if constexpr (ET::kLnApply) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      f[4 * j + 0] = fmaf(ln_a, __uint_as_float(v[4 * j + 0]), b[j].x);
+      f[4 * j + 1] = fmaf(ln_a, __uint_as_float(v[4 * j + 1]), b[j].y);
+      f[4 * j + 2] = fmaf(ln_a, __uint_as_float(v[4 * j + 2]), b[j].z);
+      f[4 * j + 3] = fmaf(ln_a, __uint_as_float(v[4 * j + 3]), b[j].w);
     }
     return;
   }
@@ -173,32 +244,6 @@ __device__ __forceinline__ void epilogue_store_direct(const GemmParams& p, int64
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       o4[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-  } else if constexpr (EPI == DUO_EPI_RESIDUAL_F32) {
-    float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + row * p.ldo + col);
-    float4 r[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) r[j] = o4[j];
-    if (p.gamma != nullptr) {
-      const float4* g4 = reinterpret_cast<const float4*>(p.gamma + col);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 g = __ldg(g4 + j);
-        r[j].x = fmaf(g.x, f[4 * j + 0], r[j].x);
-        r[j].y = fmaf(g.y, f[4 * j + 1], r[j].y);
-        r[j].z = fmaf(g.z, f[4 * j + 2], r[j].z);
-        r[j].w = fmaf(g.w, f[4 * j + 3], r[j].w);
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        r[j].x += f[4 * j + 0];
-        r[j].y += f[4 * j + 1];
-        r[j].z += f[4 * j + 2];
-        r[j].w += f[4 * j + 3];
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) o4[j] = r[j];
   } else if constexpr (EPI == DUO_EPI_SCATTER_F32) {
     const int64_t grp = row / p.rows_per_group;
     const int32_t in_grp = static_cast<int32_t>(row - grp * p.rows_per_group);
@@ -236,7 +281,7 @@ template <int EPI, int NBUF, typename ReleaseFn>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtensorMap* tmap_out,
                                               uint32_t taddr, int row0, int lane, int n0, int c_begin,
                                               int c_end, uint32_t stg, uint32_t& stg_buf,
-                                              ReleaseFn release) {
+                                              float ln_a, float ln_c, ReleaseFn release) {
   using ET = EpiTraits<EPI>;
   const int64_t row = static_cast<int64_t>(row0) + lane;
   const bool valid = row < p.M;
@@ -254,13 +299,18 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
         float4 bia[8];
         ptx::tmem_ld_32x32(taddr + static_cast<uint32_t>(c + 32 * h), v);
         epilogue_bias_load(p, n0 + c + 32 * h, bia);
+        if constexpr (ET::kLnApply) {
+          float4 cs[8];
+          epilogue_colsum_load(p, n0 + c + 32 * h, cs);
+          epilogue_ln_fold_bias(ln_c, cs, bia);
+        }
         ptx::tmem_ld_wait();
         if (h == 1 && c + 64 >= c_end) {  // accumulator fully read: hand the TMEM buffer back early
           ptx::tc_fence_before();
           release();
         }
         float f[32];
-        epilogue_math<EPI>(p, n0 + c + 32 * h, v, bia, f);
+        epilogue_math<EPI>(p, n0 + c + 32 * h, v, bia, f, ln_a);
         if (h == 0) {
           if (lane == 0) ptx::tma_store_wait_read<NBUF - 1>();  // buffer `stg_buf` no longer being read
           __syncwarp();
@@ -293,7 +343,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
         release();
       }
       float f[32];
-      epilogue_math<EPI>(p, n0 + c, v, bia, f);
+      epilogue_math<EPI>(p, n0 + c, v, bia, f, 1.f);
       if (lane == 0) ptx::tma_store_wait_read<NBUF - 1>();
       __syncwarp();
       const uint32_t buf = stg + stg_buf * (32u * 128u) + my_row_off;
@@ -356,7 +406,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
         release();
       }
       float f[32];
-      epilogue_math<EPI>(p, n0 + c, v, bia, f);
+      epilogue_math<EPI>(p, n0 + c, v, bia, f, 1.f);
       __syncwarp();  // previous chunk's reads of the staging tile are done
 #pragma unroll
       for (int j = 0; j < 8; ++j)
@@ -391,7 +441,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
       }
       if (valid) {
         float f[32];
-        epilogue_math<EPI>(p, n0 + c, v, bia, f);
+        epilogue_math<EPI>(p, n0 + c, v, bia, f, 1.f);
         epilogue_store_direct<EPI>(p, row, n0 + c, f);
       }
     }
@@ -542,12 +592,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const int n_blk = static_cast<int>(tile - static_cast<int64_t>(m_blk) * p.num_n_blocks);
       const int row0 = m_blk * kBlockM + quarter * 32;  // first row of this warp's slab
       const int n0 = n_blk * BLOCK_N;
+      float ln_a = 1.f, ln_c = 0.f;
+      if constexpr (ET::kLnApply) ln_row_coeffs(p, static_cast<int64_t>(row0) + lane, row0 + lane < p.M, ln_a, ln_c);
       ptx::mbar_wait(tmem_full_bar(acc), acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr =
           tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
 
-      epilogue_tile<EPI, 2>(p, &tmap_out, taddr, row0, lane, n0, 0, BLOCK_N, stg, stg_buf,
+      epilogue_tile<EPI, 2>(p, &tmap_out, taddr, row0, lane, n0, 0, BLOCK_N, stg, stg_buf, ln_a, ln_c,
                          [&]() {
                            __syncwarp();
                            if (lane == 0) ptx::mbar_arrive(tmem_empty_bar(acc));
@@ -580,97 +632,31 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 // the "slot free" / "accumulator full" arrivals to both CTAs; each CTA runs its own epilogue.
 // ===========================================================================================
 constexpr int kPairBlockN = 256;
+// Statistics-forwarding residual epilogue (kEpiResidualFwd): per epilogue warp a ring of kFwdSlots
+// slots, each one 32 x 32 fp32 chunk of X (TMA-loaded, updated in place, TMA-stored) plus its bf16 copy.
+constexpr int kFwdSlots = 4;
+constexpr uint32_t kFwdXBytes = 32 * 128;  // 32 rows x 32 fp32, SWIZZLE_128B
+constexpr uint32_t kFwdBBytes = 32 * 64;   // 32 rows x 32 bf16, SWIZZLE_64B
 // EPI_WARPS epilogue warps: 4 (one per TMEM lane quarter, all 256 columns, 6 operand stages) or 8
 // (two per quarter, 128 columns each, 5 operand stages — used when the epilogue is heavy: GELU,
 // token scatter; both only occur with short K).  Staging is double-buffered per warp either way.
-// FUSED_LN: four extra LayerNorm warps (one per epilogue warp) and a panel counter each.
-constexpr int kLnWarps = 4;  // one per epilogue warp (32 rows each, four in flight)
-template <int EPI_WARPS, bool FUSED_LN = false>
+template <int EPI_WARPS, bool FWD = false>
 struct PairCfg {
-  static constexpr int kStages = EPI_WARPS == 8 ? 5 : 6;
-  static constexpr int kThreads = 64 + 32 * EPI_WARPS + (FUSED_LN ? 32 * kLnWarps : 0);
+  static constexpr int kStages = FWD ? 4 : (EPI_WARPS == 8 ? 5 : 6);
+  static constexpr int kThreads = 64 + 32 * EPI_WARPS;
   static constexpr int kStagingBufs = 2;
   static constexpr uint32_t kABytes = kBlockM * kBlockK * 2;          // 16 KB (this CTA's 128 rows)
   static constexpr uint32_t kBBytes = (kPairBlockN / 2) * kBlockK * 2;  // 16 KB (this CTA's N half)
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
   static constexpr uint32_t kTmemCols = 2 * kPairBlockN;
-  static constexpr uint32_t kStagingBytes = EPI_WARPS * kStagingBufs * 32 * 128;  // 32 KB
-  static constexpr uint32_t kBarrierBytes = (2 * kStages + 4) * 8 + 8 + (FUSED_LN ? kLnWarps * 4 : 0);
+  static constexpr uint32_t kStagingBytes =
+      FWD ? EPI_WARPS * kFwdSlots * (kFwdXBytes + kFwdBBytes) : EPI_WARPS * kStagingBufs * 32 * 128;
+  static constexpr int kNumBars = 2 * kStages + 4;                    // + one slot for the TMEM pointer
+  static constexpr int kNumXBars = FWD ? EPI_WARPS * kFwdSlots : 0;   // "X chunk loaded", one per ring slot
+  static constexpr uint32_t kBarrierBytes = (kNumBars + 1 + kNumXBars) * 8;
   static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kStagingBytes + kBarrierBytes + 1024;
+  static_assert(kSmemBytes <= 232448, "shared memory budget of one CTA per SM exceeded");
 };
-
-// ---- residual update + fused LayerNorm (kEpiResidualLn, pair kernel, row-panel tile order) ------
-// The residual update is the ordinary TMA reduce-add epilogue in the ordinary tile order (the N
-// tiles of a 256-row panel run on neighbouring pairs at the same time, which keeps the A panel
-// in L2).  When an epilogue warp knows the reduce-adds of a tile have completed
-// (cp.async.bulk.wait_group, checked one tile late so the store pipeline never drains) it bumps
-// the global counter of its 32-row slab, p.ln_sync[m_blk][cta][quarter].  The pair that owns the
-// panel's LAST N tile runs the LayerNorm: its LN warp waits until the slab's counter reaches the
-// number of N tiles, resets it, re-reads the finished rows (L2 hits: they were just written
-// there), normalises them exactly like layernorm.cu (two-pass statistics in registers) and
-// writes the bf16 operand of the next GEMM.  LN warps never touch TMEM or the smem ring, so the
-// GEMM pipeline does not wait on them; every CTA of the persistent grid is resident, so the
-// producers of a counter are always running (a bounded spin traps instead of hanging).
-__device__ __forceinline__ float4 ld_l2_f4(const float4* ptr) {
-  float4 r;
-  asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];"
-               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
-               : "l"(ptr)
-               : "memory");
-  return r;
-}
-
-template <int NV>
-__device__ __forceinline__ void ln_row_store(const float4 (&v)[NV], const float4* g4, const float4* b4,
-                                             float eps, int lane, __nv_bfloat16* yrow) {
-  constexpr int D = NV * 128;
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-  const float mean = warp_sum(s) * (1.0f / D);
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const float a0 = v[i].x - mean, a1 = v[i].y - mean, a2 = v[i].z - mean, a3 = v[i].w - mean;
-    q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
-  }
-  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const float4 g = __ldg(g4 + lane + 32 * i);
-    const float4 b = __ldg(b4 + lane + 32 * i);
-    uint2 w;
-    w.x = pack_bf16x2((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y);
-    w.y = pack_bf16x2((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
-    reinterpret_cast<uint2*>(yrow)[lane + 32 * i] = w;
-  }
-}
-
-// rows [row_begin, row_begin + nrows) of X (= p.out, fp32, leading dim p.ldo) -> p.ln_out (bf16 [M, N]);
-// four rows in flight per warp (the loads are L2 / HBM latency bound).
-template <int NV>
-__device__ __forceinline__ void ln_rows_from_l2(const GemmParams& p, int64_t row_begin, int nrows, int lane) {
-  constexpr int D = NV * 128;
-  constexpr int kRows = NV > 6 ? 2 : 4;
-  const float4* g4 = reinterpret_cast<const float4*>(p.ln_gamma);
-  const float4* b4 = reinterpret_cast<const float4*>(p.ln_beta);
-  const float* x0 = reinterpret_cast<const float*>(p.out) + row_begin * p.ldo;
-  __nv_bfloat16* y0 = reinterpret_cast<__nv_bfloat16*>(p.ln_out) + row_begin * D;
-#pragma unroll 1
-  for (int r = 0; r < nrows; r += kRows) {
-    float4 v[kRows][NV];
-#pragma unroll
-    for (int k = 0; k < kRows; ++k) {
-      const int rk = (r + k < nrows) ? r + k : nrows - 1;
-      const float4* xr = reinterpret_cast<const float4*>(x0 + static_cast<int64_t>(rk) * p.ldo);
-#pragma unroll
-      for (int i = 0; i < NV; ++i) v[k][i] = ld_l2_f4(xr + lane + 32 * i);
-    }
-#pragma unroll
-    for (int k = 0; k < kRows; ++k)
-      if (r + k < nrows) ln_row_store<NV>(v[k], g4, b4, p.ln_eps, lane, y0 + static_cast<int64_t>(r + k) * D);
-  }
-}
 
 // Tile order of the pair kernels: tiles round-robin over pairs, N fastest — the N tiles of a row panel
 // run on neighbouring pairs at the same time and share the A panel through L2.  (Pair-owned row
@@ -684,14 +670,19 @@ __device__ __forceinline__ bool pair_tile(int64_t it, int64_t pair_idx, int64_t 
   return true;
 }
 
+__device__ __forceinline__ void ld_shared_v4(uint32_t addr, float& a, float& b, float& c, float& d) {
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "r"(addr) : "memory");
+}
+
 template <int EPI, int EPI_WARPS>
 __global__ void __cluster_dims__(2, 1, 1)
-__launch_bounds__(PairCfg<EPI_WARPS, EPI == kEpiResidualLn>::kThreads, 1)
+__launch_bounds__(PairCfg<EPI_WARPS, EPI == kEpiResidualFwd>::kThreads, 1)
 gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
                          const __grid_constant__ CUtensorMap tmap_b,
                          const __grid_constant__ CUtensorMap tmap_out,
+                         const __grid_constant__ CUtensorMap tmap_aux,  // kEpiResidualFwd: the bf16 copy
                          const GemmParams p) {
-  using C = PairCfg<EPI_WARPS, EPI == kEpiResidualLn>;
+  using C = PairCfg<EPI_WARPS, EPI == kEpiResidualFwd>;
   using ET = EpiTraits<EPI>;
   constexpr int kStages = C::kStages;
   constexpr int BLOCK_N = kPairBlockN;
@@ -704,12 +695,13 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
   auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
   auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };  // leader only
-  const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * kStages + 4);
+  const uint32_t tmem_ptr_smem = bar_base + 8u * C::kNumBars;
+  auto x_bar = [&](int i) { return bar_base + 8u * (C::kNumBars + 1 + i); };  // kEpiResidualFwd only
+  (void)x_bar;
   uint32_t* tmem_ptr_generic =
       reinterpret_cast<uint32_t*>(smem_raw + (tmem_ptr_smem - ptx::smem_u32(smem_raw)));
 
-  constexpr int kExtraWarps = (EPI == kEpiResidualLn) ? kLnWarps : 0;  // LayerNorm warps sit after the epilogue warps
-  constexpr int kTmaWarp = EPI_WARPS + kExtraWarps, kMmaWarp = kTmaWarp + 1;  // highest warp ids: never starved
+  constexpr int kTmaWarp = EPI_WARPS, kMmaWarp = kTmaWarp + 1;  // highest warp ids: never starved
   const int warp_idx = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   const uint32_t cta_rank = ptx::cluster_ctarank();
@@ -719,8 +711,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
     ptx::prefetch_tmap(&tmap_a);
     ptx::prefetch_tmap(&tmap_b);
     if constexpr (ET::kStaged) ptx::prefetch_tmap(&tmap_out);
-    if constexpr (EPI == kEpiResidualLn) {
-    }
+    if constexpr (ET::kFwd) ptx::prefetch_tmap(&tmap_aux);
 #pragma unroll
     for (int s = 0; s < kStages; ++s) {
       ptx::mbar_init(full_bar(s), 1);   // leader's producer arms it with both CTAs' bytes
@@ -731,6 +722,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
       ptx::mbar_init(tmem_full_bar(a), 1);
       ptx::mbar_init(tmem_empty_bar(a), 2 * EPI_WARPS);  // one arrival per epilogue warp of BOTH CTAs
     }
+    for (int i = 0; i < C::kNumXBars; ++i) ptx::mbar_init(x_bar(i), 1);
     ptx::fence_barrier_init();
   }
   if (warp_idx == kMmaWarp) {
@@ -822,85 +814,168 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
         }
       }
     }
-  } else if (EPI == kEpiResidualLn && warp_idx >= EPI_WARPS) {
-    // ===================== LayerNorm warps (fused LN only): warp j serves epilogue warp j =====================
-    const int j = warp_idx - EPI_WARPS;
-    const uint32_t want = static_cast<uint32_t>(p.num_n_blocks);
-    for (int64_t it = 0; pair_tile(it, pair_idx, pair_stride, p.num_m_blocks, p.num_n_blocks, m_blk, n_blk); ++it) {
-      if (n_blk != p.num_n_blocks - 1) continue;  // the owner of the last N tile normalises the panel
-      const int64_t mb = m_blk;
-      if (lane == 0) {
-        uint32_t* cnt = p.ln_sync + (mb * 8 + cta_rank * 4 + j);
-        uint32_t have = 0, spins = 0;
-        while (true) {
-          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(have) : "l"(cnt) : "memory");
-          if (have >= want) break;
-          __nanosleep(256);
-          if (++spins > (1u << 23)) __trap();  // seconds without progress: fail instead of hanging
-        }
-        asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(cnt), "r"(0u) : "memory");  // ready for the next launch
-        asm volatile("fence.proxy.async;" ::: "memory");
-      }
-      __syncwarp();
-      const int64_t row_begin = mb * (2 * kBlockM) + static_cast<int64_t>(cta_rank) * kBlockM + j * 32;
-      const int64_t left = p.M - row_begin;
-      const int nrows = left >= 32 ? 32 : static_cast<int>(left);
-      if (nrows > 0) {
-        switch (p.N) {
-          case 384: ln_rows_from_l2<3>(p, row_begin, nrows, lane); break;
-          case 768: ln_rows_from_l2<6>(p, row_begin, nrows, lane); break;
-          default: ln_rows_from_l2<8>(p, row_begin, nrows, lane); break;  // 1024
-        }
-      }
-    }
   } else {
     // ===================== epilogue warps (0..EPI_WARPS-1, both CTAs) =====================
     const int quarter = warp_idx & 3;             // TMEM lane quarter (rows) of this warp
     const int col_part = warp_idx >> 2;           // which slice of the 256 columns (EPI_WARPS == 8)
     constexpr int kColsPerWarp = BLOCK_N / (EPI_WARPS / 4);
-    const uint32_t stg = staging_base + static_cast<uint32_t>(warp_idx) * (C::kStagingBufs * 32u * 128u);
-    uint32_t stg_buf = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    int ln_prev_m = -1;  // tile whose reduce-adds are issued but not yet known to be complete
-    auto ln_publish = [&](int mb) {  // lane 0: this warp's slab of tile (mb, *) is final in L2
-      asm volatile("fence.proxy.async;" ::: "memory");
-      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.ln_sync + (static_cast<int64_t>(mb) * 8 + cta_rank * 4 + quarter)) : "memory");
-    };
-    (void)ln_prev_m;
-    for (int64_t it = 0; pair_tile(it, pair_idx, pair_stride, p.num_m_blocks, p.num_n_blocks, m_blk, n_blk); ++it) {
-      const int row0 = m_blk * (2 * kBlockM) + static_cast<int>(cta_rank) * kBlockM + quarter * 32;
-      const int n0 = n_blk * BLOCK_N;
-      ptx::mbar_wait(tmem_full_bar(acc), acc_phase);
-      ptx::tc_fence_after();
-      const uint32_t taddr =
-          tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
-      const uint32_t leader_empty = ptx::mapa(tmem_empty_bar(acc), 0);
-      constexpr int kTileEpi = (EPI == kEpiResidualLn) ? kEpiResidualTma : EPI;
-      epilogue_tile<kTileEpi, C::kStagingBufs>(p, &tmap_out, taddr, row0, lane, n0, col_part * kColsPerWarp,
-                                               (col_part + 1) * kColsPerWarp, stg, stg_buf,
-                         [&]() {
-                           __syncwarp();
-                           if (lane == 0) ptx::mbar_arrive_cluster(leader_empty);
-                         });
-      if constexpr (EPI == kEpiResidualLn) {
-        if (ln_prev_m >= 0 && lane == 0) {
-          // everything older than this tile's BLOCK_N / 32 reduce-add groups has completed
-          ptx::tma_store_wait<BLOCK_N / 32>();
-          ln_publish(ln_prev_m);
+    if constexpr (ET::kFwd) {
+      // ---- residual update with statistics forwarding --------------------------------------------
+      // X chunk g of this warp (32 rows x 32 columns, chunks numbered across tiles) lives in ring slot
+      // g % kFwdSlots: TMA load (issued kFwdSlots - 1 chunks ahead, also across tile boundaries, so the
+      // reads of X overlap the MMAs of the tile) -> x += gamma * (acc + bias) in place -> TMA store of the
+      // fp32 chunk and of its bf16 copy (one bulk group).  A slot is reloaded once the group that stored
+      // it has been read out (wait_group.read 1 right after committing the NEXT group).
+      constexpr int kChunks = kColsPerWarp / 32;
+      const uint32_t xbuf0 = staging_base + static_cast<uint32_t>(warp_idx) * (kFwdSlots * kFwdXBytes);
+      const uint32_t bbuf0 = staging_base + EPI_WARPS * kFwdSlots * kFwdXBytes +
+                             static_cast<uint32_t>(warp_idx) * (kFwdSlots * kFwdBBytes);
+      const int parts = p.N / kStatCols;
+      auto issue_load = [&](uint32_t gi) {  // lane 0 only
+        int mb, nb;
+        if (!pair_tile(gi / kChunks, pair_idx, pair_stride, p.num_m_blocks, p.num_n_blocks, mb, nb)) return;
+        const int r = mb * (2 * kBlockM) + static_cast<int>(cta_rank) * kBlockM + quarter * 32;
+        const int c = nb * BLOCK_N + col_part * kColsPerWarp + static_cast<int>(gi % kChunks) * 32;
+        const uint32_t s = gi % kFwdSlots;
+        const uint32_t bar = x_bar(warp_idx * kFwdSlots + static_cast<int>(s));
+        ptx::mbar_arrive_expect_tx(bar, kFwdXBytes);
+        ptx::tma_load_2d(xbuf0 + s * kFwdXBytes, &tmap_out, bar, c, r);
+      };
+      if (lane == 0) {
+#pragma unroll
+        for (uint32_t i = 0; i + 1 < kFwdSlots; ++i) issue_load(i);
+      }
+      uint32_t g = 0;
+      const uint32_t sw128 = static_cast<uint32_t>(lane & 7);         // 16-byte chunk XOR, 128 B rows
+      const uint32_t sw64 = static_cast<uint32_t>((lane >> 1) & 3);   // 16-byte chunk XOR, 64 B rows
+      for (int64_t it = 0; pair_tile(it, pair_idx, pair_stride, p.num_m_blocks, p.num_n_blocks, m_blk, n_blk); ++it) {
+        const int row0 = m_blk * (2 * kBlockM) + static_cast<int>(cta_rank) * kBlockM + quarter * 32;
+        const int n0 = n_blk * BLOCK_N;
+        const int64_t row = static_cast<int64_t>(row0) + lane;
+        const bool valid = row < p.M;
+        ptx::mbar_wait(tmem_full_bar(acc), acc_phase);
+        ptx::tc_fence_after();
+        const uint32_t taddr =
+            tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
+        const uint32_t leader_empty = ptx::mapa(tmem_empty_bar(acc), 0);
+        float pivot = 0.f;
+        uint64_t s1 = 0, s2 = 0;  // packed (even, odd) partial sums of (x - pivot), (x - pivot)^2
+#pragma unroll 1
+        for (int ci = 0; ci < kChunks; ++ci, ++g) {
+          const int c = col_part * kColsPerWarp + ci * 32;  // first column of the chunk inside the tile
+          const uint32_t s = g % kFwdSlots;
+          const uint32_t xrow = xbuf0 + s * kFwdXBytes + static_cast<uint32_t>(lane) * 128u;
+          const uint32_t brow = bbuf0 + s * kFwdBBytes + static_cast<uint32_t>(lane) * 64u;
+          uint32_t v[32];
+          float4 bia[8];
+          ptx::tmem_ld_32x32(taddr + static_cast<uint32_t>(c), v);
+          epilogue_bias_load(p, n0 + c, bia);
+          ptx::mbar_wait(x_bar(warp_idx * kFwdSlots + static_cast<int>(s)), (g / kFwdSlots) & 1u);
+          ptx::tmem_ld_wait();
+          if (ci == kChunks - 1) {  // accumulator fully read: hand the TMEM buffer back
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(leader_empty);
+          }
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float x0, x1, x2, x3;
+            ld_shared_v4(xrow + ((static_cast<uint32_t>(j) ^ sw128) << 4), x0, x1, x2, x3);
+            float a0 = __uint_as_float(v[4 * j + 0]) + bia[j].x, a1 = __uint_as_float(v[4 * j + 1]) + bia[j].y;
+            float a2 = __uint_as_float(v[4 * j + 2]) + bia[j].z, a3 = __uint_as_float(v[4 * j + 3]) + bia[j].w;
+            if (p.gamma != nullptr) {
+              const float4 gm = __ldg(reinterpret_cast<const float4*>(p.gamma + n0 + c) + j);
+              f[4 * j + 0] = fmaf(gm.x, a0, x0);
+              f[4 * j + 1] = fmaf(gm.y, a1, x1);
+              f[4 * j + 2] = fmaf(gm.z, a2, x2);
+              f[4 * j + 3] = fmaf(gm.w, a3, x3);
+            } else {
+              f[4 * j + 0] = x0 + a0;
+              f[4 * j + 1] = x1 + a1;
+              f[4 * j + 2] = x2 + a2;
+              f[4 * j + 3] = x3 + a3;
+            }
+          }
+          // LayerNorm partial statistics of the updated fp32 row, per 128-column part (4 chunks):
+          // shifted sums around the part's first element (no cancellation for |mean| >> spread)
+          if ((ci & 3) == 0) {
+            pivot = f[0];
+            s1 = 0;
+            s2 = 0;
+          }
+          {
+            const uint64_t np = pack2(-pivot, -pivot);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const uint64_t d = add2(pack2(f[2 * j], f[2 * j + 1]), np);
+              s1 = add2(s1, d);
+              s2 = fma2(d, d, s2);
+            }
+          }
+          if ((ci & 3) == 3) {
+            float a, b, q, r;
+            unpack2(s1, a, b);
+            unpack2(s2, q, r);
+            const float sum = a + b;
+            const float mean = fmaf(sum, 1.0f / kStatCols, pivot);
+            const float m2 = fmaxf((q + r) - sum * sum * (1.0f / kStatCols), 0.f);
+            if (valid) p.stats_out[row * parts + (n0 + c) / kStatCols] = make_float2(mean, m2);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j)  // updated fp32 chunk, in place
+            st_shared_v4(xrow + ((static_cast<uint32_t>(j) ^ sw128) << 4), __float_as_uint(f[4 * j + 0]),
+                         __float_as_uint(f[4 * j + 1]), __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3]));
+#pragma unroll
+          for (int j = 0; j < 4; ++j)  // bf16 copy (A operand of the next GEMM)
+            st_shared_v4(brow + ((static_cast<uint32_t>(j) ^ sw64) << 4),
+                         pack_bf16x2(f[8 * j + 0], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                         pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+          ptx::fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_store_2d(&tmap_out, xbuf0 + s * kFwdXBytes, n0 + c, row0);
+            ptx::tma_store_2d(&tmap_aux, bbuf0 + s * kFwdBBytes, n0 + c, row0);
+            ptx::tma_store_commit();
+            ptx::tma_store_wait_read<1>();        // the previous chunk's stores have left their slot ...
+            issue_load(g + kFwdSlots - 1);        // ... which is the one chunk g + kFwdSlots - 1 uses
+          }
         }
-        ln_prev_m = m_blk;
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
       }
-      if (++acc == 2) {
-        acc = 0;
-        acc_phase ^= 1u;
-      }
-    }
-    if constexpr (ET::kStaged) {
       if (lane == 0) ptx::tma_store_wait<0>();
-    }
-    if constexpr (EPI == kEpiResidualLn) {
-      if (ln_prev_m >= 0 && lane == 0) ln_publish(ln_prev_m);
+    } else {
+      const uint32_t stg = staging_base + static_cast<uint32_t>(warp_idx) * (C::kStagingBufs * 32u * 128u);
+      uint32_t stg_buf = 0;
+      for (int64_t it = 0; pair_tile(it, pair_idx, pair_stride, p.num_m_blocks, p.num_n_blocks, m_blk, n_blk); ++it) {
+        const int row0 = m_blk * (2 * kBlockM) + static_cast<int>(cta_rank) * kBlockM + quarter * 32;
+        const int n0 = n_blk * BLOCK_N;
+        float ln_a = 1.f, ln_c = 0.f;
+        if constexpr (ET::kLnApply) ln_row_coeffs(p, static_cast<int64_t>(row0) + lane, row0 + lane < p.M, ln_a, ln_c);
+        ptx::mbar_wait(tmem_full_bar(acc), acc_phase);
+        ptx::tc_fence_after();
+        const uint32_t taddr =
+            tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
+        const uint32_t leader_empty = ptx::mapa(tmem_empty_bar(acc), 0);
+        epilogue_tile<EPI, C::kStagingBufs>(p, &tmap_out, taddr, row0, lane, n0, col_part * kColsPerWarp,
+                                            (col_part + 1) * kColsPerWarp, stg, stg_buf, ln_a, ln_c,
+                           [&]() {
+                             __syncwarp();
+                             if (lane == 0) ptx::mbar_arrive_cluster(leader_empty);
+                           });
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+      }
+      if constexpr (ET::kStaged) {
+        if (lane == 0) ptx::tma_store_wait<0>();
+      }
     }
   }
 
@@ -930,10 +1005,38 @@ PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
-// Row-major [rows, cols] matrix (leading dim ld elements); box = box_rows x (128 B of columns),
-// 128B swizzle.  elem_bytes 2 -> bf16, 4 -> fp32.
+// Tensor maps are a pure function of (base, shape, leading dim, box, element size, swizzle): the model calls
+// duo_gemm with the same few dozen operand descriptions every step (workspace views, packed weights), so the
+// encoded maps are kept in a small per-thread cache and cuTensorMapEncodeTiled stays off the launch path.
+struct TmapKey {
+  const void* base;
+  int64_t rows, cols, ld;
+  int32_t box_rows, elem_bytes, swizzle_bytes;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows &&
+           elem_bytes == o.elem_bytes && swizzle_bytes == o.swizzle_bytes;
+  }
+};
+constexpr int kTmapCacheSize = 128;
+struct TmapCache {
+  TmapKey key[kTmapCacheSize];
+  CUtensorMap map[kTmapCacheSize];
+  int used = 0, next = 0;
+};
+thread_local TmapCache g_tmap_cache;
+
+// Row-major [rows, cols] matrix (leading dim ld elements); box = box_rows x (swizzle_bytes of columns),
+// swizzle 128 B or 64 B.  elem_bytes 2 -> bf16 (fp16 operands share the encoding), 4 -> fp32.
 int make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld,
-              int box_rows, int elem_bytes) {
+              int box_rows, int elem_bytes, int swizzle_bytes = 128) {
+  TmapCache& tc = g_tmap_cache;
+  const TmapKey k{base, rows, cols, ld, box_rows, elem_bytes, swizzle_bytes};
+  for (int i = 0; i < tc.used; ++i) {
+    if (tc.key[i] == k) {
+      *tm = tc.map[i];
+      return DUO_OK;
+    }
+  }
   PFN_encodeTiled fn = get_encode_fn();
   if (fn == nullptr) {
     set_error("cuTensorMapEncodeTiled entry point not available");
@@ -941,17 +1044,20 @@ int make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int
   }
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * elem_bytes};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / elem_bytes), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(swizzle_bytes / elem_bytes), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(tm, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
                   2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed: CUresult %d (rows=%lld cols=%lld ld=%lld)", (int)r,
               (long long)rows, (long long)cols, (long long)ld);
     return DUO_ERR_CUDA;
   }
+  const int slot = tc.used < kTmapCacheSize ? tc.used++ : (tc.next = (tc.next + 1) % kTmapCacheSize);
+  tc.key[slot] = k;
+  tc.map[slot] = *tm;
   return DUO_OK;
 }
 
@@ -978,7 +1084,8 @@ int dispatch_epi(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap
   switch (epi) {
     case DUO_EPI_BF16: return launch<BLOCK_N, DUO_EPI_BF16>(ta, tb, to, p, st);
     case DUO_EPI_GELU_BF16: return launch<BLOCK_N, DUO_EPI_GELU_BF16>(ta, tb, to, p, st);
-    case DUO_EPI_RESIDUAL_F32: return launch<BLOCK_N, DUO_EPI_RESIDUAL_F32>(ta, tb, to, p, st);
+    case kEpiBf16Ln: return launch<BLOCK_N, kEpiBf16Ln>(ta, tb, to, p, st);
+    case kEpiGeluBf16Ln: return launch<BLOCK_N, kEpiGeluBf16Ln>(ta, tb, to, p, st);
     case kEpiResidualTma: return launch<BLOCK_N, kEpiResidualTma>(ta, tb, to, p, st);
     case DUO_EPI_SCATTER_F32: return launch<BLOCK_N, DUO_EPI_SCATTER_F32>(ta, tb, to, p, st);
     case DUO_EPI_F32: return launch<BLOCK_N, DUO_EPI_F32>(ta, tb, to, p, st);
@@ -989,67 +1096,39 @@ int dispatch_epi(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap
 }
 
 template <int EPI, int EPI_WARPS>
-int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
+int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tx,
                 const GemmParams& p, cudaStream_t st) {
-  using C = PairCfg<EPI_WARPS, EPI == kEpiResidualLn>;
+  using C = PairCfg<EPI_WARPS, EPI == kEpiResidualFwd>;
   static uint64_t configured = 0;  // per device
   auto kfn = gemm_tcgen05_pair_kernel<EPI, EPI_WARPS>;
   if (first_use_on_device(configured))
     DUO_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(C::kSmemBytes)));
   const int64_t units = static_cast<int64_t>(p.num_m_blocks) * p.num_n_blocks;  // tiles, round-robin over pairs
-  // DUO_GEMM_MAX_SMS caps the persistent grid (leaves SMs to kernels running beside the GEMM)
-  static const int sm_cap = [] { const char* e = getenv("DUO_GEMM_MAX_SMS"); return e ? atoi(e) : 0; }();
-  const int sms_avail = device_sm_count();
-  const int pairs_max = ((sm_cap > 1 && sm_cap < sms_avail) ? sm_cap : sms_avail) / 2;
+  const int pairs_max = device_sm_count() / 2;
   const int pairs = static_cast<int>(units < pairs_max ? units : pairs_max);
-  kfn<<<2 * pairs, C::kThreads, C::kSmemBytes, st>>>(ta, tb, to, p);
+  kfn<<<2 * pairs, C::kThreads, C::kSmemBytes, st>>>(ta, tb, to, tx, p);
   DUO_LAUNCH_CHECK("gemm_tcgen05_pair_kernel");
   return DUO_OK;
 }
 
-int dispatch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
+// Epilogue warps of the pair kernel: 8 (two per TMEM lane quarter) where the epilogue is heavy and K short
+// (GELU, token scatter), 4 otherwise.
+int dispatch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tx,
                   const GemmParams& p, int epi, cudaStream_t st) {
   switch (epi) {
-    case kEpiResidualLn: return launch_pair<kEpiResidualLn, 4>(ta, tb, to, p, st);
-    case DUO_EPI_BF16: return launch_pair<DUO_EPI_BF16, 4>(ta, tb, to, p, st);
-    case DUO_EPI_GELU_BF16: {
-      static const int gelu_warps = [] { const char* e = getenv("DUO_GEMM_GELU_WARPS"); return (e && e[0] == '4') ? 4 : 8; }();
-      return gelu_warps == 8 ? launch_pair<DUO_EPI_GELU_BF16, 8>(ta, tb, to, p, st)
-                             : launch_pair<DUO_EPI_GELU_BF16, 4>(ta, tb, to, p, st);
-    }
-    case DUO_EPI_RESIDUAL_F32: return launch_pair<DUO_EPI_RESIDUAL_F32, 4>(ta, tb, to, p, st);
-    case kEpiResidualTma: return launch_pair<kEpiResidualTma, 4>(ta, tb, to, p, st);
-    case DUO_EPI_SCATTER_F32: {  // short K, store-bound epilogue: 8 warps (DUO_GEMM_SCATTER_WARPS=4 for the A/B)
-      static const int w = [] { const char* e = getenv("DUO_GEMM_SCATTER_WARPS"); return (e && e[0] == '4') ? 4 : 8; }();
-      return w == 8 ? launch_pair<DUO_EPI_SCATTER_F32, 8>(ta, tb, to, p, st)
-                    : launch_pair<DUO_EPI_SCATTER_F32, 4>(ta, tb, to, p, st);
-    }
-    case DUO_EPI_F32: return launch_pair<DUO_EPI_F32, 4>(ta, tb, to, p, st);
-    case DUO_EPI_SPLIT_BF16: return launch_pair<DUO_EPI_SPLIT_BF16, 4>(ta, tb, to, p, st);
-    case DUO_EPI_GELU_SPLIT_BF16: return launch_pair<DUO_EPI_GELU_SPLIT_BF16, 8>(ta, tb, to, p, st);
+    case DUO_EPI_BF16: return launch_pair<DUO_EPI_BF16, 4>(ta, tb, to, tx, p, st);
+    case DUO_EPI_GELU_BF16: return launch_pair<DUO_EPI_GELU_BF16, 8>(ta, tb, to, tx, p, st);
+    case kEpiBf16Ln: return launch_pair<kEpiBf16Ln, 4>(ta, tb, to, tx, p, st);
+    case kEpiGeluBf16Ln: return launch_pair<kEpiGeluBf16Ln, 8>(ta, tb, to, tx, p, st);
+    case kEpiResidualTma: return launch_pair<kEpiResidualTma, 4>(ta, tb, to, tx, p, st);
+    case kEpiResidualFwd: return launch_pair<kEpiResidualFwd, 4>(ta, tb, to, tx, p, st);
+    case DUO_EPI_SCATTER_F32: return launch_pair<DUO_EPI_SCATTER_F32, 8>(ta, tb, to, tx, p, st);
+    case DUO_EPI_F32: return launch_pair<DUO_EPI_F32, 4>(ta, tb, to, tx, p, st);
+    case DUO_EPI_SPLIT_BF16: return launch_pair<DUO_EPI_SPLIT_BF16, 4>(ta, tb, to, tx, p, st);
+    case DUO_EPI_GELU_SPLIT_BF16: return launch_pair<DUO_EPI_GELU_SPLIT_BF16, 8>(ta, tb, to, tx, p, st);
     default: set_error("duo_gemm: unknown epilogue %d", epi); return DUO_ERR_INVALID;
   }
-}
-
-// DUO_GEMM_PAIR=0 disables the CTA-pair (cta_group::2) kernel.
-bool pair_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("DUO_GEMM_PAIR");
-    v = (e != nullptr && e[0] == '0') ? 0 : 1;
-  }
-  return v == 1;
-}
-
-// DUO_GEMM_RESIDUAL=direct selects the load/add/store residual epilogue instead of TMA reduce-add.
-bool residual_via_tma() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("DUO_GEMM_RESIDUAL");
-    v = (e != nullptr && e[0] == 'd') ? 0 : 1;
-  }
-  return v == 1;
 }
 
 }  // namespace
@@ -1080,48 +1159,64 @@ extern "C" int duo_gemm(const duo_gemm_args* a, duo_stream_t stream) {
     DUO_CHECK_ARG(a->pos == nullptr || a->pos_period > 0, "duo_gemm: pos_period must be > 0");
   }
   DUO_CHECK_ARG(a->M < (int64_t(1) << 31) - 256, "duo_gemm: M too large for a 32-bit TMA coordinate");
+  int epi = a->epilogue;
+  // statistics forwarding, producer side: residual update that also emits the bf16 copy + row statistics
+  const bool fwd = a->xb_out != nullptr || a->stats_out != nullptr;
+  if (fwd) {
+    DUO_CHECK_ARG(epi == DUO_EPI_RESIDUAL_F32 && a->split3 == 0 && a->xb_out && a->stats_out,
+                  "duo_gemm: statistics forwarding needs the plain-bf16 residual epilogue and both xb_out and stats_out");
+    DUO_CHECK_ARG(a->N % kPairBlockN == 0, "duo_gemm: statistics forwarding needs N %% 256 == 0 (N=%d)", a->N);
+    DUO_CHECK_ARG((reinterpret_cast<uintptr_t>(a->xb_out) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->stats_out) & 7) == 0,
+                  "duo_gemm: xb_out must be 16-byte aligned, stats_out 8-byte aligned");
+  }
+  // consumer side: LayerNorm applied in the epilogue from forwarded statistics
+  const bool ln_apply = a->ln_stats != nullptr || a->ln_colsum != nullptr;
+  if (ln_apply) {
+    DUO_CHECK_ARG((epi == DUO_EPI_BF16 || epi == DUO_EPI_GELU_BF16) && a->split3 == 0 && !a->relu && a->ln_stats && a->ln_colsum,
+                  "duo_gemm: a forwarded LayerNorm needs the BF16 / GELU_BF16 epilogue, plain bf16 operands, ln_stats and ln_colsum");
+    DUO_CHECK_ARG(a->K % kStatCols == 0, "duo_gemm: a forwarded LayerNorm needs K %% 128 == 0 (K=%d)", a->K);
+    DUO_CHECK_ARG((reinterpret_cast<uintptr_t>(a->ln_stats) & 7) == 0 && (reinterpret_cast<uintptr_t>(a->ln_colsum) & 15) == 0,
+                  "duo_gemm: ln_stats must be 8-byte aligned, ln_colsum 16-byte aligned");
+    epi = epi == DUO_EPI_BF16 ? kEpiBf16Ln : kEpiGeluBf16Ln;
+  }
+  if (epi == DUO_EPI_RESIDUAL_F32) epi = fwd ? kEpiResidualFwd : kEpiResidualTma;
 
   // Tile shape: CTA-pair 256x256 when N allows and there are at least two waves of pair tiles;
-  // else 128 x 256 (enough tiles to fill the machine) or 128 x 128.
+  // else 128 x 256 (enough tiles to fill the machine) or 128 x 128.  The forwarding epilogue exists in the
+  // pair kernel only.
   int64_t m_blocks = (a->M + kBlockM - 1) / kBlockM;
   int block_n = 128;
   if (a->N % 256 == 0 && m_blocks * (a->N / 256) >= 2 * device_sm_count()) block_n = 256;
   const int64_t m2_blocks = (a->M + 2 * kBlockM - 1) / (2 * kBlockM);
-  const bool use_pair = pair_enabled() && a->N % 256 == 0 && m2_blocks * (a->N / 256) >= device_sm_count();
+  const bool use_pair = fwd || (a->N % 256 == 0 && m2_blocks * (a->N / 256) >= device_sm_count());
   if (use_pair) {
     block_n = 128;  // W box rows: each CTA loads half of the 256-wide tile
     m_blocks = m2_blocks;
   }
 
-  CUtensorMap ta, tb, to;
+  CUtensorMap ta, tb, to, tx;
   int rc = make_tmap(&ta, a->A, a->M, acols, a->lda, kBlockM, 2);
   if (rc != DUO_OK) return rc;
   rc = make_tmap(&tb, a->W, a->N, kcols, a->ldw, block_n, 2);
   if (rc != DUO_OK) return rc;
-  int epi = a->epilogue;
-  const bool want_ln = a->ln_out != nullptr;
-  if (want_ln) {
-    DUO_CHECK_ARG(epi == DUO_EPI_RESIDUAL_F32 && !a->split3 && a->ln_gamma && a->ln_beta,
-                  "duo_gemm: fused LayerNorm needs the bf16 residual epilogue and ln_gamma / ln_beta");
-    DUO_CHECK_ARG(a->N % 128 == 0 && a->N <= 1024, "duo_gemm: fused LayerNorm needs N %% 128 == 0, N <= 1024");
-    DUO_CHECK_ARG((reinterpret_cast<uintptr_t>(a->ln_out) & 15) == 0, "duo_gemm: ln_out must be 16-byte aligned");
-  }
-  const bool fused_ln = want_ln && use_pair && a->ln_sync != nullptr && (a->N == 384 || a->N == 768 || a->N == 1024);
-  if (fused_ln) epi = kEpiResidualLn;
-  if (epi == DUO_EPI_RESIDUAL_F32 && residual_via_tma()) epi = kEpiResidualTma;
-  if (epi == DUO_EPI_BF16 || epi == DUO_EPI_GELU_BF16) {
+  if (epi == DUO_EPI_BF16 || epi == DUO_EPI_GELU_BF16 || epi == kEpiBf16Ln || epi == kEpiGeluBf16Ln) {
     rc = make_tmap(&to, a->out, a->M, a->N, a->ldo, 32, 2);
-  } else if (epi == kEpiResidualTma || epi == kEpiResidualLn) {
+  } else if (epi == kEpiResidualTma || epi == kEpiResidualFwd) {
     rc = make_tmap(&to, a->out, a->M, a->N, a->ldo, 32, 4);
   } else {
     to = ta;  // unused by the direct-store epilogues
   }
   if (rc != DUO_OK) return rc;
+  if (fwd) {
+    rc = make_tmap(&tx, a->xb_out, a->M, a->N, a->N, 32, 2, 64);
+    if (rc != DUO_OK) return rc;
+  } else {
+    tx = ta;  // unused
+  }
   GemmParams p;
-  p.ln_gamma = a->ln_gamma;
-  p.ln_beta = a->ln_beta;
-  p.ln_out = a->ln_out;
-  p.ln_sync = a->ln_sync;
+  p.stats_out = reinterpret_cast<float2*>(a->stats_out);
+  p.ln_stats = reinterpret_cast<const float2*>(a->ln_stats);
+  p.ln_colsum = a->ln_colsum;
   p.ln_eps = a->ln_eps;
   p.relu = a->relu;
   p.bias = a->bias;
@@ -1141,10 +1236,6 @@ extern "C" int duo_gemm(const duo_gemm_args* a, duo_stream_t stream) {
   p.idesc_mask = a->fp16_operands ? ~((1u << 7) | (1u << 10)) : ~0u;  // a_format / b_format: 1 = BF16, 0 = F16
   p.num_n_blocks = use_pair ? a->N / kPairBlockN : a->N / block_n;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (use_pair) return dispatch_pair(ta, tb, to, p, epi, st);
-  rc = block_n == 256 ? dispatch_epi<256>(ta, tb, to, p, epi, st) : dispatch_epi<128>(ta, tb, to, p, epi, st);
-  if (rc != DUO_OK || !want_ln) return rc;
-  // small problems: unfused — LayerNorm of the updated rows as a second launch
-  return duo_layernorm(reinterpret_cast<const float*>(a->out), a->ln_gamma, a->ln_beta, a->ln_out, DUO_ACT_BF16,
-                       a->M, a->N, a->ldo, a->ln_eps, stream);
+  if (use_pair) return dispatch_pair(ta, tb, to, tx, p, epi, st);
+  return block_n == 256 ? dispatch_epi<256>(ta, tb, to, p, epi, st) : dispatch_epi<128>(ta, tb, to, p, epi, st);
 }

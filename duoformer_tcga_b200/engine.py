@@ -75,59 +75,76 @@ def _align(n: int, a: int = 1024) -> int:
     return (n + a - 1) // a * a
 
 
-# bf16 mode: run each LayerNorm inside the preceding residual GEMM (duo_gemm's ln_out: extra LayerNorm
-# warps re-read every finished 256-row panel and write the bf16 operand of the next GEMM).
-# Correct (tests/test_kernels_gpu.py, parity suite with the flag on) but OFF by default: on the
-# power-capped B200 the LayerNorm's traffic costs the same time inside the GEMM as beside it —
-# per 64 images fc2+LN1 1.13 ms fused vs 1.15 ms as two launches, proj+LN2 0.60 vs 0.55 ms
-# (profiles/r01_notes.md; the first version, LN in the epilogue warps, was 2x slower still).
-FUSE_LAYERNORM = False
+# bf16 mode: LayerNorm statistics forwarding (duo_gemm's xb_out / stats_out / ln_stats).  Every residual GEMM
+# (proj, fc2) also writes the bf16 copy of the updated rows and their per-row partial statistics; the GEMM that
+# follows (fc1, next block's QKV) runs on W * diag(ln_weight) and applies mean / rstd in its epilogue, so no
+# LayerNorm kernel re-reads the fp32 stream (only block 0's norm1 and the live rows of the last block run as
+# standalone launches).  Precision study: tests/diag_ln_forwarding.py (same error as LayerNorm-then-round for
+# |row mean| <= row spread; fp32 mode keeps the standalone LayerNorm).  Needs D % 256 == 0.
+FORWARD_LN_STATS = True
+
+STAT_COLS = 128  # columns per forwarded (mean, M2) pair (csrc/gemm_tcgen05.cu kStatCols)
 
 
-_LN_SYNC = {}
+def pack_ln_linear(weight: torch.Tensor, bias: Optional[torch.Tensor], ln_weight: torch.Tensor, ln_bias: torch.Tensor):
+    """Linear(LayerNorm(x)) with the affine part of the norm folded in (consumer side of the statistics forwarding):
+    W' = bf16(W * ln_weight), bias' = W ln_bias + b (fp32, exact W), colsum[n] = sum_k W'[n, k] of the ROUNDED values
+    (it must cancel against the tensor-core product of the same values)."""
+    w = weight.detach().to(torch.float32)
+    wp = (w * ln_weight.detach().to(torch.float32)[None, :]).to(torch.bfloat16).contiguous()
+    b = w @ ln_bias.detach().to(torch.float32)
+    if bias is not None:
+        b = b + bias.detach().to(torch.float32)
+    return wp, b.contiguous(), wp.to(torch.float32).sum(dim=1).contiguous()
 
 
-def _ln_sync(device, rows, slot):
-    """Zeroed row-panel counters for duo_gemm's fused LayerNorm (8 per 256 rows).  Every launch leaves
-    them zero, so one buffer per (device, concurrently running chunk) is allocated once and reused."""
-    need = 8 * ((rows + 255) // 256)
-    key = (device.index, slot)
-    t = _LN_SYNC.get(key)
-    if t is None or t.numel() < need:
-        t = torch.zeros(need, dtype=torch.int32, device=device)
-        _LN_SYNC[key] = t
-    return t
+def pack_scale_block(precision: str, n1w, n1b, n2w, n2b, qkv, proj, fc1, fc2, g1=None, g2=None) -> Dict:
+    """Packed device operands of one scale block ((weight, bias) pairs of the four Linears + the two norms)."""
+    d = {
+        "n1w": _f32(n1w), "n1b": _f32(n1b), "n2w": _f32(n2w), "n2b": _f32(n2b),
+        "qkv": pack_linear(qkv[0], qkv[1], precision), "proj": pack_linear(proj[0], proj[1], precision),
+        "fc1": pack_linear(fc1[0], fc1[1], precision), "fc2": pack_linear(fc2[0], fc2[1], precision),
+        "g1": _f32(g1), "g2": _f32(g2),
+    }
+    if precision == "bf16":
+        d["qkv_ln"] = pack_ln_linear(qkv[0], qkv[1], n1w, n1b)
+        d["fc1_ln"] = pack_ln_linear(fc1[0], fc1[1], n2w, n2b)
+    return d
 
 
-def _scale_chunk_ops(X, b0, nb, buf, blocks, num_heads, scale, eps, precision, capture, attn_algo, live_only_last):
-    """Generator over the kernel launches of all scale blocks for images [b0, b0+nb): yields after
-    every launch so that two chunks can be issued interleaved on two streams (see scale_stage).
+def _scale_chunk(X, b0, nb, buf, blocks, num_heads, scale, eps, precision, capture, attn_algo, live_only_last):
+    """All scale blocks for images [b0, b0+nb).
 
-    bf16 mode, per block (5 launches): QKV GEMM, attention, proj GEMM (+residual +LayerNorm2),
-    fc1 GEMM (+GELU), fc2 GEMM (+residual +LayerNorm1 of the NEXT block); only block 0 needs a
-    standalone LayerNorm launch.  fp32 mode keeps the LayerNorm launches (split hi|lo outputs)."""
+    bf16 mode with statistics forwarding, per block (5 launches): QKV GEMM (LayerNorm applied in its epilogue),
+    attention, proj GEMM (+residual, emits bf16 rows + statistics), fc1 GEMM (LayerNorm in the epilogue, +GELU),
+    fc2 GEMM (+residual, emits the next block's bf16 rows + statistics).  fp32 mode (and D % 256 != 0): 7 launches
+    with standalone LayerNorm kernels (split hi|lo outputs in fp32 mode)."""
     B, P, S, D = X.shape
     fp32 = precision == "fp32"
-    fuse = FUSE_LAYERNORM and not fp32
+    fwd = FORWARD_LN_STATS and not fp32 and D % 256 == 0 and "qkv_ln" in blocks[0]
     kd = 2 if fp32 else 1
     hidden = blocks[0]["fc1"][0].shape[0]
     T = nb * P * S
     hn_bytes = _align(T * kd * D * 2)
     Xc = X[b0 : b0 + nb].view(T, D)
-    Ha = Workspace.view(buf, 0, (T, kd * D), torch.bfloat16)             # LayerNorm outputs
+    Ha = Workspace.view(buf, 0, (T, kd * D), torch.bfloat16)             # LayerNorm output / bf16 copy of the stream
     Hb = Workspace.view(buf, hn_bytes, (T, kd * D), torch.bfloat16)      # attention output
     QKV = Workspace.view(buf, 2 * hn_bytes, (T, 3 * D), torch.float32 if fp32 else torch.bfloat16)
     HID = Workspace.view(buf, 2 * hn_bytes, (T, kd * hidden), torch.bfloat16)  # aliases QKV (dead after attention)
+    big = _align(max(T * 3 * D * (4 if fp32 else 2), T * kd * hidden * 2))
+    ST = Workspace.view(buf, 2 * hn_bytes + big, (T, D // STAT_COLS, 2), torch.float32) if fwd else None
     gelu = ops.EPI_GELU_SPLIT_BF16 if fp32 else ops.EPI_GELU_BF16
     L = len(blocks)
-    sync = _ln_sync(X.device, T, b0) if fuse else None
+    have_ln1 = False  # Ha / ST hold the forwarded norm1 input of the current block
     for i, blk in enumerate(blocks):
         last = i == L - 1
-        if i == 0 or not fuse:
+        if have_ln1:
+            w, b, cs = blk["qkv_ln"]
+            ops.gemm(Ha, w, b, QKV, ops.EPI_BF16, ln_stats=ST, ln_colsum=cs, ln_eps=eps)
+        else:
             ops.layernorm(Xc, blk["n1w"], blk["n1b"], Ha, eps)
-            yield
-        ops.gemm(Ha, blk["qkv"][0], blk["qkv"][1], QKV, ops.EPI_F32 if fp32 else ops.EPI_BF16, split3=fp32)
-        yield
+            ops.gemm(Ha, blk["qkv"][0], blk["qkv"][1], QKV, ops.EPI_F32 if fp32 else ops.EPI_BF16, split3=fp32)
+        have_ln1 = False
         if live_only_last and last:
             # Last scale block: only the scale token (s = 0) of every patch is consumed downstream
             # (scale_attention.py:183-185), so K/V are needed for all tokens but the query,
@@ -138,44 +155,28 @@ def _scale_chunk_ops(X, b0, nb, buf, blocks, num_heads, scale, eps, precision, c
             A0 = Workspace.view(buf, hn_bytes, (R, kd * D), torch.bfloat16)
             N0 = Workspace.view(buf, 0, (R, kd * D), torch.bfloat16)
             ops.group_attention(QKV, A0, S, num_heads, scale, algo=attn_algo, q_rows=1)
-            yield
-            if fuse:
-                ops.gemm(A0, blk["proj"][0], blk["proj"][1], X0, ops.EPI_RESIDUAL_F32, gamma=blk["g1"],
-                         ln_gamma=blk["n2w"], ln_beta=blk["n2b"], ln_out=N0, ln_eps=eps, ln_sync=sync)
-                yield
-            else:
-                ops.gemm(A0, blk["proj"][0], blk["proj"][1], X0, ops.EPI_RESIDUAL_F32, gamma=blk["g1"], split3=fp32)
-                yield
-                ops.layernorm(X0, blk["n2w"], blk["n2b"], N0, eps)
-                yield
+            ops.gemm(A0, blk["proj"][0], blk["proj"][1], X0, ops.EPI_RESIDUAL_F32, gamma=blk["g1"], split3=fp32)
+            ops.layernorm(X0, blk["n2w"], blk["n2b"], N0, eps)
             H0 = Workspace.view(buf, 2 * hn_bytes, (R, kd * hidden), torch.bfloat16)
             ops.gemm(N0, blk["fc1"][0], blk["fc1"][1], H0, gelu, split3=fp32)
-            yield
             ops.gemm(H0, blk["fc2"][0], blk["fc2"][1], X0, ops.EPI_RESIDUAL_F32, gamma=blk["g2"], split3=fp32)
-            yield
             if capture is not None:
                 capture[f"scale_block_{i}_s0"] = X[:, :, 0, :].clone()
             continue
         ops.group_attention(QKV, Hb, S, num_heads, scale, algo=attn_algo)
-        yield
-        if fuse:
-            ops.gemm(Hb, blk["proj"][0], blk["proj"][1], Xc, ops.EPI_RESIDUAL_F32, gamma=blk["g1"],
-                     ln_gamma=blk["n2w"], ln_beta=blk["n2b"], ln_out=Ha, ln_eps=eps, ln_sync=sync)
-            yield
+        if fwd:
+            ops.gemm(Hb, blk["proj"][0], blk["proj"][1], Xc, ops.EPI_RESIDUAL_F32, gamma=blk["g1"], xb_out=Ha, stats_out=ST)
+            w, b, cs = blk["fc1_ln"]
+            ops.gemm(Ha, w, b, HID, gelu, ln_stats=ST, ln_colsum=cs, ln_eps=eps)
         else:
             ops.gemm(Hb, blk["proj"][0], blk["proj"][1], Xc, ops.EPI_RESIDUAL_F32, gamma=blk["g1"], split3=fp32)
-            yield
             ops.layernorm(Xc, blk["n2w"], blk["n2b"], Ha, eps)
-            yield
-        ops.gemm(Ha, blk["fc1"][0], blk["fc1"][1], HID, gelu, split3=fp32)
-        yield
-        if fuse and not last:
-            nxt = blocks[i + 1]
-            ops.gemm(HID, blk["fc2"][0], blk["fc2"][1], Xc, ops.EPI_RESIDUAL_F32, gamma=blk["g2"],
-                     ln_gamma=nxt["n1w"], ln_beta=nxt["n1b"], ln_out=Ha, ln_eps=eps, ln_sync=sync)
+            ops.gemm(Ha, blk["fc1"][0], blk["fc1"][1], HID, gelu, split3=fp32)
+        if fwd and not last:
+            ops.gemm(HID, blk["fc2"][0], blk["fc2"][1], Xc, ops.EPI_RESIDUAL_F32, gamma=blk["g2"], xb_out=Ha, stats_out=ST)
+            have_ln1 = True
         else:
             ops.gemm(HID, blk["fc2"][0], blk["fc2"][1], Xc, ops.EPI_RESIDUAL_F32, gamma=blk["g2"], split3=fp32)
-        yield
         if capture is not None:
             capture[f"scale_block_{i}"] = X.clone()
 
@@ -183,17 +184,8 @@ def _scale_chunk_ops(X, b0, nb, buf, blocks, num_heads, scale, eps, precision, c
 def _chunk_workspace_bytes(nb, P, S, D, hidden, fp32):
     T = nb * P * S
     kd = 2 if fp32 else 1
-    return 2 * _align(T * kd * D * 2) + _align(max(T * 3 * D * (4 if fp32 else 2), T * kd * hidden * 2))
-
-
-# Optional two-lane issue: the HBM-bound kernels (LayerNorm) of one half of the batch overlap the
-# tensor-bound GEMMs of the other half (LN CTAs need no shared memory, so they co-reside with the
-# persistent GEMM CTAs).  Lane 1 trails lane 0 by _LANE_OFFSET launches.  Measured on a
-# power-capped B200 (profiles/r01_notes.md): 1 217 vs 1 210 images/s — within noise, because the
-# step is limited by the 1 kW cap rather than by idle pipes — so it is OFF by default.
-OVERLAP_LANES = False
-_LANE_OFFSET = 1
-_side_streams: Dict[int, Tuple[torch.cuda.Stream, torch.cuda.Stream]] = {}
+    stats = 0 if fp32 else _align(T * (D // STAT_COLS) * 8)
+    return 2 * _align(T * kd * D * 2) + _align(max(T * 3 * D * (4 if fp32 else 2), T * kd * hidden * 2)) + stats
 
 
 def scale_stage(
@@ -207,10 +199,14 @@ def scale_stage(
     capture: Optional[Dict[str, torch.Tensor]] = None,
     attn_algo: int = 0,
     max_chunk_tokens: int = 1 << 21,
-    live_only_last: bool = True,
+    live_only_last: bool = False,
 ) -> torch.Tensor:
     """L x { X += g1*Attn(LN1 X) ; X += g2*MLP(LN2 X) } in place on the fp32 token tensor
-    X [B, P, S, D]  (scale_attention.py:90-93 / multiscale_attn.py:282-285)."""
+    X [B, P, S, D]  (scale_attention.py:90-93 / multiscale_attn.py:282-285).
+
+    live_only_last: whole-model callers only — the LAST block updates just the s = 0 row of every patch
+    (all that MultiscaleFormer / MultiscaleTransformer consume afterwards); the other rows keep their
+    pre-block values."""
     B, P, S, D = X.shape
     if not blocks:
         return X
@@ -220,54 +216,10 @@ def scale_stage(
     chunk_images = max(1, min(B, max_chunk_tokens // tokens_per_image))
     if capture is not None:
         chunk_images = B  # captures want whole-batch tensors after every block
-    two_lanes = OVERLAP_LANES and capture is None and B >= 2 and B * tokens_per_image >= (1 << 13)
-    if two_lanes:
-        chunk_images = max(1, min(chunk_images, (B + 1) // 2))
-    chunks = [(b0, min(chunk_images, B - b0)) for b0 in range(0, B, chunk_images)]
-    per_chunk = _chunk_workspace_bytes(chunk_images, P, S, D, hidden, fp32)
-    args = (blocks, num_heads, scale, eps, precision, capture, attn_algo, live_only_last)
-    if not two_lanes:
-        buf = ws.get(per_chunk)
-        for b0, nb in chunks:
-            for _ in _scale_chunk_ops(X, b0, nb, buf, *args):
-                pass
-        return X
-
-    buf = ws.get(2 * per_chunk)
-    bufs = (buf[:per_chunk], buf[per_chunk:])
-    dev = X.device.index if X.device.index is not None else torch.cuda.current_device()
-    if dev not in _side_streams:
-        _side_streams[dev] = (torch.cuda.Stream(device=X.device), torch.cuda.Stream(device=X.device))
-    lanes = _side_streams[dev]
-    main = torch.cuda.current_stream(X.device)
-    start = torch.cuda.Event()
-    start.record(main)
-    for s in lanes:
-        s.wait_event(start)
-    for c in range(0, len(chunks), 2):
-        gens = [_scale_chunk_ops(X, chunks[c][0], chunks[c][1], bufs[0], *args)]
-        if c + 1 < len(chunks):
-            gens.append(_scale_chunk_ops(X, chunks[c + 1][0], chunks[c + 1][1], bufs[1], *args))
-        alive = [True] * len(gens)
-
-        def step(k):
-            if alive[k]:
-                with torch.cuda.stream(lanes[k]):
-                    try:
-                        next(gens[k])
-                    except StopIteration:
-                        alive[k] = False
-
-        for _ in range(_LANE_OFFSET):
-            step(0)
-        while any(alive):
-            if len(gens) > 1:
-                step(1)
-            step(0)
-    for s in lanes:
-        done = torch.cuda.Event()
-        done.record(s)
-        main.wait_event(done)
+    buf = ws.get(_chunk_workspace_bytes(chunk_images, P, S, D, hidden, fp32))
+    for b0 in range(0, B, chunk_images):
+        _scale_chunk(X, b0, min(chunk_images, B - b0), buf, blocks, num_heads, scale, eps, precision, capture,
+                     attn_algo, live_only_last)
     return X
 
 

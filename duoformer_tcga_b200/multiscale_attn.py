@@ -48,19 +48,16 @@ class MultiscaleBlock(nn.Module, engine.PackCache):
     def pack(self, precision: str) -> Dict:
         def build():
             pl = partial(engine.pack_linear, precision=precision)
-            return {
-                "n1w": engine._f32(self.norm1.weight), "n1b": engine._f32(self.norm1.bias),
-                "n2w": engine._f32(self.norm2.weight), "n2b": engine._f32(self.norm2.bias),
-                # scale attention uses the second weight set (forward_with_scale :149-166)
-                "qkv": pl(self.attn.qkv1.weight, self.attn.qkv1.bias),
-                "proj": pl(self.attn.proj1.weight, self.attn.proj1.bias),
-                "fc1": pl(self.mlp.fc1.weight, self.mlp.fc1.bias),
-                "fc2": pl(self.mlp.fc2.weight, self.mlp.fc2.bias),
-                "g1": engine._f32(self.ls1.gamma) if isinstance(self.ls1, LayerScale) else None,
-                "g2": engine._f32(self.ls2.gamma) if isinstance(self.ls2, LayerScale) else None,
-                # region attention uses the inherited set (forward_with_region :190-221)
-                "region": {"qkv": pl(self.attn.qkv.weight, self.attn.qkv.bias),
-                           "proj": pl(self.attn.proj.weight, self.attn.proj.bias)},
-            }
+            at, mlp = self.attn, self.mlp
+            # scale attention uses the second weight set (forward_with_scale :149-166)
+            d = engine.pack_scale_block(
+                precision, self.norm1.weight, self.norm1.bias, self.norm2.weight, self.norm2.bias,
+                (at.qkv1.weight, at.qkv1.bias), (at.proj1.weight, at.proj1.bias),
+                (mlp.fc1.weight, mlp.fc1.bias), (mlp.fc2.weight, mlp.fc2.bias),
+                self.ls1.gamma if isinstance(self.ls1, LayerScale) else None,
+                self.ls2.gamma if isinstance(self.ls2, LayerScale) else None)
+            # region attention uses the inherited set (forward_with_region :190-221)
+            d["region"] = {"qkv": pl(at.qkv.weight, at.qkv.bias), "proj": pl(at.proj.weight, at.proj.bias)}
+            return d
 
         return self.packed(build, self, precision)

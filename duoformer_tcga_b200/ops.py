@@ -7,6 +7,7 @@ non-CUDA tensor raises.
 from __future__ import annotations
 
 import ctypes
+import functools
 from typing import Optional
 
 import torch
@@ -35,6 +36,28 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def _on_operand_device(fn):
+    """Run `fn` with the operands' device current: the library launches on the CURRENT device (kernel
+    attributes, SM count, tensor maps), so tensors living on another device must switch it first.  All
+    tensor operands must share one device."""
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = None
+        for v in list(args) + list(kwargs.values()):
+            if isinstance(v, torch.Tensor) and v.is_cuda:
+                if dev is None:
+                    dev = v.device
+                elif v.device != dev:
+                    raise RuntimeError(f"{fn.__name__}: operands on different devices ({dev} and {v.device})")
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+
+    return wrapper
+
+
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     if t is None:
         return None
@@ -51,6 +74,7 @@ def _act_kind(t: torch.Tensor, cols: int) -> int:
     return ACT_SPLIT if t.shape[-1] == 2 * cols else ACT_BF16
 
 
+@_on_operand_device
 def gemm(
     A: torch.Tensor,
     W: torch.Tensor,
@@ -65,15 +89,20 @@ def gemm(
     dest_rows_per_group: int = 0,
     pos: Optional[torch.Tensor] = None,
     pos_period: int = 0,
-    ln_gamma: Optional[torch.Tensor] = None,
-    ln_beta: Optional[torch.Tensor] = None,
-    ln_out: Optional[torch.Tensor] = None,
-    ln_eps: float = 1e-6,
     relu: bool = False,
-    ln_sync: Optional[torch.Tensor] = None,
+    xb_out: Optional[torch.Tensor] = None,
+    stats_out: Optional[torch.Tensor] = None,
+    ln_stats: Optional[torch.Tensor] = None,
+    ln_colsum: Optional[torch.Tensor] = None,
+    ln_eps: float = 1e-6,
 ) -> torch.Tensor:
     """out = epilogue(A @ W.T + bias).  A [M,K] / W [N,K] bf16 (or [.,2K] split when split3).
-    ln_out (bf16 [M,N], with EPI_RESIDUAL_F32): also LayerNorm(updated out rows) in the same kernel."""
+
+    LayerNorm statistics forwarding (include/duoformer_sm100.h):
+      producer  EPI_RESIDUAL_F32 with xb_out (bf16 [M,N]) + stats_out (fp32 [M, N/128, 2]): the updated rows are
+                also written un-normalised in bf16 together with their per-128-column (mean, M2) pairs;
+      consumer  EPI_BF16 / EPI_GELU_BF16 with ln_stats + ln_colsum: A is such a copy, W = W * ln_weight,
+                bias = W ln_bias + b; the epilogue applies mean / rstd."""
     split3 = int(split3)  # 0 plain, 1 both operands split (hi|lo), 2 only W split (A exact bf16)
     assert A.dim() == 2 and W.dim() == 2 and W.dtype == A.dtype, "A and W must share one 16-bit format"
     assert A.dtype == torch.bfloat16 or (A.dtype == torch.float16 and split3 == 0), "operands must be bf16 (or fp16 in plain mode)"
@@ -93,12 +122,14 @@ def gemm(
     a.fp16_operands = 1 if A.dtype == torch.float16 else 0
     a.epilogue = epilogue
     a.rows_per_group, a.dest_rows_per_group, a.pos_period = rows_per_group, dest_rows_per_group, pos_period
-    if ln_out is not None:
-        assert ln_out.dtype == torch.bfloat16 and ln_out.is_contiguous() and ln_out.shape[-1] == N
-        a.ln_gamma, a.ln_beta, a.ln_out, a.ln_eps = _ptr(ln_gamma), _ptr(ln_beta), _ptr(ln_out), float(ln_eps)
-        if ln_sync is not None:  # zeroed int32 scratch, 8 per 256-row panel; left zero by every launch
-            assert ln_sync.dtype == torch.int32 and ln_sync.is_contiguous() and ln_sync.numel() >= 8 * ((M + 255) // 256)
-            a.ln_sync = _ptr(ln_sync)
+    if xb_out is not None or stats_out is not None:
+        assert xb_out.dtype == torch.bfloat16 and xb_out.is_contiguous() and xb_out.numel() == M * N
+        assert stats_out.dtype == torch.float32 and stats_out.is_contiguous() and stats_out.numel() >= M * (N // 128) * 2
+        a.xb_out, a.stats_out = _ptr(xb_out), _ptr(stats_out)
+    if ln_stats is not None or ln_colsum is not None:
+        assert ln_stats.dtype == torch.float32 and ln_stats.is_contiguous() and ln_stats.numel() >= M * (K // 128) * 2
+        assert ln_colsum.dtype == torch.float32 and ln_colsum.is_contiguous() and ln_colsum.numel() == N
+        a.ln_stats, a.ln_colsum, a.ln_eps = _ptr(ln_stats), _ptr(ln_colsum), float(ln_eps)
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() == N
     if row_map is not None:
@@ -114,6 +145,7 @@ def gemm(
     return out
 
 
+@_on_operand_device
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out: torch.Tensor, eps: float) -> torch.Tensor:
     """out (bf16 [rows,D] or split bf16 [rows,2D], dense) = LayerNorm(x fp32 [rows,D]).
     x may be a 2-D row-strided view (e.g. the s = 0 token of every patch)."""
@@ -133,6 +165,7 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out: tor
     return out
 
 
+@_on_operand_device
 def group_attention(
     qkv: torch.Tensor, out: torch.Tensor, S: int, num_heads: int, scale: float, algo: int = 0, q_rows: int = 0,
     split_in: bool = False,
@@ -159,6 +192,7 @@ def group_attention(
     return out
 
 
+@_on_operand_device
 def fill_scale_token(X: torch.Tensor, tok: torch.Tensor, pos0: torch.Tensor) -> torch.Tensor:
     """X[b,p,0,:] = tok[b,p,:] + pos0.  X fp32 [B,P,S,D]; tok [D] (broadcast) or [B,P,D]."""
     B, P, S, D = X.shape
@@ -175,6 +209,7 @@ def fill_scale_token(X: torch.Tensor, tok: torch.Tensor, pos0: torch.Tensor) -> 
     return X
 
 
+@_on_operand_device
 def add_pos(x: torch.Tensor, pos: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     """out[..., s, :] = x[..., s, :] + pos[s, :]  (x fp32 [..., S, D] contiguous)."""
     S, D = x.shape[-2], x.shape[-1]
@@ -185,6 +220,7 @@ def add_pos(x: torch.Tensor, pos: torch.Tensor, out: torch.Tensor) -> torch.Tens
     return out
 
 
+@_on_operand_device
 def assemble_patch_tokens(X: torch.Tensor, cls: torch.Tensor, pos: torch.Tensor, Z: torch.Tensor) -> torch.Tensor:
     """Z[b,0]=cls+pos[0]; Z[b,1+p]=X[b,p,0]+pos[1+p].  Z bf16 [B,P+1,D] or split [B,P+1,2D]."""
     B, P, S, D = X.shape
@@ -197,6 +233,7 @@ def assemble_patch_tokens(X: torch.Tensor, cls: torch.Tensor, pos: torch.Tensor,
     return Z
 
 
+@_on_operand_device
 def head(
     inp: torch.Tensor,
     row_stride: int,
@@ -220,6 +257,7 @@ def head(
     return logits
 
 
+@_on_operand_device
 def convert(inp: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     """fp32 [rows, cols] -> bf16 [rows, cols] or split bf16 [rows, 2*cols]."""
     assert inp.dtype == torch.float32 and inp.dim() == 2 and inp.stride(1) == 1 and out.is_contiguous()
@@ -234,6 +272,7 @@ def convert(inp: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
 _IN_KIND = {torch.bfloat16: _lib.ACT_BF16, torch.float16: _lib.ACT_F16, torch.float32: ACT_F32}
 
 
+@_on_operand_device
 def im2col3x3(x_nhwc: torch.Tensor, stride: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """NHWC [B,H,W,C] (bf16/f16/f32, contiguous) -> bf16 [B*Ho*Wo, 9*C] patches of a 3x3 / pad 1 / stride s conv."""
     assert x_nhwc.dim() == 4 and x_nhwc.is_contiguous()
@@ -247,6 +286,7 @@ def im2col3x3(x_nhwc: torch.Tensor, stride: int, out: Optional[torch.Tensor] = N
     return out
 
 
+@_on_operand_device
 def pool_to_slice(x_nhwc: torch.Tensor, out_slice: torch.Tensor, pool: int) -> torch.Tensor:
     """2x2 max-pool (pool=2) or copy (pool=1) of NHWC [B,H,W,C] into out_slice = wide[:, c0:c0+C]
     (a bf16 [B*Ho*Wo, C] column slice of a wider contiguous matrix)."""
@@ -258,6 +298,7 @@ def pool_to_slice(x_nhwc: torch.Tensor, out_slice: torch.Tensor, pool: int) -> t
     return out_slice
 
 
+@_on_operand_device
 def maxpool3x3s2(x: torch.Tensor) -> torch.Tensor:
     """nn.MaxPool2d(3, 2, 1) of a channels-last fp16 / bf16 NCHW tensor; returns a channels-last tensor."""
     assert x.dim() == 4 and x.dtype in (torch.float16, torch.bfloat16)

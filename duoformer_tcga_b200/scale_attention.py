@@ -56,17 +56,13 @@ class ScaleBlock(nn.Module, engine.PackCache):
 
     def pack(self, precision: str) -> Dict:
         def build():
-            pl = partial(engine.pack_linear, precision=precision)
-            return {
-                "n1w": engine._f32(self.norm1.weight), "n1b": engine._f32(self.norm1.bias),
-                "n2w": engine._f32(self.norm2.weight), "n2b": engine._f32(self.norm2.bias),
-                "qkv": pl(self.attn.qkv.weight, self.attn.qkv.bias),
-                "proj": pl(self.attn.proj.weight, self.attn.proj.bias),
-                "fc1": pl(self.mlp.fc1.weight, self.mlp.fc1.bias),
-                "fc2": pl(self.mlp.fc2.weight, self.mlp.fc2.bias),
-                "g1": engine._f32(self.ls1.gamma) if isinstance(self.ls1, LayerScale) else None,
-                "g2": engine._f32(self.ls2.gamma) if isinstance(self.ls2, LayerScale) else None,
-            }
+            at, mlp = self.attn, self.mlp
+            return engine.pack_scale_block(
+                precision, self.norm1.weight, self.norm1.bias, self.norm2.weight, self.norm2.bias,
+                (at.qkv.weight, at.qkv.bias), (at.proj.weight, at.proj.bias),
+                (mlp.fc1.weight, mlp.fc1.bias), (mlp.fc2.weight, mlp.fc2.bias),
+                self.ls1.gamma if isinstance(self.ls1, LayerScale) else None,
+                self.ls2.gamma if isinstance(self.ls2, LayerScale) else None)
 
         return self.packed(build, self, precision)
 
@@ -77,7 +73,7 @@ class ScaleBlock(nn.Module, engine.PackCache):
         X = x.to(torch.float32).contiguous().clone()
         ws = engine.Workspace(X.device)
         return engine.scale_stage(X, [self.pack(self.precision)], self.num_heads, self.attn.scale,
-                                  self.norm1.eps, self.precision, ws)
+                                  self.norm1.eps, self.precision, ws, live_only_last=False)
 
 
 class AttentionForPatch(AttentionParams):

@@ -95,22 +95,31 @@ typedef struct duo_gemm_args {
   int32_t rows_per_group;      /* SCATTER: source rows per image (h*w of the stage)        */
   int32_t dest_rows_per_group; /* SCATTER: token rows per image (P*S)                      */
   int32_t pos_period;          /* SCATTER: S                                               */
-  float ln_eps;                /* fused LayerNorm epsilon                                  */
+  float ln_eps;                /* forwarded LayerNorm epsilon (consumer side)              */
   int32_t relu;                /* BF16 / F32 epilogues: out = max(acc + bias, 0) (conv + BN + ReLU of   */
   int32_t fp16_operands;       /* the channel-token branch, projection_head.py:242-254).               */
                                /* fp16_operands = 1: A and W hold IEEE fp16 instead of bf16 (the cuDNN */
                                /* trunk maps are fed as they are; plain mode only, split3 == 0; one    */
                                /* tcgen05.mma takes A and B of the same 16-bit format)                 */
-  /* RESIDUAL_F32 + fused LayerNorm (optional, ln_out != NULL, bf16 operands, N <= 1024):     */
-  /* after out += gamma*(acc+bias), ln_out[M,N] (bf16, dense) = LayerNorm(out rows) — the      */
-  /* x = x + f(x); norm(x) pair of scale_attention.py:91-92 in one kernel.                     */
-  const float* ln_gamma;
-  const float* ln_beta;
-  void* ln_out;
-  /* fused LayerNorm only: caller-owned scratch of 8 * ceil(M / 256) uint32, ZERO before the first */
-  /* use; every launch leaves it zero again (row-panel completion counters shared by the CTAs).    */
-  /* NULL -> the LayerNorm runs as a second launch.                                                */
-  uint32_t* ln_sync;
+  /*
+   * LayerNorm statistics forwarding — the `x = x + f(x); y = Linear(norm(x))` pairs of
+   * scale_attention.py:91-92 without a LayerNorm pass over the residual stream:
+   *
+   * producer (RESIDUAL_F32, bf16 operands, N % 256 == 0, both pointers set): the epilogue loads the fp32
+   *   rows of `out` itself (TMA), adds gamma * (acc + bias), stores them back and ALSO writes
+   *     xb_out    bf16 [M, N] dense: the updated, un-normalised rows (A operand of the next GEMM), and
+   *     stats_out float [M, N / 128, 2]: (mean, sum of squared deviations) of every 128-column part of
+   *               the updated fp32 row.
+   * consumer (BF16 / GELU_BF16, bf16 operands, K % 128 == 0, both pointers set): A is such an un-normalised
+   *   copy, W holds W * diag(ln_weight) and bias holds W ln_bias + b; the epilogue merges the row's K / 128
+   *   partial statistics (ln_stats, same layout as stats_out) into mean / rstd and computes
+   *     out = rstd * (acc - mean * ln_colsum[n]) + bias[n],   ln_colsum[n] = sum_k W'[n, k] (of the bf16 values),
+   *   which equals Linear(LayerNorm(x)) up to operand rounding.
+   */
+  void* xb_out;
+  float* stats_out;
+  const float* ln_stats;
+  const float* ln_colsum;
 } duo_gemm_args;
 int duo_gemm(const duo_gemm_args* args, duo_stream_t stream);
 

@@ -22,14 +22,14 @@ def test_c_abi_library_loads_and_exports_every_declared_symbol():
     lib = _lib.load()  # built by __graft_entry__.build(); fails loudly if missing
     for name in declared:
         assert hasattr(lib, name), f"{name} not exported"
-    assert lib.duo_abi_version() == _lib.ABI_VERSION == 2
+    assert lib.duo_abi_version() == _lib.ABI_VERSION == 3
     assert lib.duo_last_error() is not None
 
 
 def test_gemm_args_struct_layout_matches_header():
     # 7 pointers, 4 int64, 7 int32 + float + 2 int32, 4 pointers -> 8*7 + 8*4 + 4*10 + 8*4 = 160 bytes
     assert ctypes.sizeof(_lib.GemmArgs) == 160
-    assert _lib.GemmArgs.ln_gamma.offset == 128 and _lib.GemmArgs.ln_sync.offset == 152
+    assert _lib.GemmArgs.xb_out.offset == 128 and _lib.GemmArgs.ln_colsum.offset == 152
     assert _lib.GemmArgs.M.offset == 56 and _lib.GemmArgs.N.offset == 88
 
 

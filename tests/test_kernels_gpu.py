@@ -269,32 +269,114 @@ def test_invalid_arguments_raise():
                       torch.zeros(100, device="cuda"), torch.zeros(4, 100, dtype=torch.bfloat16, device="cuda"), 1e-6)
 
 
-@pytest.mark.parametrize("M,K,with_gamma", [(256 * 60 + 77, 768, False), (256 * 60 + 77, 768, True), (256 * 52, 3072, False), (300, 768, True)])
-def test_gemm_residual_with_fused_layernorm(M, K, with_gamma):
-    """x = x + gamma*(A W^T + b); ln = LayerNorm(x) in one kernel (pair kernel: LayerNorm warps re-read
-    each finished row panel from L2); small M falls back to GEMM + LayerNorm launches with the same
-    result.  The panel counters (ln_sync) must be zero again after every launch."""
+def _merge_stats(st, N):
+    """[M, N/128, 2] (mean, M2) partial statistics -> per-row mean, biased variance (Chan's formula)."""
+    parts = st.shape[1]
+    mean = st[:, :, 0].mean(dim=1)
+    m2 = st[:, :, 1].sum(dim=1) + 128.0 * ((st[:, :, 0] - mean[:, None]) ** 2).sum(dim=1)
+    return mean, m2 / (128.0 * parts)
+
+
+@pytest.mark.parametrize("M,K,with_gamma", [(256 * 60 + 77, 768, False), (256 * 60 + 77, 768, True), (256 * 152, 3072, False),
+                                            (300, 768, True), (4214, 768, False), (129, 3072, False)])
+def test_gemm_residual_statistics_forwarding_producer(M, K, with_gamma):
+    """x = x + gamma*(A W^T + b) with xb_out / stats_out: the fp32 rows are updated exactly like the plain residual
+    epilogue, xb_out is their bf16 rounding and stats_out holds (mean, M2) of every 128-column part of the fp32 row
+    (any M: the forwarding epilogue always runs on the CTA-pair kernel; a large row mean exercises the shifted sums)."""
     N = 768
     A = _gen((M, K), 111).to(torch.bfloat16)
     W = _gen((N, K), 112, 0.05).to(torch.bfloat16)
     bias = _gen((N,), 113)
     gamma = _gen((N,), 114) if with_gamma else None
-    X = _gen((M, N), 115, 5.0) + 7.0  # non-zero row mean: exercises the shifted variance
-    lg, lb = _gen((N,), 116) + 1.0, _gen((N,), 117)
+    X = _gen((M, N), 115, 5.0) + 70.0
     upd = A.float() @ W.float().t() + bias
     Xr = X + (gamma * upd if with_gamma else upd)
-    lnr = torch.nn.functional.layer_norm(Xr, (N,), lg, lb, 1e-6)
-    ln = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
-    sync = torch.zeros(8 * ((M + 255) // 256), dtype=torch.int32, device="cuda")
+    xb = torch.zeros(M, N, dtype=torch.bfloat16, device="cuda")
+    st = torch.full((M, N // 128, 2), float("nan"), device="cuda")
     X0 = X.clone()
-    for _ in range(2):  # second launch reuses the self-resetting counters
+    for _ in range(2):
         X.copy_(X0)
-        ln.zero_()
-        ops.gemm(A, W, bias, X, ops.EPI_RESIDUAL_F32, gamma=gamma, ln_gamma=lg, ln_beta=lb, ln_out=ln, ln_eps=1e-6,
-                 ln_sync=sync)
+        ops.gemm(A, W, bias, X, ops.EPI_RESIDUAL_F32, gamma=gamma, xb_out=xb, stats_out=st)
         assert relerr(X, Xr) < 1e-4
-        assert relerr(ln, lnr) < 8e-3
-        assert int(sync.abs().max()) == 0
+        assert torch.equal(xb, X.to(torch.bfloat16))  # the copy is the rounding of the stored fp32 rows
+        mean, var = _merge_stats(st, N)
+        assert torch.isfinite(st).all()
+        assert (mean - X.mean(dim=1)).abs().max().item() < 1e-3
+        assert relerr(var, X.var(dim=1, unbiased=False)) < 1e-4
+        parts = X.view(M, N // 128, 128)
+        assert (st[:, :, 0] - parts.mean(dim=2)).abs().max().item() < 1e-3
+        assert relerr(st[:, :, 1], ((parts - parts.mean(dim=2, keepdim=True)) ** 2).sum(dim=2)) < 1e-3
+
+
+@pytest.mark.parametrize("M,N,epi", [(256 * 60 + 77, 2304, "bf16"), (256 * 60 + 77, 3072, "gelu"), (300, 2304, "bf16"),
+                                     (300, 3072, "gelu"), (4214, 3072, "gelu"), (128 * 310 + 5, 768, "bf16")])
+def test_gemm_forwarded_layernorm_consumer(M, N, epi):
+    """out = f(Linear(LayerNorm(x))) computed from the UN-normalised bf16 copy of x, its forwarded statistics and the
+    folded weights (engine.pack_ln_linear), against LayerNorm -> Linear in fp32 on the same x (pair and 1-CTA kernels)."""
+    from duoformer_tcga_b200 import engine
+
+    K = 768
+    x = _gen((M, K), 121, 4.0) + _gen((M, 1), 122, 2.0)  # per-row means of the order of the spread
+    lw, lb = _gen((K,), 123, 0.1) + 1.0, _gen((K,), 124, 0.05)
+    W = _gen((N, K), 125, 0.03)
+    bias = _gen((N,), 126, 0.1)
+    ref = torch.nn.functional.layer_norm(x, (K,), lw, lb, 1e-6) @ W.t() + bias
+    if epi == "gelu":
+        ref = torch.nn.functional.gelu(ref)
+    parts = x.view(M, K // 128, 128)
+    pm = parts.mean(dim=2)
+    st = torch.stack([pm, ((parts - pm[:, :, None]) ** 2).sum(dim=2)], dim=2).contiguous()
+    wp, bp, cs = engine.pack_ln_linear(W, bias, lw, lb)
+    out = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    ops.gemm(x.to(torch.bfloat16), wp, bp, out, ops.EPI_GELU_BF16 if epi == "gelu" else ops.EPI_BF16,
+             ln_stats=st, ln_colsum=cs, ln_eps=1e-6)
+    assert relerr(out, ref) < 1.5e-2
+
+
+def test_gemm_statistics_forwarding_chain_matches_layernorm_path():
+    """proj(+residual) -> fc1(+GELU) through the forwarding pair of epilogues equals residual GEMM -> LayerNorm
+    kernel -> fc1 GEMM (the round-1 sequence) within bf16 rounding."""
+    from duoformer_tcga_b200 import engine
+
+    M, D, Hd = 256 * 40 + 13, 768, 3072
+    A = _gen((M, D), 141).to(torch.bfloat16)
+    Wp = _gen((D, D), 142, 0.05).to(torch.bfloat16)
+    bp = _gen((D,), 143)
+    X = _gen((M, D), 144, 3.0)
+    lw, lb = _gen((D,), 145, 0.1) + 1.0, _gen((D,), 146, 0.05)
+    W1 = _gen((Hd, D), 147, 0.03)
+    b1 = _gen((Hd,), 148, 0.1)
+    # round-1 sequence
+    X1 = X.clone()
+    ops.gemm(A, Wp, bp, X1, ops.EPI_RESIDUAL_F32)
+    hn = torch.empty(M, D, dtype=torch.bfloat16, device="cuda")
+    ops.layernorm(X1, lw, lb, hn, 1e-6)
+    h1 = torch.empty(M, Hd, dtype=torch.bfloat16, device="cuda")
+    ops.gemm(hn, W1.to(torch.bfloat16), b1, h1, ops.EPI_GELU_BF16)
+    # forwarding sequence
+    X2 = X.clone()
+    xb = torch.empty(M, D, dtype=torch.bfloat16, device="cuda")
+    st = torch.empty(M, D // 128, 2, device="cuda")
+    ops.gemm(A, Wp, bp, X2, ops.EPI_RESIDUAL_F32, xb_out=xb, stats_out=st)
+    w, b, cs = engine.pack_ln_linear(W1, b1, lw, lb)
+    h2 = torch.empty(M, Hd, dtype=torch.bfloat16, device="cuda")
+    ops.gemm(xb, w, b, h2, ops.EPI_GELU_BF16, ln_stats=st, ln_colsum=cs, ln_eps=1e-6)
+    assert relerr(X2, X1) < 1e-5
+    ref = torch.nn.functional.gelu(torch.nn.functional.layer_norm(X1, (D,), lw, lb, 1e-6) @ W1.t() + b1)
+    e1, e2 = relerr(h1, ref), relerr(h2, ref)
+    assert e2 < 1.5e-2 and e2 < 2.0 * e1 + 1e-3, (e1, e2)
+
+
+def test_gemm_forwarding_argument_checks():
+    A = torch.zeros(256, 768, dtype=torch.bfloat16, device="cuda")
+    W = torch.zeros(768, 768, dtype=torch.bfloat16, device="cuda")
+    X = torch.zeros(256, 768, device="cuda")
+    xb = torch.zeros(256, 768, dtype=torch.bfloat16, device="cuda")
+    st = torch.zeros(256, 6, 2, device="cuda")
+    with pytest.raises(RuntimeError, match="statistics forwarding"):  # only with the residual epilogue
+        ops.gemm(A, W, None, xb, ops.EPI_BF16, xb_out=xb, stats_out=st)
+    with pytest.raises(RuntimeError, match="forwarded LayerNorm"):  # not with the residual epilogue
+        ops.gemm(A, W, None, X, ops.EPI_RESIDUAL_F32, ln_stats=st, ln_colsum=torch.zeros(768, device="cuda"))
 
 
 @pytest.mark.parametrize("M,N,K", [(300, 768, 256), (256 * 150 + 3, 768, 512)])

@@ -85,24 +85,42 @@ def main():
         emit("cublas_" + name, ms2, best2, flops=2.0 * M * N * K)
         del A, W, out
 
-    # residual GEMM + LayerNorm: fused (LN warps inside the GEMM) vs the two launches
-    if not a.only or "fusedln" in a.only:
-        for name, K in (("proj", D), ("fc2", 4 * D)):
+    # LayerNorm statistics forwarding: residual GEMM (+ bf16 copy + statistics) -> consumer GEMM (LayerNorm in the
+    # epilogue) against the three-launch sequence residual GEMM, LayerNorm, GEMM
+    if not a.only or "fwd" in a.only:
+        from duoformer_tcga_b200 import engine
+        st = torch.empty(M, D // 128, 2, device=dev)
+        for name, K, N2, epi2 in (("proj", D, 4 * D, ops.EPI_GELU_BF16), ("fc2", 4 * D, 3 * D, ops.EPI_BF16)):
             A = (torch.randn(M, K, device=dev) * 0.5).to(torch.bfloat16)
             W = (torch.randn(D, K, device=dev) * 0.02).to(torch.bfloat16)
             bias = torch.zeros(D, device=dev)
-            sync = torch.zeros(8 * ((M + 255) // 256), dtype=torch.int32, device=dev)
-            ms, best = timeit(lambda: ops.gemm(A, W, bias, x, ops.EPI_RESIDUAL_F32, ln_gamma=g, ln_beta=b, ln_out=hn,
-                                               ln_sync=sync))
-            assert int(sync.abs().max()) == 0, "panel counters must be left zero"
-            emit(f"gemm_{name}_residual_fusedln", ms, best, flops=2.0 * M * D * K)
+            W2 = torch.randn(N2, D, device=dev) * 0.02
+            b2 = torch.zeros(N2, device=dev)
+            w2p, b2p, cs = engine.pack_ln_linear(W2, b2, g, b)
+            W2b = W2.to(torch.bfloat16)
+            out2 = torch.empty(M, N2, dtype=torch.bfloat16, device=dev)
+            ms, best = timeit(lambda: ops.gemm(A, W, bias, x, ops.EPI_RESIDUAL_F32, xb_out=hn, stats_out=st))
+            emit(f"gemm_{name}_residual_fwd", ms, best, flops=2.0 * M * D * K, nbytes=M * (K * 2 + D * 10))
+            ms, best = timeit(lambda: ops.gemm(A, W, bias, x, ops.EPI_RESIDUAL_F32))
+            emit(f"gemm_{name}_residual", ms, best, flops=2.0 * M * D * K, nbytes=M * (K * 2 + D * 8))
+            ms, best = timeit(lambda: ops.gemm(hn, w2p, b2p, out2, epi2, ln_stats=st, ln_colsum=cs))
+            emit(f"gemm_after_{name}_ln_applied", ms, best, flops=2.0 * M * N2 * D)
+            ms, best = timeit(lambda: ops.gemm(hn, W2b, b2, out2, epi2))
+            emit(f"gemm_after_{name}_plain", ms, best, flops=2.0 * M * N2 * D)
 
-            def two():
+            def fwd_seq():
+                ops.gemm(A, W, bias, x, ops.EPI_RESIDUAL_F32, xb_out=hn, stats_out=st)
+                ops.gemm(hn, w2p, b2p, out2, epi2, ln_stats=st, ln_colsum=cs)
+
+            def ln_seq():
                 ops.gemm(A, W, bias, x, ops.EPI_RESIDUAL_F32)
                 ops.layernorm(x, g, b, hn, 1e-6)
-            ms, best = timeit(two)
-            emit(f"gemm_{name}_residual_then_ln", ms, best, flops=2.0 * M * D * K)
-            del A, W
+                ops.gemm(hn, W2b, b2, out2, epi2)
+            ms, best = timeit(fwd_seq)
+            emit(f"seq_{name}_forwarding", ms, best, flops=2.0 * M * D * (K + N2))
+            ms, best = timeit(ln_seq)
+            emit(f"seq_{name}_layernorm_launch", ms, best, flops=2.0 * M * D * (K + N2))
+            del A, W, W2, W2b, w2p, out2
 
     # token scatter GEMMs (projection of one trunk stage straight into token rows + positional add)
     if not a.only or "scatter" in a.only or "gemm" in a.only:
