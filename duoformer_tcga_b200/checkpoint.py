@@ -134,15 +134,26 @@ def is_dead_key(key: str) -> bool:
     return any(re.search(p, key) for p in DEAD_KEY_PATTERNS)
 
 
-def load_checkpoint(model: nn.Module, source: Union[str, dict, nn.Module], strict: bool = True
-                    ) -> Tuple[Iterable[str], Iterable[str]]:
+def load_checkpoint(model: nn.Module, source: Union[str, dict, nn.Module], strict: bool = True,
+                    trust_pickle: bool = False) -> Tuple[Iterable[str], Iterable[str]]:
     """Load reference weights into a duoformer_tcga_b200 model.
+
+    A path is first read with torch.load(weights_only=True) (state_dict files: tensors only, no code execution).
+    Whole-module pickles — what the reference's training script saves (main_toy.py:170-183) — execute arbitrary
+    pickle code on load and are only read when the caller passes trust_pickle=True.
 
     Returns (missing, unexpected) AFTER discounting the reference's dead keys; with strict=True a
     RuntimeError is raised if either list is non-empty or a shape differs."""
     if isinstance(source, str):
-        with reference_unpickle_stubs():
-            source = torch.load(source, map_location="cpu", weights_only=False)
+        path = source
+        try:
+            source = torch.load(path, map_location="cpu", weights_only=True)
+        except Exception as e:  # not a plain tensor container
+            if not trust_pickle:
+                raise RuntimeError(f"{path} is not a tensors-only checkpoint ({type(e).__name__}); a whole-module pickle "
+                                   "runs arbitrary code when loaded — pass trust_pickle=True if you trust its origin") from e
+            with reference_unpickle_stubs():
+                source = torch.load(path, map_location="cpu", weights_only=False)
     sd = normalise_keys(extract_state_dict(source), model)
     own = model.state_dict()
     bad_shape = [k for k, v in sd.items() if k in own and tuple(own[k].shape) != tuple(v.shape)]

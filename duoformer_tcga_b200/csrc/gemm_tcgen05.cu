@@ -52,6 +52,7 @@ constexpr int kEpiResidualTma = 100;  // DUO_EPI_RESIDUAL_F32: TMA reduce-add in
 constexpr int kEpiResidualFwd = 101;  // residual update + statistics forwarding (pair kernel): X is TMA-loaded,
                                       // updated in shared memory and stored back together with its bf16 copy and
                                       // per-row LayerNorm partial statistics (duo_gemm_args.xb_out / stats_out)
+constexpr int kEpiResidualFwdLongK = 104;  // same, tuned for long K (fc2): one more operand stage, shallower X ring
 constexpr int kEpiBf16Ln = 102;       // DUO_EPI_BF16 with the forwarded LayerNorm applied in the epilogue
 constexpr int kEpiGeluBf16Ln = 103;   // DUO_EPI_GELU_BF16 with the forwarded LayerNorm applied in the epilogue
 
@@ -63,7 +64,12 @@ struct EpiTraits {
   static constexpr bool kGelu = (EPI == DUO_EPI_GELU_BF16 || EPI == kEpiGeluBf16Ln);
   static constexpr bool kStagedBf16 = (EPI == DUO_EPI_BF16 || EPI == DUO_EPI_GELU_BF16 || kLnApply);
   static constexpr bool kStagedF32 = (EPI == kEpiResidualTma);
-  static constexpr bool kFwd = (EPI == kEpiResidualFwd);
+  static constexpr bool kFwd = (EPI == kEpiResidualFwd || EPI == kEpiResidualFwdLongK);
+  // X chunks in flight per epilogue warp (ring of in-place slots).  Short K (proj): the tile's MMAs take ~6 us and
+  // its 128 KB of X per CTA must stream in meanwhile -> 3 chunks ahead per warp.  Long K (fc2): ~20 us per tile,
+  // one chunk ahead is plenty and the shared memory buys a fifth operand stage instead.
+  static constexpr int kFwdSlots = (EPI == kEpiResidualFwd) ? 4 : (EPI == kEpiResidualFwdLongK ? 2 : 0);
+  static constexpr int kFwdStages = (EPI == kEpiResidualFwd) ? 4 : 5;
   static constexpr bool kStaged = kStagedBf16 || kStagedF32 || kFwd;
 };
 
@@ -107,26 +113,38 @@ struct GemmParams {
 // so the epilogue computes  ln_a * acc + (ln_c * colsum[n] + bias'[n])  with ln_a = rstd, ln_c = -mean * rstd.
 // The (mean, M2) pairs of the row's K / 128 column parts (written by the producing residual GEMM from the
 // fp32 row) are merged with Chan's formula.
-__device__ __forceinline__ void ln_row_coeffs(const GemmParams& p, int64_t row, bool valid, float& ln_a, float& ln_c) {
-  ln_a = 1.f;
-  ln_c = 0.f;
-  if (!valid) return;
+constexpr int kMaxStatParts = 8;  // K <= 1024
+struct LnRowStats {
+  float2 s[kMaxStatParts];
+};
+// Issue the loads of one row's partial statistics (done one tile ahead: the latency of these L2 / DRAM reads
+// hides behind the epilogue of the current tile).
+__device__ __forceinline__ void ln_stats_load(const GemmParams& p, int64_t row, LnRowStats& st) {
   const int parts = p.K / kStatCols;
-  const float2* st = p.ln_stats + row * parts;
+  const bool valid = row < p.M;
+  const float2* src = p.ln_stats + row * parts;
+#pragma unroll
+  for (int i = 0; i < kMaxStatParts; ++i)
+    st.s[i] = (valid && i < parts) ? __ldg(src + i) : make_float2(0.f, 0.f);
+}
+__device__ __forceinline__ void ln_stats_finish(const GemmParams& p, const LnRowStats& st, float& ln_a, float& ln_c) {
+  const int parts = p.K / kStatCols;
   float mean = 0.f, m2 = 0.f;
-  for (int i = 0; i < parts; ++i) mean += __ldg(st + i).x;
+#pragma unroll
+  for (int i = 0; i < kMaxStatParts; ++i) mean += st.s[i].x;  // absent parts are zero
   mean *= 1.0f / static_cast<float>(parts);
-  for (int i = 0; i < parts; ++i) {
-    const float2 s = __ldg(st + i);
-    const float d = s.x - mean;
-    m2 += s.y + static_cast<float>(kStatCols) * d * d;
+#pragma unroll
+  for (int i = 0; i < kMaxStatParts; ++i) {
+    if (i < parts) {
+      const float d = st.s[i].x - mean;
+      m2 += st.s[i].y + static_cast<float>(kStatCols) * d * d;
+    }
   }
   const float rstd = rsqrtf(m2 / static_cast<float>(p.K) + p.ln_eps);
   ln_a = rstd;
   ln_c = -mean * rstd;
 }
 
-// acc[32] (fp32 bits) -> f[32] = acc + bias (optionally GELU'd / scaled by LayerScale gamma)
 // Bias slice [col, col+32) -> registers; issued BEFORE waiting on the TMEM load so both latencies overlap.
 __device__ __forceinline__ void epilogue_bias_load(const GemmParams& p, int col, float4 (&b)[8]) {
   if (p.bias != nullptr) {
@@ -587,13 +605,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     uint32_t stg_buf = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    LnRowStats ln_next;  // forwarded LayerNorm: the row statistics of the NEXT tile, loaded one tile ahead
+    if constexpr (ET::kLnApply) {
+      if (static_cast<int64_t>(blockIdx.x) < num_tiles)
+        ln_stats_load(p, static_cast<int64_t>(blockIdx.x / p.num_n_blocks) * kBlockM + quarter * 32 + lane, ln_next);
+    }
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = static_cast<int>(tile / p.num_n_blocks);
       const int n_blk = static_cast<int>(tile - static_cast<int64_t>(m_blk) * p.num_n_blocks);
       const int row0 = m_blk * kBlockM + quarter * 32;  // first row of this warp's slab
       const int n0 = n_blk * BLOCK_N;
       float ln_a = 1.f, ln_c = 0.f;
-      if constexpr (ET::kLnApply) ln_row_coeffs(p, static_cast<int64_t>(row0) + lane, row0 + lane < p.M, ln_a, ln_c);
+      if constexpr (ET::kLnApply) {
+        ln_stats_finish(p, ln_next, ln_a, ln_c);
+        const int64_t nt = tile + gridDim.x;
+        if (nt < num_tiles) ln_stats_load(p, (nt / p.num_n_blocks) * kBlockM + quarter * 32 + lane, ln_next);
+      }
       ptx::mbar_wait(tmem_full_bar(acc), acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr =
@@ -632,17 +659,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 // the "slot free" / "accumulator full" arrivals to both CTAs; each CTA runs its own epilogue.
 // ===========================================================================================
 constexpr int kPairBlockN = 256;
-// Statistics-forwarding residual epilogue (kEpiResidualFwd): per epilogue warp a ring of kFwdSlots
+// Statistics-forwarding residual epilogue (kEpiResidualFwd*): per epilogue warp a ring of kFwdSlots
 // slots, each one 32 x 32 fp32 chunk of X (TMA-loaded, updated in place, TMA-stored) plus its bf16 copy.
-constexpr int kFwdSlots = 4;
 constexpr uint32_t kFwdXBytes = 32 * 128;  // 32 rows x 32 fp32, SWIZZLE_128B
 constexpr uint32_t kFwdBBytes = 32 * 64;   // 32 rows x 32 bf16, SWIZZLE_64B
 // EPI_WARPS epilogue warps: 4 (one per TMEM lane quarter, all 256 columns, 6 operand stages) or 8
 // (two per quarter, 128 columns each, 5 operand stages — used when the epilogue is heavy: GELU,
 // token scatter; both only occur with short K).  Staging is double-buffered per warp either way.
-template <int EPI_WARPS, bool FWD = false>
+template <int EPI, int EPI_WARPS>
 struct PairCfg {
-  static constexpr int kStages = FWD ? 4 : (EPI_WARPS == 8 ? 5 : 6);
+  using ET = EpiTraits<EPI>;
+  static constexpr bool FWD = ET::kFwd;
+  static constexpr int kFwdSlots = ET::kFwdSlots;
+  static constexpr int kStages = FWD ? ET::kFwdStages : (EPI_WARPS == 8 ? 5 : 6);
   static constexpr int kThreads = 64 + 32 * EPI_WARPS;
   static constexpr int kStagingBufs = 2;
   static constexpr uint32_t kABytes = kBlockM * kBlockK * 2;          // 16 KB (this CTA's 128 rows)
@@ -676,16 +705,18 @@ __device__ __forceinline__ void ld_shared_v4(uint32_t addr, float& a, float& b, 
 
 template <int EPI, int EPI_WARPS>
 __global__ void __cluster_dims__(2, 1, 1)
-__launch_bounds__(PairCfg<EPI_WARPS, EPI == kEpiResidualFwd>::kThreads, 1)
+__launch_bounds__(PairCfg<EPI, EPI_WARPS>::kThreads, 1)
 gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
                          const __grid_constant__ CUtensorMap tmap_b,
                          const __grid_constant__ CUtensorMap tmap_out,
                          const __grid_constant__ CUtensorMap tmap_aux,  // kEpiResidualFwd: the bf16 copy
                          const GemmParams p) {
-  using C = PairCfg<EPI_WARPS, EPI == kEpiResidualFwd>;
+  using C = PairCfg<EPI, EPI_WARPS>;
   using ET = EpiTraits<EPI>;
   constexpr int kStages = C::kStages;
   constexpr int BLOCK_N = kPairBlockN;
+  constexpr int kFwdSlots = C::kFwdSlots;
+  (void)kFwdSlots;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -845,7 +876,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
       };
       if (lane == 0) {
 #pragma unroll
-        for (uint32_t i = 0; i + 1 < kFwdSlots; ++i) issue_load(i);
+        for (int i = 0; i + 1 < kFwdSlots; ++i) issue_load(static_cast<uint32_t>(i));
       }
       uint32_t g = 0;
       const uint32_t sw128 = static_cast<uint32_t>(lane & 7);         // 16-byte chunk XOR, 128 B rows
@@ -952,11 +983,22 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
     } else {
       const uint32_t stg = staging_base + static_cast<uint32_t>(warp_idx) * (C::kStagingBufs * 32u * 128u);
       uint32_t stg_buf = 0;
+      LnRowStats ln_next;  // forwarded LayerNorm: the row statistics of the NEXT tile, loaded one tile ahead
+      auto ln_prefetch = [&](int64_t it) {
+        int mb, nb;
+        if (pair_tile(it, pair_idx, pair_stride, p.num_m_blocks, p.num_n_blocks, mb, nb))
+          ln_stats_load(p, static_cast<int64_t>(mb) * (2 * kBlockM) + static_cast<int>(cta_rank) * kBlockM + quarter * 32 + lane,
+                        ln_next);
+      };
+      if constexpr (ET::kLnApply) ln_prefetch(0);
       for (int64_t it = 0; pair_tile(it, pair_idx, pair_stride, p.num_m_blocks, p.num_n_blocks, m_blk, n_blk); ++it) {
         const int row0 = m_blk * (2 * kBlockM) + static_cast<int>(cta_rank) * kBlockM + quarter * 32;
         const int n0 = n_blk * BLOCK_N;
         float ln_a = 1.f, ln_c = 0.f;
-        if constexpr (ET::kLnApply) ln_row_coeffs(p, static_cast<int64_t>(row0) + lane, row0 + lane < p.M, ln_a, ln_c);
+        if constexpr (ET::kLnApply) {
+          ln_stats_finish(p, ln_next, ln_a, ln_c);
+          ln_prefetch(it + 1);
+        }
         ptx::mbar_wait(tmem_full_bar(acc), acc_phase);
         ptx::tc_fence_after();
         const uint32_t taddr =
@@ -1098,7 +1140,7 @@ int dispatch_epi(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap
 template <int EPI, int EPI_WARPS>
 int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tx,
                 const GemmParams& p, cudaStream_t st) {
-  using C = PairCfg<EPI_WARPS, EPI == kEpiResidualFwd>;
+  using C = PairCfg<EPI, EPI_WARPS>;
   static uint64_t configured = 0;  // per device
   auto kfn = gemm_tcgen05_pair_kernel<EPI, EPI_WARPS>;
   if (first_use_on_device(configured))
@@ -1123,6 +1165,7 @@ int dispatch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
     case kEpiGeluBf16Ln: return launch_pair<kEpiGeluBf16Ln, 8>(ta, tb, to, tx, p, st);
     case kEpiResidualTma: return launch_pair<kEpiResidualTma, 4>(ta, tb, to, tx, p, st);
     case kEpiResidualFwd: return launch_pair<kEpiResidualFwd, 4>(ta, tb, to, tx, p, st);
+    case kEpiResidualFwdLongK: return launch_pair<kEpiResidualFwdLongK, 4>(ta, tb, to, tx, p, st);
     case DUO_EPI_SCATTER_F32: return launch_pair<DUO_EPI_SCATTER_F32, 8>(ta, tb, to, tx, p, st);
     case DUO_EPI_F32: return launch_pair<DUO_EPI_F32, 4>(ta, tb, to, tx, p, st);
     case DUO_EPI_SPLIT_BF16: return launch_pair<DUO_EPI_SPLIT_BF16, 4>(ta, tb, to, tx, p, st);
@@ -1179,7 +1222,10 @@ extern "C" int duo_gemm(const duo_gemm_args* a, duo_stream_t stream) {
                   "duo_gemm: ln_stats must be 8-byte aligned, ln_colsum 16-byte aligned");
     epi = epi == DUO_EPI_BF16 ? kEpiBf16Ln : kEpiGeluBf16Ln;
   }
-  if (epi == DUO_EPI_RESIDUAL_F32) epi = fwd ? kEpiResidualFwd : kEpiResidualTma;
+#ifndef DUO_FWD_LONGK_FROM
+#define DUO_FWD_LONGK_FROM 1536  // K at which the long-K forwarding variant takes over (tools/bench_kernels.py --lib sweeps it)
+#endif
+  if (epi == DUO_EPI_RESIDUAL_F32) epi = !fwd ? kEpiResidualTma : (a->K >= DUO_FWD_LONGK_FROM ? kEpiResidualFwdLongK : kEpiResidualFwd);
 
   // Tile shape: CTA-pair 256x256 when N allows and there are at least two waves of pair tiles;
   // else 128 x 256 (enough tiles to fill the machine) or 128 x 128.  The forwarding epilogue exists in the
@@ -1201,7 +1247,7 @@ extern "C" int duo_gemm(const duo_gemm_args* a, duo_stream_t stream) {
   if (rc != DUO_OK) return rc;
   if (epi == DUO_EPI_BF16 || epi == DUO_EPI_GELU_BF16 || epi == kEpiBf16Ln || epi == kEpiGeluBf16Ln) {
     rc = make_tmap(&to, a->out, a->M, a->N, a->ldo, 32, 2);
-  } else if (epi == kEpiResidualTma || epi == kEpiResidualFwd) {
+  } else if (epi == kEpiResidualTma || fwd) {
     rc = make_tmap(&to, a->out, a->M, a->N, a->ldo, 32, 4);
   } else {
     to = ta;  // unused by the direct-store epilogues

@@ -18,7 +18,7 @@ from .projection_head import (Channel_Projector_All, Channel_Projector_layer1, C
                               Channel_Projector_layer3, Projection)
 from .scale_attention import _check_eval
 from .channel_branch import ChannelBranch
-from .token_builder import TokenBuilder, TrunkRunner
+from .token_builder import TokenBuilder, TrunkRunner, _unscaled
 
 
 class MyModel(nn.Module):
@@ -82,7 +82,11 @@ class MyModel(nn.Module):
 
     @torch.no_grad()
     def get_features(self, x):
-        f = self._trunk_runner.features(self.resnet_projector, x, self.precision, False)
+        """Stage feature maps keyed '0'..'3' (model_wo_extra_params.py:214-224 / model.py:213-223), unscaled."""
+        tr = self._trunk_runner
+        f = tr.features(self.resnet_projector, x, self.precision, False)
+        if tr.act_scale != 1.0:  # the fp16 range guard engaged: hand back true magnitudes
+            f = {k: v.float() / tr.act_scale for k, v in f.items()}
         return {str(k): v for k, v in f.items()}
 
     @torch.no_grad()
@@ -111,10 +115,11 @@ class MyModel(nn.Module):
     def build_tokens(self, x: torch.Tensor) -> torch.Tensor:
         if self.name != "scaleformer":
             raise NotImplementedError("only model_ver='scaleformer' is on the DuoFormer path")
-        feats = self._trunk_runner.features(self.resnet_projector, x, self.precision, False)
-        tok = self.channel_branch(feats)
+        tr = self._trunk_runner
+        feats = tr.features(self.resnet_projector, x, self.precision, False)
+        tok = self.channel_branch(_unscaled(feats, tr.act_scale))
         return self._token_builder.build(feats, self.projection, self.num_layers, tok,
-                                         self.vision_transformer.pos_scale_table(), self.precision)
+                                         self.vision_transformer.pos_scale_table(), self.precision, tr.act_scale)
 
     @torch.no_grad()
     def forward(self, x: torch.Tensor) -> torch.Tensor:

@@ -18,7 +18,7 @@ from .projection_head import (Channel_Projector_All, Channel_Projector_layer1, C
 from .resnet50ssl import resnet50FeatureExtractor
 from .scale_attention import MultiscaleFormer, _check_eval
 from .channel_branch import ChannelBranch
-from .token_builder import TokenBuilder, TrunkRunner
+from .token_builder import TokenBuilder, TrunkRunner, _unscaled
 
 
 def _tv_resnet(name: str, pretrained: bool) -> nn.Module:
@@ -113,8 +113,11 @@ class MyModel_no_extra_params(nn.Module):
     # ---- reference API ------------------------------------------------------------------------
     @torch.no_grad()
     def get_features(self, x):
-        """Stage feature maps keyed '0'..'3' (model_wo_extra_params.py:214-224)."""
-        f = self._trunk_runner.features(self.resnet_projector, x, self.precision, self.backbone == "r50_Swav")
+        """Stage feature maps keyed '0'..'3' (model_wo_extra_params.py:214-224 / model.py:213-223), unscaled."""
+        tr = self._trunk_runner
+        f = tr.features(self.resnet_projector, x, self.precision, self.backbone == "r50_Swav")
+        if tr.act_scale != 1.0:  # the fp16 range guard engaged: hand back true magnitudes
+            f = {k: v.float() / tr.act_scale for k, v in f.items()}
         return {str(k): v for k, v in f.items()}
 
     @torch.no_grad()
@@ -137,14 +140,15 @@ class MyModel_no_extra_params(nn.Module):
     @torch.no_grad()
     def build_tokens(self, x: torch.Tensor) -> torch.Tensor:
         """Image batch -> fp32 tokens [B, P, S, D] including pos_embed_for_scale."""
-        feats = self._trunk_runner.features(self.resnet_projector, x, self.precision, self.backbone == "r50_Swav")
+        tr = self._trunk_runner
+        feats = tr.features(self.resnet_projector, x, self.precision, self.backbone == "r50_Swav")
         vt = self.vision_transformer
         if self.scale_token == "channel":
-            tok = self.channel_branch(feats)
+            tok = self.channel_branch(_unscaled(feats, tr.act_scale))
         else:
             tok = self.channel_token.detach().reshape(-1).to(torch.float32)
         return self._token_builder.build(feats, self.projection, self.num_layers, tok, vt.pos_scale_table(),
-                                         self.precision)
+                                         self.precision, tr.act_scale)
 
     @torch.no_grad()
     def forward(self, x: torch.Tensor) -> torch.Tensor:

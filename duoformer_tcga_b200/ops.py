@@ -27,9 +27,24 @@ from ._lib import (  # noqa: F401  (re-exported)
 )
 
 
-# Optional per-launch CUDA-event timing of the GEMM kernel (bench.py's live roofline): when a
-# list is installed here, every gemm() appends (start_event, end_event, flops, tag).
-GEMM_PROFILE = None
+# Optional per-launch CUDA-event timing (bench.py's profiled pass): when a list is installed here, gemm(),
+# layernorm() and group_attention() append (start_event, end_event, kind, algorithmic flops, algorithmic bytes, tag).
+PROFILE = None
+
+
+def _prof_begin():
+    if PROFILE is None:
+        return None
+    e0 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    return e0
+
+
+def _prof_end(e0, kind, flops, nbytes, tag):
+    if e0 is not None and PROFILE is not None:
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        PROFILE.append((e0, e1, kind, float(flops), float(nbytes), tag))
 
 
 def _stream() -> int:
@@ -134,14 +149,14 @@ def gemm(
         assert bias.dtype == torch.float32 and bias.numel() == N
     if row_map is not None:
         assert row_map.dtype == torch.int32
-    prof = GEMM_PROFILE
-    if prof is not None:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+    e0 = _prof_begin()
     _lib.check(_lib.load().duo_gemm(ctypes.byref(a), _stream()), "duo_gemm")
-    if prof is not None:
-        e1.record()
-        prof.append((e0, e1, 2.0 * M * N * K * (3 if split3 == 1 else (2 if split3 == 2 else 1)), f"{N}x{K}:epi{epilogue}"))
+    if e0 is not None:
+        passes = 3 if split3 == 1 else (2 if split3 == 2 else 1)
+        out_bytes = {EPI_BF16: 2, EPI_GELU_BF16: 2, EPI_RESIDUAL_F32: 8, EPI_SCATTER_F32: 4, EPI_F32: 4, EPI_SPLIT_BF16: 4,
+                     EPI_GELU_SPLIT_BF16: 4}[epilogue] + (2 if xb_out is not None else 0)
+        tag = f"{N}x{K}:epi{epilogue}" + ("+fwd" if xb_out is not None else "") + ("+ln" if ln_stats is not None else "")
+        _prof_end(e0, "gemm", 2.0 * M * N * K * passes, M * (A.shape[1] * 2 + N * out_bytes) + W.numel() * 2, tag)
     return out
 
 
@@ -158,10 +173,12 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out: tor
         rows, ldx = x.shape[0], x.stride(0)
     kind = _act_kind(out, D)
     assert kind in (ACT_BF16, ACT_SPLIT)
+    e0 = _prof_begin()
     _lib.check(
         _lib.load().duo_layernorm(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(out), kind, rows, D, ldx, float(eps), _stream()),
         "duo_layernorm",
     )
+    _prof_end(e0, "layernorm", 0.0, rows * (D * 4 + out.shape[-1] * 2), f"layernorm:{rows}x{D}")
     return out
 
 
@@ -182,6 +199,7 @@ def group_attention(
         assert qkv.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and out.shape[-1] == 2 * D
     in_kind = ACT_SPLIT if split_in else (ACT_F32 if qkv.dtype == torch.float32 else ACT_BF16)
     out_kind = _act_kind(out, D)
+    e0 = _prof_begin()
     _lib.check(
         _lib.load().duo_group_attention(
             _ptr(qkv), in_kind, _ptr(out), out_kind, rows // S, S, num_heads, float(scale), algo,
@@ -189,6 +207,11 @@ def group_attention(
         ),
         "duo_group_attention",
     )
+    if e0 is not None:
+        qr = q_rows if q_rows > 0 else S
+        in_bytes = rows * qkv.shape[-1] * qkv.element_size() * (1.0 if qr == S else (2.0 + qr / S) / 3.0)
+        _prof_end(e0, "attention", 4.0 * (rows // S) * qr * S * D, in_bytes + out.numel() * out.element_size(),
+                  f"attention:S{S}:q{qr}:in{in_kind}")
     return out
 
 

@@ -106,19 +106,28 @@ class HostPipeline:
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self._bufs = [None, None]
         self._consumed = [None, None]  # event: the forward that read buffer k has been enqueued and finished
+        self._compute: Optional[torch.cuda.Stream] = None  # stream the forwards run on (set by run())
 
     def _stage(self, k: int, host: torch.Tensor):
         """Enqueue the copy of `host` into device buffer k on the copy stream; returns (tensor, ready event)."""
         buf = self._bufs[k]
-        if buf is None or buf.shape != host.shape or buf.dtype != host.dtype:
-            buf = torch.empty(host.shape, dtype=host.dtype, device=self.device)
-            self._bufs[k] = buf
+        fresh = buf is None or buf.shape != host.shape or buf.dtype != host.dtype
         with torch.cuda.stream(self.copy_stream):
-            if self._consumed[k] is not None:
+            if fresh:
+                # A new device buffer may reuse a block the caching allocator just took back from the compute
+                # stream (activations of the forward still in flight): allocate it on the copy stream's pool and let
+                # the copy wait for everything enqueued on the compute stream so far.
+                fence = torch.cuda.Event()
+                fence.record(self._compute)
+                self.copy_stream.wait_event(fence)
+                buf = torch.empty(host.shape, dtype=host.dtype, device=self.device)
+                self._bufs[k] = buf
+            if self._consumed[k] is not None and not fresh:
                 self.copy_stream.wait_event(self._consumed[k])  # the previous user of this buffer is done
             buf.copy_(host, non_blocking=True)
             ready = torch.cuda.Event()
             ready.record(self.copy_stream)
+        buf.record_stream(self._compute)  # read by kernels of the compute stream
         return buf, ready
 
     @torch.no_grad()
@@ -128,8 +137,9 @@ class HostPipeline:
         if first is None:
             return
         k = 0
-        staged = self._stage(k, first)
         compute = torch.cuda.current_stream(self.device)
+        self._compute = compute
+        staged = self._stage(k, first)
         pending = None  # (pinned host logits, event) of the previous batch
         while staged is not None:
             x, ready = staged

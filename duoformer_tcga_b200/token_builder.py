@@ -108,62 +108,111 @@ def _fused_trunk_forward(t: nn.Module, x: torch.Tensor, by_scale: bool) -> Dict[
     return feats
 
 
+# fp16 range guard of the trunk (bf16 mode).  The BN-folded trunk is positively homogeneous once its biases are
+# scaled with the input (convolution, ReLU, max-pool and the residual add all commute with a positive factor), so
+# running it on alpha * x with alpha * bias yields alpha * (every activation) EXACTLY for a power of two alpha.
+# alpha is chosen once per weight set from the largest activation magnitude of a bf16 calibration pass (bf16 has
+# fp32's range) so that it lands near 2^10 — a factor 64 below the fp16 maximum 65504 — and 1 / alpha is folded into
+# the 1x1 projection weights of the token builder.  alpha == 1 (every activation <= 2^12, the usual case) leaves the
+# path bit-identical to an unguarded one.
+_FP16_SAFE_MAX = 4096.0   # no rescaling below this calibration maximum
+_FP16_TARGET_MAX = 1024.0  # rescaled activations peak near this value
+
+
 class TrunkRunner:
-    """Runs the torch/cuDNN ResNet trunk in the precision of the path (bf16 channels-last copy
-    of the fp32 master weights, re-made when they change) and returns the tapped stage maps."""
+    """Runs the torch/cuDNN ResNet trunk in the precision of the path (fp16 channels-last BN-folded copy of the fp32
+    master weights, re-made when they change) and returns the tapped stage maps, scaled by `act_scale`."""
 
     def __init__(self):
         self._sig = None
         self._trunk: Optional[nn.Module] = None
-        self.fused_ok: Optional[bool] = None  # None = not tried yet
+        self._verified = False  # fused cuDNN path checked against the plain module path for this weight set
         # dtype of the cuDNN trunk in bf16 mode: "fp16" (default: same speed as bf16, 11-bit mantissa —
         # the ~50 stacked convolutions otherwise contribute ~1e-2 of the 2e-2 bf16 error budget before
         # the first transformer block), "bf16", or "fp32"
         self.trunk_dtype = "fp16"
+        # power-of-two factor the stage maps are scaled by (fp16 trunk only; 1.0 otherwise); set by calibration on
+        # the first forward of a weight set, or pinned by the caller through `act_scale_override`
+        self.act_scale = 1.0
+        self.act_scale_override: Optional[float] = None
+        self.calibration_max: Optional[float] = None
 
     def _dtype(self, precision: str) -> torch.dtype:
         if precision == "fp32":
             return torch.float32
         return {"fp16": torch.float16, "bf16": torch.bfloat16, "fp32": torch.float32}[self.trunk_dtype]
 
-    def _packed_trunk(self, trunk: nn.Module, precision: str) -> nn.Module:
+    @staticmethod
+    def _calibrate(folded_fp32: nn.Module, x: torch.Tensor, by_scale: bool) -> float:
+        """Largest |activation| any convolution of the BN-folded trunk produces for (a sample of) x, measured in bf16."""
+        t = copy.deepcopy(folded_fp32).to(dtype=torch.bfloat16, memory_format=torch.channels_last)
+        peaks: List[torch.Tensor] = []
+        hooks = [m.register_forward_hook(lambda _m, _i, o: peaks.append(o.detach().abs().amax().float()))
+                 for m in t.modules() if isinstance(m, nn.Conv2d)]
+        xs = x[:16].to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        TrunkRunner._plain_forward(t, xs, by_scale)
+        for h in hooks:
+            h.remove()
+        return float(torch.stack(peaks).max().item())
+
+    def _packed_trunk(self, trunk: nn.Module, precision: str, x: torch.Tensor, by_scale: bool) -> nn.Module:
         dt = self._dtype(precision)
-        sig = engine.param_signature(trunk, precision + str(dt))
+        sig = engine.param_signature(trunk, precision + str(dt) + str(self.act_scale_override))
         if self._trunk is None or self._sig != sig:
             t = copy.deepcopy(trunk).eval().float()
+            scale = 1.0
             if dt != torch.float32:
                 _fold_batchnorm_(t)  # eval-mode BN -> scale/shift of the preceding conv (fp32, before the cast)
+            if dt == torch.float16:
+                if self.act_scale_override is not None:
+                    scale = float(self.act_scale_override)
+                else:
+                    self.calibration_max = self._calibrate(t, x, by_scale)
+                    if not (self.calibration_max < float("inf")):
+                        raise RuntimeError("trunk calibration: non-finite activations — check the input / checkpoint")
+                    if self.calibration_max > _FP16_SAFE_MAX:
+                        import math
+
+                        scale = 2.0 ** -math.ceil(math.log2(self.calibration_max / _FP16_TARGET_MAX))
+                if scale != 1.0:
+                    for m in t.modules():
+                        if isinstance(m, nn.Conv2d) and m.bias is not None:
+                            m.bias.data.mul_(scale)
             t = t.to(dtype=dt, memory_format=torch.channels_last)
             for p in t.parameters():
                 p.requires_grad_(False)
-            self._trunk, self._sig = t, sig
+            self._trunk, self._sig, self.act_scale, self._verified = t, sig, scale, False
         return self._trunk
 
     @torch.no_grad()
     def features(self, trunk: nn.Module, x: torch.Tensor, precision: str, by_scale: bool) -> Dict[int, torch.Tensor]:
-        t = self._packed_trunk(trunk, precision)
+        """Stage maps 0..3, each multiplied by `self.act_scale` (1.0 unless the fp16 range guard engaged)."""
+        t = self._packed_trunk(trunk, precision, x, by_scale)
         dt = self._dtype(precision)
+        if self.act_scale != 1.0:
+            x = x * self.act_scale
         x = x.to(dtype=dt).contiguous(memory_format=torch.channels_last)
         old_tf32 = torch.backends.cudnn.allow_tf32
         if precision == "fp32":
             torch.backends.cudnn.allow_tf32 = False
         try:
-            if dt != torch.float32 and self.fused_ok is not False:
-                # BN-folded bottlenecks through cuDNN's fused conv+bias(+add)+ReLU; verified once
-                # against the plain module path, with a permanent fallback if unsupported.
-                try:
-                    feats = _fused_trunk_forward(t, x, by_scale)
-                    if self.fused_ok is None:
-                        ref = self._plain_forward(t, x, by_scale)
-                        ok = all(torch.allclose(feats[k].float(), ref[k].float(), rtol=5e-2, atol=5e-2 * float(ref[k].float().abs().max()))
-                                 for k in ref)
-                        self.fused_ok = bool(ok)
-                        if not ok:
-                            return ref
-                    return feats
-                except (RuntimeError, AttributeError, KeyError, TypeError):
-                    self.fused_ok = False
-            return self._plain_forward(t, x, by_scale)
+            if dt == torch.float32:
+                return self._plain_forward(t, x, by_scale)
+            # BN-folded bottlenecks through cuDNN's fused conv+bias(+add)+ReLU.  Checked ONCE per weight set against
+            # the plain module path; a mismatch (or any error of the fused calls) is raised, never papered over.
+            feats = _fused_trunk_forward(t, x, by_scale)
+            if not self._verified:
+                ref = self._plain_forward(t, x, by_scale)
+                for k in ref:
+                    a, r = feats[k].float(), ref[k].float()
+                    if not torch.isfinite(a).all():
+                        raise RuntimeError(f"trunk stage {k}: non-finite {dt} activations (act_scale={self.act_scale}, "
+                                           f"calibration max {self.calibration_max}) — pin TrunkRunner.act_scale_override")
+                    err = float((a - r).abs().max() / r.abs().max().clamp_min(1e-30))
+                    if err > 1e-2:
+                        raise RuntimeError(f"trunk stage {k}: fused cuDNN path differs from the module path by {err:.2e}")
+                self._verified = True
+            return feats
         finally:
             torch.backends.cudnn.allow_tf32 = old_tf32
 
@@ -182,6 +231,14 @@ class TrunkRunner:
         return feats
 
 
+def _unscaled(feats: Dict[int, torch.Tensor], act_scale: float) -> Dict[int, torch.Tensor]:
+    """Stage maps with the trunk's fp16 range-guard factor removed (bf16: fp32's range), for consumers other than
+    the token-builder GEMM (the channel-token branch).  The usual act_scale == 1 returns the maps untouched."""
+    if act_scale == 1.0:
+        return feats
+    return {k: (v.float() * (1.0 / act_scale)).to(torch.bfloat16) for k, v in feats.items()}
+
+
 class TokenBuilder(engine.PackCache):
     def __init__(self):
         self._maps: Dict[Tuple[int, int, str], Dict[int, torch.Tensor]] = {}
@@ -193,12 +250,15 @@ class TokenBuilder(engine.PackCache):
         return self._maps[key]
 
     def pack(self, projection: nn.Module, num_layers: int, precision: str,
-             dtype: torch.dtype = torch.bfloat16) -> Dict[int, Tuple]:
+             dtype: torch.dtype = torch.bfloat16, act_scale: float = 1.0) -> Dict[int, Tuple]:
+        """1x1 projection weights as GEMM operands; 1 / act_scale (a power of two: exact) folded in when the stage
+        maps arrive scaled by the trunk's fp16 range guard."""
         def build():
-            return {k: engine.pack_linear(projection.head(k).weight, projection.head(k).bias, precision, dtype)
+            return {k: engine.pack_linear(projection.head(k).weight.detach().float() / act_scale, projection.head(k).bias,
+                                          precision, dtype)
                     for k in stages_used(num_layers)}
 
-        return self.packed(build, projection, precision + str(dtype))
+        return self.packed(build, projection, precision + str(dtype) + str(act_scale))
 
     @torch.no_grad()
     def build(
@@ -209,8 +269,9 @@ class TokenBuilder(engine.PackCache):
         scale_tok: torch.Tensor,
         pos_scale: torch.Tensor,
         precision: str,
+        act_scale: float = 1.0,
     ) -> torch.Tensor:
-        """feats[k]: [B, C_k, g*w, g*w] (any memory format; channels-last is free).
+        """feats[k]: [B, C_k, g*w, g*w] (any memory format; channels-last is free), multiplied by act_scale.
         scale_tok: [D] learned channel_token, or [B, P, D] channel-branch output (fp32).
         pos_scale: [S, D] fp32.  Returns X fp32 [B, P, S, D]."""
         B, _, h3, w3 = feats[3].shape
@@ -225,7 +286,7 @@ class TokenBuilder(engine.PackCache):
         maps = self.row_maps(num_layers, g, dev)
         # fp16 trunk maps feed the GEMM as they are, against fp16 copies of the 1x1-conv weights
         op_dtype = torch.float16 if (precision == "bf16" and feats[3].dtype == torch.float16) else torch.bfloat16
-        packs = self.pack(projection, num_layers, precision, op_dtype)
+        packs = self.pack(projection, num_layers, precision, op_dtype, act_scale)
         for k in stages_used(num_layers):
             f = feats[k]
             Bk, C, H, W = f.shape

@@ -82,7 +82,12 @@ def test_whole_module_pickle_of_the_real_reference_loads_without_reference_or_ti
         from duoformer_tcga_b200 import checkpoint
         from oracle import synth
         m = duo.MyModel_no_extra_params(depth=1, num_layers=2, pretrained=False, embed_dim=768, num_heads=12, num_classes=10, proj_dim=768)
-        missing, unexpected = checkpoint.load_checkpoint(m, {ckpt!r})
+        try:  # a whole-module pickle executes code on load: refused unless the caller vouches for it
+            checkpoint.load_checkpoint(m, {ckpt!r})
+            raise SystemExit("untrusted pickle was loaded")
+        except RuntimeError as e:
+            assert "trust_pickle" in str(e)
+        missing, unexpected = checkpoint.load_checkpoint(m, {ckpt!r}, trust_pickle=True)
         assert not missing and not unexpected, (missing, unexpected)
         want = synth.synth_state_dict(m.state_dict(), seed=9)
         assert all(torch.equal(m.state_dict()[k], want[k]) for k in want)
@@ -91,3 +96,14 @@ def test_whole_module_pickle_of_the_real_reference_loads_without_reference_or_ti
     """)
     r = subprocess.run([sys.executable, "-c", load], capture_output=True, text=True)
     assert r.returncode == 0 and "OK" in r.stdout, r.stderr[-2000:]
+
+
+def test_state_dict_file_loads_with_weights_only(tmp_path):
+    """A tensors-only checkpoint file needs no trust flag (torch.load(weights_only=True))."""
+    src = _small()
+    path = str(tmp_path / "sd.pt")
+    torch.save({"epoch": 3, "model_state_dict": src.state_dict()}, path)
+    dst = _small()
+    missing, unexpected = checkpoint.load_checkpoint(dst, path)
+    assert not missing and not unexpected
+    assert all(torch.equal(dst.state_dict()[k], v) for k, v in src.state_dict().items())

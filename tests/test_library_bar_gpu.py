@@ -1,50 +1,42 @@
-"""Informational (-m gpu, opt-in with DUO_RUN_LIBRARY_BAR=1): the "library bar" of BASELINE.md §5 — the
-reference's algorithm (the oracle's functional forward: plain torch ops over cuBLAS / cuDNN) run eagerly
-on the same B200 in bf16 and fp32, next to this repo's path, on the bench workload (4-scale, depth 12).
-Writes gpurun_out/library_bar.json; asserts only that the CUDA path is not slower than eager bf16."""
+"""-m gpu: the "library bar" of BASELINE.md §5 — the same forward as plain torch ops (cuDNN / cuBLAS / SDPA, eager,
+tools/library_bar.py) on the same B200 and parameters, next to this repo's path.  bench.py reports it as
+`library_bar`; here: the eager forward computes the same function, and the CUDA path is not slower than it."""
 import json
 import os
 
 import pytest
 import torch
 
-from common import COMMON
-import duoformer_tcga_b200 as duo
-from oracle import duoformer_oracle as orc
+from common import build_product, load_golden, relerr
+from oracle import synth
+from tools import library_bar
 
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.skipif(os.environ.get("DUO_RUN_LIBRARY_BAR") != "1", reason="opt-in measurement")
-def test_library_bar():
-    B = int(os.environ.get("DUO_LIBRARY_BAR_BATCH", "64"))
-    torch.manual_seed(0)
-    model = duo.MyModel_no_extra_params(depth=12, num_layers=4, pretrained=False, **COMMON).eval()
-    sd32 = {k: v.cuda() for k, v in orc.cpu_state_dict(model).items()}
-    sd16 = {k: (v.to(torch.bfloat16) if v.is_floating_point() else v) for k, v in sd32.items()}
-    x = torch.randn(B, 3, 224, 224, device="cuda")
-    model = model.cuda()
-
-    def timeit(fn, iters=3):
-        with torch.no_grad():
-            fn(); fn()
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(iters):
-                fn()
-            e1.record()
-            torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / iters
-
-    res = {"batch": B}
-    res["this_repo_bf16_ms"] = timeit(lambda: model(x))
-    res["torch_eager_bf16_ms"] = timeit(lambda: orc.forward_wo_extra(x.to(torch.bfloat16), sd16, 12, 12, 4))
-    res["torch_eager_fp32_tf32_ms"] = timeit(lambda: orc.forward_wo_extra(x, sd32, 12, 12, 4))
-    for k in list(res):
-        if k.endswith("_ms"):
-            res[k.replace("_ms", "_images_per_s")] = round(B / res[k] * 1000, 1)
+def test_library_bar_same_function_and_slower_than_this_repo():
+    gold = load_golden("wo4_d2")
+    model = build_product(gold["case"])
+    model.load_state_dict(synth.synth_state_dict(model.state_dict(), seed=gold["weight_seed"]))
+    model = model.cuda().eval()
+    B = 16
+    res, eager = library_bar.measure(model, batch=B, iters=2)
+    x = synth.synth_images(B, seed=5).cuda()
+    with torch.no_grad():
+        y = model(x).float()
+        assert relerr(eager(x), y) < 4e-2  # two bf16 paths of the same function
+        e32 = library_bar.EagerDuoFormer(model, torch.float32)
+        assert relerr(y[:4], e32(x[:4])) < 2e-2
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        model(x)
+        e0.record()
+        for _ in range(2):
+            model(x)
+        e1.record()
+        torch.cuda.synchronize()
+    ours = B / (e0.elapsed_time(e1) / 2) * 1000.0
+    res["this_repo_images_per_s"] = ours
     os.makedirs("gpurun_out", exist_ok=True)
-    json.dump(res, open("gpurun_out/library_bar.json", "w"), indent=1)
-    print(json.dumps(res))
-    assert res["this_repo_bf16_ms"] < res["torch_eager_bf16_ms"]
+    json.dump(res, open("gpurun_out/library_bar_test.json", "w"), indent=1)
+    assert res["finite"] and ours > res["value"], res

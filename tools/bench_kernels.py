@@ -40,7 +40,12 @@ def main():
     ap.add_argument("--images", type=int, default=64)
     ap.add_argument("--S", type=int, default=86)
     ap.add_argument("--only", default="")
+    ap.add_argument("--lib", default="", help="alternative build of the library (csrc/Makefile `tuning` targets)")
+    ap.add_argument("--tag", default="")
     a = ap.parse_args()
+    if a.lib:
+        from duoformer_tcga_b200 import _lib
+        _lib.LIB_PATH = os.path.abspath(a.lib)
     tf_peak, gb_peak, which = peaks()
     D, P, S = 768, 49, a.S
     M = a.images * P * S
@@ -153,7 +158,7 @@ def main():
         emit(f"scale_attention_algo{algo}_S{S}", ms, best, flops=4.0 * (M // S) * S * S * D, nbytes=M * D * 8)
     out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
     os.makedirs(out_dir, exist_ok=True)
-    json.dump(res, open(os.path.join(out_dir, "bench_kernels.json"), "w"), indent=1)
+    json.dump(res, open(os.path.join(out_dir, f"bench_kernels{a.tag}.json"), "w"), indent=1)
 
 
 if __name__ == "__main__":

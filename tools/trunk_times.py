@@ -11,7 +11,7 @@ m = duo.MyModel_no_extra_params(depth=1, num_layers=4, pretrained=False, embed_d
 x = torch.randn(B, 3, 224, 224, device="cuda")
 with torch.no_grad():
     m(x)
-    t = m._trunk_runner._packed_trunk(m.resnet_projector, "bf16")
+    t = m._trunk_runner._packed_trunk(m.resnet_projector, "bf16", x, False)
     ch = dict(t.named_children())
     by_scale = "conv1" in ch
     stem, pool = (t.conv1, t.maxpool) if by_scale else (ch["0"], ch["3"])
