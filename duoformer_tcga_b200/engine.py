@@ -12,6 +12,7 @@ Stage-wise parity tests hook `capture` dicts (name -> tensor clone).
 """
 from __future__ import annotations
 
+import contextlib
 from typing import Callable, Dict, List, Optional, Tuple
 
 import torch
@@ -20,6 +21,17 @@ from torch import nn
 from . import ops
 
 PRECISIONS = ("bf16", "fp32")
+
+
+@contextlib.contextmanager
+def nvtx(name: str):
+    """NVTX range around a stage of the forward (trunk / token builder / scale block i / patch stage / head): shows
+    up on the timeline of nsys / ncu --nvtx; a host-side marker only (safe under CUDA-graph capture, ~100 ns idle)."""
+    torch.cuda.nvtx.range_push("duo/" + name)
+    try:
+        yield
+    finally:
+        torch.cuda.nvtx.range_pop()
 
 
 def require_cuda(t: torch.Tensor, what: str) -> None:
@@ -135,8 +147,9 @@ def _scale_chunk(X, b0, nb, buf, blocks, num_heads, scale, eps, precision, captu
     ST = Workspace.view(buf, 2 * hn_bytes + big, (T, D // STAT_COLS, 2), torch.float32) if fwd else None
     gelu = ops.EPI_GELU_SPLIT_BF16 if fp32 else ops.EPI_GELU_BF16
     L = len(blocks)
-    have_ln1 = False  # Ha / ST hold the forwarded norm1 input of the current block
-    for i, blk in enumerate(blocks):
+
+    def run_block(i: int, blk: Dict, have_ln1: bool) -> bool:
+        """One scale block; have_ln1: Ha / ST hold this block's forwarded norm1 input.  Returns the same for the next."""
         last = i == L - 1
         if have_ln1:
             w, b, cs = blk["qkv_ln"]
@@ -144,7 +157,6 @@ def _scale_chunk(X, b0, nb, buf, blocks, num_heads, scale, eps, precision, captu
         else:
             ops.layernorm(Xc, blk["n1w"], blk["n1b"], Ha, eps)
             ops.gemm(Ha, blk["qkv"][0], blk["qkv"][1], QKV, ops.EPI_F32 if fp32 else ops.EPI_BF16, split3=fp32)
-        have_ln1 = False
         if live_only_last and last:
             # Last scale block: only the scale token (s = 0) of every patch is consumed downstream
             # (scale_attention.py:183-185), so K/V are needed for all tokens but the query,
@@ -162,7 +174,7 @@ def _scale_chunk(X, b0, nb, buf, blocks, num_heads, scale, eps, precision, captu
             ops.gemm(H0, blk["fc2"][0], blk["fc2"][1], X0, ops.EPI_RESIDUAL_F32, gamma=blk["g2"], split3=fp32)
             if capture is not None:
                 capture[f"scale_block_{i}_s0"] = X[:, :, 0, :].clone()
-            continue
+            return False
         ops.group_attention(QKV, Hb, S, num_heads, scale, algo=attn_algo)
         if fwd:
             ops.gemm(Hb, blk["proj"][0], blk["proj"][1], Xc, ops.EPI_RESIDUAL_F32, gamma=blk["g1"], xb_out=Ha, stats_out=ST)
@@ -172,13 +184,19 @@ def _scale_chunk(X, b0, nb, buf, blocks, num_heads, scale, eps, precision, captu
             ops.gemm(Hb, blk["proj"][0], blk["proj"][1], Xc, ops.EPI_RESIDUAL_F32, gamma=blk["g1"], split3=fp32)
             ops.layernorm(Xc, blk["n2w"], blk["n2b"], Ha, eps)
             ops.gemm(Ha, blk["fc1"][0], blk["fc1"][1], HID, gelu, split3=fp32)
-        if fwd and not last:
+        forward_next = fwd and not last
+        if forward_next:
             ops.gemm(HID, blk["fc2"][0], blk["fc2"][1], Xc, ops.EPI_RESIDUAL_F32, gamma=blk["g2"], xb_out=Ha, stats_out=ST)
-            have_ln1 = True
         else:
             ops.gemm(HID, blk["fc2"][0], blk["fc2"][1], Xc, ops.EPI_RESIDUAL_F32, gamma=blk["g2"], split3=fp32)
         if capture is not None:
             capture[f"scale_block_{i}"] = X.clone()
+        return forward_next
+
+    have_ln1 = False
+    for i, blk in enumerate(blocks):
+        with nvtx(f"scale_block_{i}"):
+            have_ln1 = run_block(i, blk, have_ln1)
 
 
 def _chunk_workspace_bytes(nb, P, S, D, hidden, fp32):
@@ -223,6 +241,31 @@ def scale_stage(
     return X
 
 
+class PatchScratch:
+    """Activation buffers of the patch stage carved out of the model's workspace (the scale stage's buffers are dead
+    by then): two ping-pong token buffers, qkv, attention output and the fp32 result of the last block — the
+    2 x depth launches of the patch stage allocate nothing."""
+
+    def __init__(self, ws: Workspace, rows: int, D: int):
+        self.sizes = {"z0": _align(rows * 2 * D * 2), "z1": _align(rows * 2 * D * 2), "qkv": _align(rows * 6 * D * 2),
+                      "ao": _align(rows * 2 * D * 2), "f32": _align(rows * D * 4)}
+        self.offsets, off = {}, 0
+        for k, n in self.sizes.items():
+            self.offsets[k] = off
+            off += n
+        self.buf = ws.get(off)
+        self._next_z = 0
+
+    def view(self, name: str, shape: Tuple[int, ...], dtype: torch.dtype) -> torch.Tensor:
+        return Workspace.view(self.buf, self.offsets[name], shape, dtype)
+
+    def next_z(self, shape: Tuple[int, ...], dtype: torch.dtype) -> torch.Tensor:
+        """The token buffer the current block's input does NOT live in."""
+        t = self.view(f"z{self._next_z}", shape, dtype)
+        self._next_z ^= 1
+        return t
+
+
 def region_attention(
     Z: torch.Tensor,
     blk: Dict,
@@ -232,6 +275,7 @@ def region_attention(
     precision: str,
     out_f32: bool,
     cls_only: bool = False,
+    scratch: Optional[PatchScratch] = None,
 ) -> torch.Tensor:
     """One patch ("region") attention block without residual / norm / MLP:
     Z <- proj(softmax(q k^T * scale) v)   (scale_attention.py:195-209, multiscale_attn.py:205-219).
@@ -244,6 +288,8 @@ def region_attention(
                        bits, weights are split too), but qkv and the attention output are bf16 so the
                        attention runs on the mma.sync kernel; proj multiplies the exact bf16
                        attention output with the split weight (2-pass).
+    scratch: buffers for qkv / attention output / result (Z itself must be scratch.next_z of the previous block or a
+             foreign tensor); None allocates.
     Returns the same kind as Z, or fp32 [rows, D] if out_f32."""
     split_io = precision in ("fp32", "mixed")
     fp32 = precision == "fp32"
@@ -252,32 +298,35 @@ def region_attention(
     rows = Z.shape[0]
     D = Z.shape[1] // kd_io
     dev = Z.device
+
+    def buf(name, shape, dtype):
+        if scratch is None:
+            return torch.empty(shape, dtype=dtype, device=dev)
+        return scratch.next_z(shape, dtype) if name == "z" else scratch.view(name, shape, dtype)
+
     if fp32 and not cls_only and N <= 64:
         # global attention on tcgen05 / TMEM in split precision: q, k, v stay hi | lo bf16 pairs end to end
-        QKV = torch.empty(rows, 6 * D, dtype=torch.bfloat16, device=dev)
+        QKV = buf("qkv", (rows, 6 * D), torch.bfloat16)
         ops.gemm(Z, blk["qkv"][0], blk["qkv"][1], QKV, ops.EPI_SPLIT_BF16, split3=1)
-        AO = torch.empty(rows, 2 * D, dtype=torch.bfloat16, device=dev)
+        AO = buf("ao", (rows, 2 * D), torch.bfloat16)
         ops.group_attention(QKV, AO, N, num_heads, scale, split_in=True)
     else:
-        QKV = torch.empty(rows, 3 * D, dtype=torch.float32 if fp32 else torch.bfloat16, device=dev)
+        QKV = buf("qkv", (rows, 3 * D), torch.float32 if fp32 else torch.bfloat16)
         ops.gemm(Z, blk["qkv"][0], blk["qkv"][1], QKV, ops.EPI_F32 if fp32 else ops.EPI_BF16, split3=1 if split_io else 0)
-        AO = None
-    if AO is not None:
-        pass
-    elif cls_only:
-        # last patch block: only the CLS query row of every image reaches the head (scale_attention.py:341)
-        rows = rows // N
-        AO = torch.empty(rows, kd_ao * D, dtype=torch.bfloat16, device=dev)
-        ops.group_attention(QKV, AO, N, num_heads, scale, q_rows=1)
-    else:
-        AO = torch.empty(rows, kd_ao * D, dtype=torch.bfloat16, device=dev)
-        ops.group_attention(QKV, AO, N, num_heads, scale)
+        if cls_only:
+            # last patch block: only the CLS query row of every image reaches the head (scale_attention.py:341)
+            rows = rows // N
+            AO = buf("ao", (rows, kd_ao * D), torch.bfloat16)
+            ops.group_attention(QKV, AO, N, num_heads, scale, q_rows=1)
+        else:
+            AO = buf("ao", (rows, kd_ao * D), torch.bfloat16)
+            ops.group_attention(QKV, AO, N, num_heads, scale)
     proj_split = 1 if fp32 else (2 if precision == "mixed" else 0)
     if out_f32:
-        out = torch.empty(rows, D, dtype=torch.float32, device=dev)
+        out = buf("f32", (rows, D), torch.float32)
         ops.gemm(AO, blk["proj"][0], blk["proj"][1], out, ops.EPI_F32, split3=proj_split)
     else:
-        out = torch.empty(rows, kd_io * D, dtype=torch.bfloat16, device=dev)
+        out = buf("z", (rows, kd_io * D), torch.bfloat16)
         ops.gemm(AO, blk["proj"][0], blk["proj"][1], out, ops.EPI_SPLIT_BF16 if split_io else ops.EPI_BF16,
                  split3=proj_split)
     return out

@@ -116,10 +116,13 @@ class MyModel(nn.Module):
         if self.name != "scaleformer":
             raise NotImplementedError("only model_ver='scaleformer' is on the DuoFormer path")
         tr = self._trunk_runner
-        feats = tr.features(self.resnet_projector, x, self.precision, False)
-        tok = self.channel_branch(_unscaled(feats, tr.act_scale))
-        return self._token_builder.build(feats, self.projection, self.num_layers, tok,
-                                         self.vision_transformer.pos_scale_table(), self.precision, tr.act_scale)
+        with engine.nvtx("trunk"):
+            feats = tr.features(self.resnet_projector, x, self.precision, False)
+        with engine.nvtx("channel_branch"):
+            tok = self.channel_branch(_unscaled(feats, tr.act_scale))
+        with engine.nvtx("token_builder"):
+            return self._token_builder.build(feats, self.projection, self.num_layers, tok,
+                                             self.vision_transformer.pos_scale_table(), self.precision, tr.act_scale)
 
     @torch.no_grad()
     def forward(self, x: torch.Tensor) -> torch.Tensor:

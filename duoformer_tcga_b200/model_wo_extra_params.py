@@ -141,14 +141,17 @@ class MyModel_no_extra_params(nn.Module):
     def build_tokens(self, x: torch.Tensor) -> torch.Tensor:
         """Image batch -> fp32 tokens [B, P, S, D] including pos_embed_for_scale."""
         tr = self._trunk_runner
-        feats = tr.features(self.resnet_projector, x, self.precision, self.backbone == "r50_Swav")
+        with engine.nvtx("trunk"):
+            feats = tr.features(self.resnet_projector, x, self.precision, self.backbone == "r50_Swav")
         vt = self.vision_transformer
         if self.scale_token == "channel":
-            tok = self.channel_branch(_unscaled(feats, tr.act_scale))
+            with engine.nvtx("channel_branch"):
+                tok = self.channel_branch(_unscaled(feats, tr.act_scale))
         else:
             tok = self.channel_token.detach().reshape(-1).to(torch.float32)
-        return self._token_builder.build(feats, self.projection, self.num_layers, tok, vt.pos_scale_table(),
-                                         self.precision, tr.act_scale)
+        with engine.nvtx("token_builder"):
+            return self._token_builder.build(feats, self.projection, self.num_layers, tok, vt.pos_scale_table(),
+                                             self.precision, tr.act_scale)
 
     @torch.no_grad()
     def forward(self, x: torch.Tensor) -> torch.Tensor:

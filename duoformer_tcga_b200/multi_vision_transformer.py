@@ -124,14 +124,15 @@ class MultiscaleTransformer(nn.Module):
         hw, hb = engine._f32(self.head.weight), engine._f32(self.head.bias)
         nw, nb = engine._f32(self.norm.weight), engine._f32(self.norm.bias)
         if depth >= 1:
-            Z = torch.empty(B * N, kd * D, dtype=torch.bfloat16, device=X.device)
+            scratch = engine.PatchScratch(self.workspace(X.device), B * N, D)  # the scale stage's workspace is free again
+            Z = scratch.next_z((B * N, kd * D), torch.bfloat16)
             ops.assemble_patch_tokens(X, engine._f32(self.cls_token).view(-1), engine._f32(self.pos_embed).view(N, D),
                                       Z.view(B, N, kd * D))
-            Z = engine.region_attention(Z, packs[0]["region"], N, self.num_heads, scale, prec, out_f32=False)
+            Z = engine.region_attention(Z, packs[0]["region"], N, self.num_heads, scale, prec, out_f32=False, scratch=scratch)
             if cap is not None:
                 cap["region_block_0"] = engine.unsplit(Z, prec).view(B, N, D).clone()
         if depth >= 2:
-            Zf = engine.region_attention(Z, packs[-1]["region"], N, self.num_heads, scale, prec, out_f32=True)
+            Zf = engine.region_attention(Z, packs[-1]["region"], N, self.num_heads, scale, prec, out_f32=True, scratch=scratch)
             if cap is not None:
                 cap["region_block_last"] = Zf.view(B, N, D).clone()
             ops.head(Zf, N * D, hw, hb, logits, ln_gamma=nw, ln_beta=nb, eps=self.norm.eps)

@@ -209,7 +209,9 @@ class MultiscaleFormer(nn.Module):
         N = P + 1
         prec = self.patch_precision or prec
         kd = 2 if prec in ("fp32", "mixed") else 1
-        Z = torch.empty(B * N, kd * D, dtype=torch.bfloat16, device=X.device)
+        torch.cuda.nvtx.range_push("duo/patch_stage")
+        scratch = engine.PatchScratch(ws, B * N, D)  # the scale stage's workspace is free again
+        Z = scratch.next_z((B * N, kd * D), torch.bfloat16)
         ops.assemble_patch_tokens(X, engine._f32(self.cls_token).view(-1), engine._f32(self.pos_embed).view(N, D), Z.view(B, N, kd * D))
         if cap is not None:
             cap["patch_in"] = engine.unsplit(Z, prec).view(B, N, D)
@@ -219,7 +221,7 @@ class MultiscaleFormer(nn.Module):
             last = i == nblk - 1
             cls_only = last and self.dead_work_elimination
             Z = engine.region_attention(Z, blk.pack("bf16" if prec == "bf16" else "fp32"), N, self.num_heads, blk.attn.scale, prec, out_f32=last,
-                                        cls_only=cls_only)
+                                        cls_only=cls_only, scratch=scratch)
             if cap is not None:
                 if cls_only:
                     cap[f"patch_block_{i}_cls"] = Z.view(B, D).clone()
@@ -232,6 +234,7 @@ class MultiscaleFormer(nn.Module):
         logits = torch.empty(B, self.head.out_features, dtype=torch.float32, device=X.device)
         # head on the CLS row; fc_norm is computed-and-discarded in the reference (:341-344)
         ops.head(Zf, D if cls_only else N * D, engine._f32(self.head.weight), engine._f32(self.head.bias), logits)
+        torch.cuda.nvtx.range_pop()
         return logits
 
     @torch.no_grad()

@@ -1,0 +1,135 @@
+"""Out-of-bounds WRITE detection with guard bands (-m gpu).
+
+compute-sanitizer is closed on this GPU pool (`gpurun` refuses it: "runs under it have left GPUs needing a reset"), so
+the memcheck pass SURVEY.md §5 asks for is replaced by this test: every output of every kernel family is carved out of
+a larger allocation whose surroundings hold a sentinel bit pattern, the kernel runs on a RAGGED problem (row counts
+that are not multiples of the 128 / 256-row tiles, partial last TMA boxes, odd group counts), and the sentinels
+before and after the output must be untouched.  TMA stores clip at the tensor-map bounds and the direct-store
+epilogues predicate on `row < M`; a missing predicate or a wrong box shows up here as a damaged guard band.
+"""
+import pytest
+import torch
+
+from duoformer_tcga_b200 import ops
+
+pytestmark = pytest.mark.gpu
+
+GUARD = 1 << 16  # bytes on either side
+SENTINEL = 0x5A
+
+
+class Guarded:
+    def __init__(self, shape, dtype):
+        self.shape, self.dtype = tuple(shape), dtype
+        n = 1
+        for s in shape:
+            n *= s
+        self.nbytes = n * torch.empty((), dtype=dtype).element_size()
+        pad = (-self.nbytes) % 256
+        self.raw = torch.full((GUARD + self.nbytes + pad + GUARD,), SENTINEL, dtype=torch.uint8, device="cuda")
+        self.t = self.raw[GUARD:GUARD + self.nbytes].view(dtype).view(*shape)
+
+    def check(self, what):
+        torch.cuda.synchronize()
+        lo, hi = self.raw[:GUARD], self.raw[GUARD + self.nbytes:]
+        assert bool((lo == SENTINEL).all()), f"{what}: wrote BEFORE the output buffer"
+        assert bool((hi == SENTINEL).all()), f"{what}: wrote PAST the output buffer"
+
+
+def _bf(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).cuda().to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("M", [1, 77, 129, 256 * 3 + 77, 256 * 152 + 131])
+def test_gemm_epilogues_stay_inside_their_outputs(M):
+    N, K = 768, 768
+    A, W = _bf((M, K), 1), _bf((N, K), 2, 0.05)
+    bias = torch.randn(N, device="cuda")
+    for epi, dtype, cols in ((ops.EPI_BF16, torch.bfloat16, N), (ops.EPI_GELU_BF16, torch.bfloat16, N),
+                             (ops.EPI_F32, torch.float32, N), (ops.EPI_SPLIT_BF16, torch.bfloat16, 2 * N)):
+        out = Guarded((M, cols), dtype)
+        ops.gemm(A, W, bias, out.t, epi)
+        out.check(f"epilogue {epi} M={M}")
+        assert torch.isfinite(out.t.float()).all()
+    X = Guarded((M, N), torch.float32)
+    X.t.zero_()
+    ops.gemm(A, W, bias, X.t, ops.EPI_RESIDUAL_F32)
+    X.check(f"residual M={M}")
+    X2, xb, st = Guarded((M, N), torch.float32), Guarded((M, N), torch.bfloat16), Guarded((M, N // 128, 2), torch.float32)
+    X2.t.zero_()
+    ops.gemm(A, W, bias, X2.t, ops.EPI_RESIDUAL_F32, xb_out=xb.t, stats_out=st.t)
+    for gd, nm in ((X2, "X"), (xb, "xb_out"), (st, "stats_out")):
+        gd.check(f"forwarding {nm} M={M}")
+    assert torch.equal(X2.t, X.t)
+    hid = Guarded((M, 4 * N), torch.bfloat16)
+    W1 = _bf((4 * N, K), 3, 0.05)
+    ops.gemm(xb.t, W1, torch.zeros(4 * N, device="cuda"), hid.t, ops.EPI_GELU_BF16, ln_stats=st.t,
+             ln_colsum=W1.float().sum(dim=1).contiguous())
+    hid.check(f"forwarded LayerNorm consumer M={M}")
+    assert torch.isfinite(hid.t.float()).all()
+
+
+@pytest.mark.parametrize("B", [1, 3, 37])
+def test_token_scatter_stays_inside_the_token_tensor(B):
+    from duoformer_tcga_b200.index_tables import token_row_maps
+
+    D, P, S = 768, 49, 86
+    X = Guarded((B, P, S, D), torch.float32)
+    maps = token_row_maps(4, 7)
+    pos = torch.randn(S, D, device="cuda")
+    for k, (C, hw) in {0: (256, 56), 1: (512, 28), 2: (1024, 14), 3: (2048, 7)}.items():
+        A, W = _bf((B * hw * hw, C), 10 + k), _bf((D, C), 20 + k, 0.05)
+        ops.gemm(A, W, None, X.t.view(B * P * S, D), ops.EPI_SCATTER_F32, row_map=maps[k].cuda(), rows_per_group=hw * hw,
+                 dest_rows_per_group=P * S, pos=pos, pos_period=S)
+    ops.fill_scale_token(X.t, torch.randn(D, device="cuda"), pos[0].contiguous())
+    X.check(f"token scatter B={B}")
+    assert torch.isfinite(X.t).all()  # every token row written exactly once (the sentinel pattern is a finite float too,
+    assert not bool((X.t.view(torch.uint8) == SENTINEL).view(B, -1).all(dim=1).any())  # but no image is left untouched)
+
+
+@pytest.mark.parametrize("S,G,algo,q_rows", [(86, 49 * 3 + 1, 3, 0), (86, 5, 2, 0), (86, 5, 2, 1), (22, 51, 2, 0), (6, 99, 1, 0),
+                                             (50, 3, 1, 1), (145, 2, 1, 0)])
+def test_attention_outputs_stay_inside(S, G, algo, q_rows):
+    D, H = 768, 12
+    qkv = _bf((G * S, 3 * D), 30)
+    rows = G * (q_rows if q_rows else S)
+    out = Guarded((rows, D), torch.bfloat16)
+    ops.group_attention(qkv, out.t, S, H, 0.125, algo=algo, q_rows=q_rows)
+    out.check(f"attention S={S} algo={algo} q_rows={q_rows}")
+    assert torch.isfinite(out.t.float()).all()
+
+
+@pytest.mark.parametrize("N,G", [(50, 5), (64, 3), (17, 7)])
+def test_split_patch_attention_output_stays_inside(N, G):
+    D, H = 768, 12
+    qkv = _bf((G * N, 6 * D), 31)
+    out = Guarded((G * N, 2 * D), torch.bfloat16)
+    ops.group_attention(qkv, out.t, N, H, 0.125, split_in=True)
+    out.check(f"split patch attention N={N}")
+
+
+def test_layernorm_helpers_and_data_movement_stay_inside():
+    D = 768
+    for rows in (1, 33, 4214 + 5):
+        x = torch.randn(rows, D, device="cuda")
+        for kd in (1, 2):
+            out = Guarded((rows, kd * D), torch.bfloat16)
+            ops.layernorm(x, torch.ones(D, device="cuda"), torch.zeros(D, device="cuda"), out.t, 1e-6)
+            out.check(f"layernorm rows={rows} kd={kd}")
+    B, P, S = 3, 49, 6
+    X = torch.randn(B, P, S, D, device="cuda")
+    Z = Guarded((B, P + 1, 2 * D), torch.bfloat16)
+    ops.assemble_patch_tokens(X, torch.randn(D, device="cuda"), torch.randn(P + 1, D, device="cuda"), Z.t)
+    Z.check("assemble_patch_tokens")
+    logits = Guarded((B, 10), torch.float32)
+    ops.head(X.view(B, -1), P * S * D, torch.randn(10, D, device="cuda"), torch.randn(10, device="cuda"), logits.t)
+    logits.check("head")
+    x = torch.randn(2, 13, 13, 64, device="cuda").to(torch.float16)
+    col = Guarded((2 * 7 * 7, 9 * 64), torch.bfloat16)
+    ops.im2col3x3(x, 2, out=col.t)
+    col.check("im2col3x3 stride 2")
+    wide = Guarded((2 * 6 * 6, 64 + 32), torch.bfloat16)
+    ops.pool_to_slice(torch.randn(2, 12, 12, 64, device="cuda").to(torch.float16), wide.t[:, :64], 2)
+    ops.pool_to_slice(torch.randn(2, 6, 6, 32, device="cuda").to(torch.float16), wide.t[:, 64:], 1)
+    wide.check("pool_to_slice")
