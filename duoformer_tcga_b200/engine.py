@@ -94,6 +94,8 @@ def _align(n: int, a: int = 1024) -> int:
 # standalone launches).  Precision study: tests/diag_ln_forwarding.py (same error as LayerNorm-then-round for
 # |row mean| <= row spread; fp32 mode keeps the standalone LayerNorm).  Needs D % 256 == 0.
 FORWARD_LN_STATS = True
+# which LayerNorms are forwarded when FORWARD_LN_STATS is on: "norm1" (fc2 -> next block's QKV), "norm2" (proj -> fc1)
+FORWARD_LINKS = ("norm1", "norm2")
 
 STAT_COLS = 128  # columns per forwarded (mean, M2) pair (csrc/gemm_tcgen05.cu kStatCols)
 
@@ -134,6 +136,7 @@ def _scale_chunk(X, b0, nb, buf, blocks, num_heads, scale, eps, precision, captu
     B, P, S, D = X.shape
     fp32 = precision == "fp32"
     fwd = FORWARD_LN_STATS and not fp32 and D % 256 == 0 and "qkv_ln" in blocks[0]
+    fwd1, fwd2 = fwd and "norm1" in FORWARD_LINKS, fwd and "norm2" in FORWARD_LINKS
     kd = 2 if fp32 else 1
     hidden = blocks[0]["fc1"][0].shape[0]
     T = nb * P * S
@@ -176,7 +179,7 @@ def _scale_chunk(X, b0, nb, buf, blocks, num_heads, scale, eps, precision, captu
                 capture[f"scale_block_{i}_s0"] = X[:, :, 0, :].clone()
             return False
         ops.group_attention(QKV, Hb, S, num_heads, scale, algo=attn_algo)
-        if fwd:
+        if fwd2:
             ops.gemm(Hb, blk["proj"][0], blk["proj"][1], Xc, ops.EPI_RESIDUAL_F32, gamma=blk["g1"], xb_out=Ha, stats_out=ST)
             w, b, cs = blk["fc1_ln"]
             ops.gemm(Ha, w, b, HID, gelu, ln_stats=ST, ln_colsum=cs, ln_eps=eps)
@@ -184,7 +187,7 @@ def _scale_chunk(X, b0, nb, buf, blocks, num_heads, scale, eps, precision, captu
             ops.gemm(Hb, blk["proj"][0], blk["proj"][1], Xc, ops.EPI_RESIDUAL_F32, gamma=blk["g1"], split3=fp32)
             ops.layernorm(Xc, blk["n2w"], blk["n2b"], Ha, eps)
             ops.gemm(Ha, blk["fc1"][0], blk["fc1"][1], HID, gelu, split3=fp32)
-        forward_next = fwd and not last
+        forward_next = fwd1 and not last
         if forward_next:
             ops.gemm(HID, blk["fc2"][0], blk["fc2"][1], Xc, ops.EPI_RESIDUAL_F32, gamma=blk["g2"], xb_out=Ha, stats_out=ST)
         else:

@@ -205,11 +205,16 @@ class MultiscaleFormer(nn.Module):
         engine.scale_stage(X, [b.pack(prec) for b in self.scaleBlocks], self.num_heads, scale,
                            self.scaleBlocks[0].norm1.eps if len(self.scaleBlocks) else 1e-6, prec, ws, cap,
                            attn_algo=self.attn_algo, live_only_last=self.dead_work_elimination)
+        with engine.nvtx("patch_stage"):
+            return self._patch_stage(X, ws, cap)
+
+    def _patch_stage(self, X: torch.Tensor, ws: engine.Workspace, cap) -> torch.Tensor:
+        B, P, S, D = X.shape
+        prec = self.precision
         # patch stage: CLS + first scale token of every patch + pos_embed (scale_attention.py:183-193)
         N = P + 1
         prec = self.patch_precision or prec
         kd = 2 if prec in ("fp32", "mixed") else 1
-        torch.cuda.nvtx.range_push("duo/patch_stage")
         scratch = engine.PatchScratch(ws, B * N, D)  # the scale stage's workspace is free again
         Z = scratch.next_z((B * N, kd * D), torch.bfloat16)
         ops.assemble_patch_tokens(X, engine._f32(self.cls_token).view(-1), engine._f32(self.pos_embed).view(N, D), Z.view(B, N, kd * D))
@@ -234,7 +239,6 @@ class MultiscaleFormer(nn.Module):
         logits = torch.empty(B, self.head.out_features, dtype=torch.float32, device=X.device)
         # head on the CLS row; fc_norm is computed-and-discarded in the reference (:341-344)
         ops.head(Zf, D if cls_only else N * D, engine._f32(self.head.weight), engine._f32(self.head.bias), logits)
-        torch.cuda.nvtx.range_pop()
         return logits
 
     @torch.no_grad()
