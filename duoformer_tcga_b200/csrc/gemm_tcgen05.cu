@@ -56,7 +56,7 @@ constexpr int kEpiResidualFwdLongK = 104;  // same, tuned for long K (fc2): one 
 constexpr int kEpiBf16Ln = 102;       // DUO_EPI_BF16 with the forwarded LayerNorm applied in the epilogue
 constexpr int kEpiGeluBf16Ln = 103;   // DUO_EPI_GELU_BF16 with the forwarded LayerNorm applied in the epilogue
 
-constexpr int kStatCols = 128;  // columns covered by one forwarded (mean, M2) pair
+constexpr int kStatCols = 256;  // columns covered by one forwarded (mean, M2) pair (= the N tile of the producer)
 
 template <int EPI>
 struct EpiTraits {
@@ -90,9 +90,9 @@ struct GemmParams {
   void* out;
   const float* gamma;
   // statistics forwarding, producer side (kEpiResidualFwd)
-  float2* stats_out;        // [M, N / 128] (mean, M2) of the updated rows, per 128-column part
+  float2* stats_out;        // [M, N / 256] (mean, M2) of the updated rows, per 256-column part
   // statistics forwarding, consumer side (kEpiBf16Ln / kEpiGeluBf16Ln)
-  const float2* ln_stats;   // [M, K / 128]
+  const float2* ln_stats;   // [M, K / 256]
   const float* ln_colsum;   // [N] sum_k W'[n, k]
   float ln_eps;
   int32_t relu;           // BF16 / F32 epilogues: clamp at zero
@@ -111,9 +111,9 @@ struct GemmParams {
 // residual stream and W' = W * diag(ln_gamma); with (mean, rstd) of the row,
 //   LN(x) W^T + b = rstd * (x W'^T - mean * colsum(W')) + (W ln_beta + b)
 // so the epilogue computes  ln_a * acc + (ln_c * colsum[n] + bias'[n])  with ln_a = rstd, ln_c = -mean * rstd.
-// The (mean, M2) pairs of the row's K / 128 column parts (written by the producing residual GEMM from the
+// The (mean, M2) pairs of the row's K / 256 column parts (written by the producing residual GEMM from the
 // fp32 row) are merged with Chan's formula.
-constexpr int kMaxStatParts = 8;  // K <= 1024
+constexpr int kMaxStatParts = 4;  // K <= 1024
 struct LnRowStats {
   float2 s[kMaxStatParts];
 };
@@ -145,29 +145,32 @@ __device__ __forceinline__ void ln_stats_finish(const GemmParams& p, const LnRow
   ln_c = -mean * rstd;
 }
 
-// Bias slice [col, col+32) -> registers; issued BEFORE waiting on the TMEM load so both latencies overlap.
-__device__ __forceinline__ void epilogue_bias_load(const GemmParams& p, int col, float4 (&b)[8]) {
+// Bias slice [col, col + 4 * NQ) -> registers; issued BEFORE waiting on the TMEM load so both latencies overlap.
+template <int NQ>
+__device__ __forceinline__ void epilogue_bias_load(const GemmParams& p, int col, float4 (&b)[NQ]) {
   if (p.bias != nullptr) {
     const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) b[j] = __ldg(b4 + j);
+    for (int j = 0; j < NQ; ++j) b[j] = __ldg(b4 + j);
   } else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) b[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < NQ; ++j) b[j] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
-// colsum(W') slice [col, col+32) (forwarded LayerNorm only)
-__device__ __forceinline__ void epilogue_colsum_load(const GemmParams& p, int col, float4 (&cs)[8]) {
+// colsum(W') slice [col, col + 4 * NQ) (forwarded LayerNorm only)
+template <int NQ>
+__device__ __forceinline__ void epilogue_colsum_load(const GemmParams& p, int col, float4 (&cs)[NQ]) {
   const float4* c4 = reinterpret_cast<const float4*>(p.ln_colsum + col);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) cs[j] = __ldg(c4 + j);
+  for (int j = 0; j < NQ; ++j) cs[j] = __ldg(c4 + j);
 }
 
 // Forwarded LayerNorm: b <- ln_c * colsum + b  (the per-row, per-column additive term)
-__device__ __forceinline__ void epilogue_ln_fold_bias(float ln_c, const float4 (&cs)[8], float4 (&b)[8]) {
+template <int NQ>
+__device__ __forceinline__ void epilogue_ln_fold_bias(float ln_c, const float4 (&cs)[NQ], float4 (&b)[NQ]) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < NQ; ++j) {
     uint64_t lo = fma2(pack2(ln_c, ln_c), pack2(cs[j].x, cs[j].y), pack2(b[j].x, b[j].y));
     uint64_t hi = fma2(pack2(ln_c, ln_c), pack2(cs[j].z, cs[j].w), pack2(b[j].z, b[j].w));
     unpack2(lo, b[j].x, b[j].y);
@@ -175,14 +178,15 @@ __device__ __forceinline__ void epilogue_ln_fold_bias(float ln_c, const float4 (
   }
 }
 
-// f = ln_a * acc + b  (ln_a == 1 without a forwarded LayerNorm: plain bias add), then the epilogue's function
-template <int EPI>
-__device__ __forceinline__ void epilogue_math(const GemmParams& p, int col, const uint32_t (&v)[32],
-                                              const float4 (&b)[8], float (&f)[32], float ln_a) {
+// f = ln_a * acc + b  (ln_a == 1 without a forwarded LayerNorm: plain bias add), then the epilogue's function;
+// 4 * NQ consecutive columns starting at `col`
+template <int EPI, int NQ>
+__device__ __forceinline__ void epilogue_math(const GemmParams& p, int col, const uint32_t (&v)[4 * NQ],
+                                              const float4 (&b)[NQ], float (&f)[4 * NQ], float ln_a) {
   using ET = EpiTraits<EPI>;
   if constexpr (ET::kGelu) {  // bias add and GELU on packed fp32 pairs
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < NQ; ++j) {
       uint64_t lo, hi;
       if constexpr (ET::kLnApply) {
         lo = fma2(pack2(ln_a, ln_a), pack2(__uint_as_float(v[4 * j + 0]), __uint_as_float(v[4 * j + 1])), pack2(b[j].x, b[j].y));
@@ -198,7 +202,7 @@ __device__ __forceinline__ void epilogue_math(const GemmParams& p, int col, cons
   }
   if constexpr (ET::kLnApply) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < NQ; ++j) {
       f[4 * j + 0] = fmaf(ln_a, __uint_as_float(v[4 * j + 0]), b[j].x);
       f[4 * j + 1] = fmaf(ln_a, __uint_as_float(v[4 * j + 1]), b[j].y);
       f[4 * j + 2] = fmaf(ln_a, __uint_as_float(v[4 * j + 2]), b[j].z);
@@ -207,7 +211,7 @@ __device__ __forceinline__ void epilogue_math(const GemmParams& p, int col, cons
     return;
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < NQ; ++j) {
     f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b[j].x;
     f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b[j].y;
     f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b[j].z;
@@ -216,18 +220,18 @@ __device__ __forceinline__ void epilogue_math(const GemmParams& p, int col, cons
   if constexpr (EPI == DUO_EPI_BF16 || EPI == DUO_EPI_F32) {
     if (p.relu) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+      for (int j = 0; j < 4 * NQ; ++j) f[j] = fmaxf(f[j], 0.f);
     }
   }
   if constexpr (EPI == DUO_EPI_GELU_SPLIT_BF16) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+    for (int j = 0; j < 4 * NQ; ++j) f[j] = gelu_erf(f[j]);
   }
   if constexpr (EPI == kEpiResidualTma) {
     if (p.gamma != nullptr) {
       const float4* g4 = reinterpret_cast<const float4*>(p.gamma + col);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < NQ; ++j) {
         const float4 g = __ldg(g4 + j);
         f[4 * j + 0] *= g.x;
         f[4 * j + 1] *= g.y;
@@ -295,7 +299,7 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 // One accumulator slab (this warp's 32 rows x columns [c_begin, c_end) of the tile): TMEM ->
 // registers -> fused math -> global memory.  `release()` is called as soon as this warp has read
 // its part of the accumulator completely.
-template <int EPI, int NBUF, typename ReleaseFn>
+template <int EPI, int NBUF, int SUBCOLS = 32, typename ReleaseFn>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtensorMap* tmap_out,
                                               uint32_t taddr, int row0, int lane, int n0, int c_begin,
                                               int c_end, uint32_t stg, uint32_t& stg_buf,
@@ -306,7 +310,49 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
   const uint32_t my_row_off = static_cast<uint32_t>(lane) * 128u;
   (void)valid;
   (void)my_row_off;
-  if constexpr (ET::kStagedBf16) {
+  if constexpr (ET::kStagedBf16 && SUBCOLS == 16) {
+    // 16-warp epilogue (GELU): each warp owns 64 columns = ONE 128-byte-wide staging tile per accumulator, filled 16
+    // columns at a time (tcgen05.ld x16: half the live registers, so four epilogue warps fit on every scheduler);
+    // single staging buffer: the TMA store of the previous tile was issued a whole tile ago.
+#pragma unroll 1
+    for (int c = c_begin; c < c_end; c += 64) {
+      const uint32_t buf = stg + my_row_off;
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        uint32_t v[16];
+        float4 bia[4];
+        ptx::tmem_ld_32x16(taddr + static_cast<uint32_t>(c + 16 * h), v);
+        epilogue_bias_load(p, n0 + c + 16 * h, bia);
+        if constexpr (ET::kLnApply) {
+          float4 cs[4];
+          epilogue_colsum_load(p, n0 + c + 16 * h, cs);
+          epilogue_ln_fold_bias(ln_c, cs, bia);
+        }
+        ptx::tmem_ld_wait();
+        if (h == 3 && c + 64 >= c_end) {  // accumulator fully read: hand the TMEM buffer back early
+          ptx::tc_fence_before();
+          release();
+        }
+        float f[16];
+        epilogue_math<EPI>(p, n0 + c + 16 * h, v, bia, f, ln_a);
+        if (h == 0) {
+          if (lane == 0) ptx::tma_store_wait_read<0>();  // the staging tile is no longer being read
+          __syncwarp();
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j)  // 16-byte chunk (2h + j) of this row, XOR-swizzled
+          st_shared_v4(buf + (static_cast<uint32_t>((2 * h + j) ^ (lane & 7)) << 4),
+                       pack_bf16x2(f[8 * j + 0], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                       pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+      }
+      ptx::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        ptx::tma_store_2d(tmap_out, stg, n0 + c, row0);
+        ptx::tma_store_commit();
+      }
+    }
+  } else if constexpr (ET::kStagedBf16) {
     // 64 output columns (= 128 B of bf16) per staged chunk, filled 32 columns at a time
 #pragma unroll 1
     for (int c = c_begin; c < c_end; c += 64) {
@@ -663,17 +709,19 @@ constexpr int kPairBlockN = 256;
 // slots, each one 32 x 32 fp32 chunk of X (TMA-loaded, updated in place, TMA-stored) plus its bf16 copy.
 constexpr uint32_t kFwdXBytes = 32 * 128;  // 32 rows x 32 fp32, SWIZZLE_128B
 constexpr uint32_t kFwdBBytes = 32 * 64;   // 32 rows x 32 bf16, SWIZZLE_64B
-// EPI_WARPS epilogue warps: 4 (one per TMEM lane quarter, all 256 columns, 6 operand stages) or 8
-// (two per quarter, 128 columns each, 5 operand stages — used when the epilogue is heavy: GELU,
-// token scatter; both only occur with short K).  Staging is double-buffered per warp either way.
+// EPI_WARPS epilogue warps: 4 (one per TMEM lane quarter, all 256 columns, 6 operand stages), 8 (two per
+// quarter, 128 columns each, 5 operand stages: token scatter) or 16 (four per quarter, 64 columns each in
+// 16-column steps so that a thread needs < 112 registers: the GELU epilogues, which are bound by dependent-issue
+// latency — ncu: issue slots 40 % busy, top stall `wait` — and need four warps per scheduler to keep up with
+// the MMAs of a K = 768 tile).
 template <int EPI, int EPI_WARPS>
 struct PairCfg {
   using ET = EpiTraits<EPI>;
   static constexpr bool FWD = ET::kFwd;
   static constexpr int kFwdSlots = ET::kFwdSlots;
-  static constexpr int kStages = FWD ? ET::kFwdStages : (EPI_WARPS == 8 ? 5 : 6);
+  static constexpr int kStages = FWD ? ET::kFwdStages : (EPI_WARPS >= 8 ? 5 : 6);
   static constexpr int kThreads = 64 + 32 * EPI_WARPS;
-  static constexpr int kStagingBufs = 2;
+  static constexpr int kStagingBufs = EPI_WARPS == 16 ? 1 : 2;  // 64 KB of staging for 8 and for 16 warps
   static constexpr uint32_t kABytes = kBlockM * kBlockK * 2;          // 16 KB (this CTA's 128 rows)
   static constexpr uint32_t kBBytes = (kPairBlockN / 2) * kBlockK * 2;  // 16 KB (this CTA's N half)
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
@@ -860,6 +908,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
       // fp32 chunk and of its bf16 copy (one bulk group).  A slot is reloaded once the group that stored
       // it has been read out (wait_group.read 1 right after committing the NEXT group).
       constexpr int kChunks = kColsPerWarp / 32;
+      static_assert(kColsPerWarp == kStatCols, "one (mean, M2) pair per epilogue warp and tile");
       const uint32_t xbuf0 = staging_base + static_cast<uint32_t>(warp_idx) * (kFwdSlots * kFwdXBytes);
       const uint32_t bbuf0 = staging_base + EPI_WARPS * kFwdSlots * kFwdXBytes +
                              static_cast<uint32_t>(warp_idx) * (kFwdSlots * kFwdBBytes);
@@ -930,9 +979,9 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
               f[4 * j + 3] = x3 + a3;
             }
           }
-          // LayerNorm partial statistics of the updated fp32 row, per 128-column part (4 chunks):
-          // shifted sums around the part's first element (no cancellation for |mean| >> spread)
-          if ((ci & 3) == 0) {
+          // LayerNorm partial statistics of the updated fp32 row over the tile's 256 columns (8 chunks):
+          // shifted sums around the first element (no cancellation for |mean| >> spread)
+          if (ci == 0) {
             pivot = f[0];
             s1 = 0;
             s2 = 0;
@@ -946,7 +995,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
               s2 = fma2(d, d, s2);
             }
           }
-          if ((ci & 3) == 3) {
+          if (ci == kChunks - 1) {
             float a, b, q, r;
             unpack2(s1, a, b);
             unpack2(s2, q, r);
@@ -1004,7 +1053,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const uint32_t taddr =
             tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
         const uint32_t leader_empty = ptx::mapa(tmem_empty_bar(acc), 0);
-        epilogue_tile<EPI, C::kStagingBufs>(p, &tmap_out, taddr, row0, lane, n0, col_part * kColsPerWarp,
+        epilogue_tile<EPI, C::kStagingBufs, (EPI_WARPS == 16 ? 16 : 32)>(p, &tmap_out, taddr, row0, lane, n0, col_part * kColsPerWarp,
                                             (col_part + 1) * kColsPerWarp, stg, stg_buf, ln_a, ln_c,
                            [&]() {
                              __syncwarp();
@@ -1154,15 +1203,17 @@ int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
   return DUO_OK;
 }
 
-// Epilogue warps of the pair kernel: 8 (two per TMEM lane quarter) where the epilogue is heavy and K short
-// (GELU, token scatter), 4 otherwise.
+// Epilogue warps of the pair kernel: 16 for the GELU epilogues, 8 for the token scatter, 4 otherwise.
 int dispatch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tx,
                   const GemmParams& p, int epi, cudaStream_t st) {
   switch (epi) {
     case DUO_EPI_BF16: return launch_pair<DUO_EPI_BF16, 4>(ta, tb, to, tx, p, st);
-    case DUO_EPI_GELU_BF16: return launch_pair<DUO_EPI_GELU_BF16, 8>(ta, tb, to, tx, p, st);
+#ifndef DUO_GELU_WARPS
+#define DUO_GELU_WARPS 16  // tuning builds (csrc/Makefile `tuning`) compare 8
+#endif
+    case DUO_EPI_GELU_BF16: return launch_pair<DUO_EPI_GELU_BF16, DUO_GELU_WARPS>(ta, tb, to, tx, p, st);
     case kEpiBf16Ln: return launch_pair<kEpiBf16Ln, 4>(ta, tb, to, tx, p, st);
-    case kEpiGeluBf16Ln: return launch_pair<kEpiGeluBf16Ln, 8>(ta, tb, to, tx, p, st);
+    case kEpiGeluBf16Ln: return launch_pair<kEpiGeluBf16Ln, DUO_GELU_WARPS>(ta, tb, to, tx, p, st);
     case kEpiResidualTma: return launch_pair<kEpiResidualTma, 4>(ta, tb, to, tx, p, st);
     case kEpiResidualFwd: return launch_pair<kEpiResidualFwd, 4>(ta, tb, to, tx, p, st);
     case kEpiResidualFwdLongK: return launch_pair<kEpiResidualFwdLongK, 4>(ta, tb, to, tx, p, st);
@@ -1217,7 +1268,7 @@ extern "C" int duo_gemm(const duo_gemm_args* a, duo_stream_t stream) {
   if (ln_apply) {
     DUO_CHECK_ARG((epi == DUO_EPI_BF16 || epi == DUO_EPI_GELU_BF16) && a->split3 == 0 && !a->relu && a->ln_stats && a->ln_colsum,
                   "duo_gemm: a forwarded LayerNorm needs the BF16 / GELU_BF16 epilogue, plain bf16 operands, ln_stats and ln_colsum");
-    DUO_CHECK_ARG(a->K % kStatCols == 0, "duo_gemm: a forwarded LayerNorm needs K %% 128 == 0 (K=%d)", a->K);
+    DUO_CHECK_ARG(a->K % kStatCols == 0 && a->K <= kStatCols * kMaxStatParts, "duo_gemm: a forwarded LayerNorm needs K %% 256 == 0, K <= 1024 (K=%d)", a->K);
     DUO_CHECK_ARG((reinterpret_cast<uintptr_t>(a->ln_stats) & 7) == 0 && (reinterpret_cast<uintptr_t>(a->ln_colsum) & 15) == 0,
                   "duo_gemm: ln_stats must be 8-byte aligned, ln_colsum 16-byte aligned");
     epi = epi == DUO_EPI_BF16 ? kEpiBf16Ln : kEpiGeluBf16Ln;

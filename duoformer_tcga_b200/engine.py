@@ -97,7 +97,7 @@ FORWARD_LN_STATS = True
 # which LayerNorms are forwarded when FORWARD_LN_STATS is on: "norm1" (fc2 -> next block's QKV), "norm2" (proj -> fc1)
 FORWARD_LINKS = ("norm1", "norm2")
 
-STAT_COLS = 128  # columns per forwarded (mean, M2) pair (csrc/gemm_tcgen05.cu kStatCols)
+STAT_COLS = 256  # columns per forwarded (mean, M2) pair (csrc/gemm_tcgen05.cu kStatCols)
 
 
 def pack_ln_linear(weight: torch.Tensor, bias: Optional[torch.Tensor], ln_weight: torch.Tensor, ln_bias: torch.Tensor):

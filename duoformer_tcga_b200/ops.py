@@ -114,8 +114,8 @@ def gemm(
     """out = epilogue(A @ W.T + bias).  A [M,K] / W [N,K] bf16 (or [.,2K] split when split3).
 
     LayerNorm statistics forwarding (include/duoformer_sm100.h):
-      producer  EPI_RESIDUAL_F32 with xb_out (bf16 [M,N]) + stats_out (fp32 [M, N/128, 2]): the updated rows are
-                also written un-normalised in bf16 together with their per-128-column (mean, M2) pairs;
+      producer  EPI_RESIDUAL_F32 with xb_out (bf16 [M,N]) + stats_out (fp32 [M, N/256, 2]): the updated rows are
+                also written un-normalised in bf16 together with their per-256-column (mean, M2) pairs;
       consumer  EPI_BF16 / EPI_GELU_BF16 with ln_stats + ln_colsum: A is such a copy, W = W * ln_weight,
                 bias = W ln_bias + b; the epilogue applies mean / rstd."""
     split3 = int(split3)  # 0 plain, 1 both operands split (hi|lo), 2 only W split (A exact bf16)
@@ -139,10 +139,10 @@ def gemm(
     a.rows_per_group, a.dest_rows_per_group, a.pos_period = rows_per_group, dest_rows_per_group, pos_period
     if xb_out is not None or stats_out is not None:
         assert xb_out.dtype == torch.bfloat16 and xb_out.is_contiguous() and xb_out.numel() == M * N
-        assert stats_out.dtype == torch.float32 and stats_out.is_contiguous() and stats_out.numel() >= M * (N // 128) * 2
+        assert stats_out.dtype == torch.float32 and stats_out.is_contiguous() and stats_out.numel() >= M * (N // 256) * 2
         a.xb_out, a.stats_out = _ptr(xb_out), _ptr(stats_out)
     if ln_stats is not None or ln_colsum is not None:
-        assert ln_stats.dtype == torch.float32 and ln_stats.is_contiguous() and ln_stats.numel() >= M * (K // 128) * 2
+        assert ln_stats.dtype == torch.float32 and ln_stats.is_contiguous() and ln_stats.numel() >= M * (K // 256) * 2
         assert ln_colsum.dtype == torch.float32 and ln_colsum.is_contiguous() and ln_colsum.numel() == N
         a.ln_stats, a.ln_colsum, a.ln_eps = _ptr(ln_stats), _ptr(ln_colsum), float(ln_eps)
     if bias is not None:

@@ -108,10 +108,10 @@ typedef struct duo_gemm_args {
    * producer (RESIDUAL_F32, bf16 operands, N % 256 == 0, both pointers set): the epilogue loads the fp32
    *   rows of `out` itself (TMA), adds gamma * (acc + bias), stores them back and ALSO writes
    *     xb_out    bf16 [M, N] dense: the updated, un-normalised rows (A operand of the next GEMM), and
-   *     stats_out float [M, N / 128, 2]: (mean, sum of squared deviations) of every 128-column part of
+   *     stats_out float [M, N / 256, 2]: (mean, sum of squared deviations) of every 256-column part of
    *               the updated fp32 row.
-   * consumer (BF16 / GELU_BF16, bf16 operands, K % 128 == 0, both pointers set): A is such an un-normalised
-   *   copy, W holds W * diag(ln_weight) and bias holds W ln_bias + b; the epilogue merges the row's K / 128
+   * consumer (BF16 / GELU_BF16, bf16 operands, K % 256 == 0, K <= 1024, both pointers set): A is such an un-normalised
+   *   copy, W holds W * diag(ln_weight) and bias holds W ln_bias + b; the epilogue merges the row's K / 256
    *   partial statistics (ln_stats, same layout as stats_out) into mean / rstd and computes
    *     out = rstd * (acc - mean * ln_colsum[n]) + bias[n],   ln_colsum[n] = sum_k W'[n, k] (of the bf16 values),
    *   which equals Linear(LayerNorm(x)) up to operand rounding.

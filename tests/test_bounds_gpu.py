@@ -56,7 +56,7 @@ def test_gemm_epilogues_stay_inside_their_outputs(M):
     X.t.zero_()
     ops.gemm(A, W, bias, X.t, ops.EPI_RESIDUAL_F32)
     X.check(f"residual M={M}")
-    X2, xb, st = Guarded((M, N), torch.float32), Guarded((M, N), torch.bfloat16), Guarded((M, N // 128, 2), torch.float32)
+    X2, xb, st = Guarded((M, N), torch.float32), Guarded((M, N), torch.bfloat16), Guarded((M, N // 256, 2), torch.float32)
     X2.t.zero_()
     ops.gemm(A, W, bias, X2.t, ops.EPI_RESIDUAL_F32, xb_out=xb.t, stats_out=st.t)
     for gd, nm in ((X2, "X"), (xb, "xb_out"), (st, "stats_out")):

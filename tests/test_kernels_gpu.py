@@ -270,18 +270,18 @@ def test_invalid_arguments_raise():
 
 
 def _merge_stats(st, N):
-    """[M, N/128, 2] (mean, M2) partial statistics -> per-row mean, biased variance (Chan's formula)."""
+    """[M, N/256, 2] (mean, M2) partial statistics -> per-row mean, biased variance (Chan's formula)."""
     parts = st.shape[1]
     mean = st[:, :, 0].mean(dim=1)
-    m2 = st[:, :, 1].sum(dim=1) + 128.0 * ((st[:, :, 0] - mean[:, None]) ** 2).sum(dim=1)
-    return mean, m2 / (128.0 * parts)
+    m2 = st[:, :, 1].sum(dim=1) + 256.0 * ((st[:, :, 0] - mean[:, None]) ** 2).sum(dim=1)
+    return mean, m2 / (256.0 * parts)
 
 
 @pytest.mark.parametrize("M,K,with_gamma", [(256 * 60 + 77, 768, False), (256 * 60 + 77, 768, True), (256 * 152, 3072, False),
                                             (300, 768, True), (4214, 768, False), (129, 3072, False)])
 def test_gemm_residual_statistics_forwarding_producer(M, K, with_gamma):
     """x = x + gamma*(A W^T + b) with xb_out / stats_out: the fp32 rows are updated exactly like the plain residual
-    epilogue, xb_out is their bf16 rounding and stats_out holds (mean, M2) of every 128-column part of the fp32 row
+    epilogue, xb_out is their bf16 rounding and stats_out holds (mean, M2) of every 256-column part of the fp32 row
     (any M: the forwarding epilogue always runs on the CTA-pair kernel; a large row mean exercises the shifted sums)."""
     N = 768
     A = _gen((M, K), 111).to(torch.bfloat16)
@@ -292,7 +292,7 @@ def test_gemm_residual_statistics_forwarding_producer(M, K, with_gamma):
     upd = A.float() @ W.float().t() + bias
     Xr = X + (gamma * upd if with_gamma else upd)
     xb = torch.zeros(M, N, dtype=torch.bfloat16, device="cuda")
-    st = torch.full((M, N // 128, 2), float("nan"), device="cuda")
+    st = torch.full((M, N // 256, 2), float("nan"), device="cuda")
     X0 = X.clone()
     for _ in range(2):
         X.copy_(X0)
@@ -303,7 +303,7 @@ def test_gemm_residual_statistics_forwarding_producer(M, K, with_gamma):
         assert torch.isfinite(st).all()
         assert (mean - X.mean(dim=1)).abs().max().item() < 1e-3
         assert relerr(var, X.var(dim=1, unbiased=False)) < 1e-4
-        parts = X.view(M, N // 128, 128)
+        parts = X.view(M, N // 256, 256)
         assert (st[:, :, 0] - parts.mean(dim=2)).abs().max().item() < 1e-3
         assert relerr(st[:, :, 1], ((parts - parts.mean(dim=2, keepdim=True)) ** 2).sum(dim=2)) < 1e-3
 
@@ -323,7 +323,7 @@ def test_gemm_forwarded_layernorm_consumer(M, N, epi):
     ref = torch.nn.functional.layer_norm(x, (K,), lw, lb, 1e-6) @ W.t() + bias
     if epi == "gelu":
         ref = torch.nn.functional.gelu(ref)
-    parts = x.view(M, K // 128, 128)
+    parts = x.view(M, K // 256, 256)
     pm = parts.mean(dim=2)
     st = torch.stack([pm, ((parts - pm[:, :, None]) ** 2).sum(dim=2)], dim=2).contiguous()
     wp, bp, cs = engine.pack_ln_linear(W, bias, lw, lb)
@@ -356,7 +356,7 @@ def test_gemm_statistics_forwarding_chain_matches_layernorm_path():
     # forwarding sequence
     X2 = X.clone()
     xb = torch.empty(M, D, dtype=torch.bfloat16, device="cuda")
-    st = torch.empty(M, D // 128, 2, device="cuda")
+    st = torch.empty(M, D // 256, 2, device="cuda")
     ops.gemm(A, Wp, bp, X2, ops.EPI_RESIDUAL_F32, xb_out=xb, stats_out=st)
     w, b, cs = engine.pack_ln_linear(W1, b1, lw, lb)
     h2 = torch.empty(M, Hd, dtype=torch.bfloat16, device="cuda")
@@ -372,7 +372,7 @@ def test_gemm_forwarding_argument_checks():
     W = torch.zeros(768, 768, dtype=torch.bfloat16, device="cuda")
     X = torch.zeros(256, 768, device="cuda")
     xb = torch.zeros(256, 768, dtype=torch.bfloat16, device="cuda")
-    st = torch.zeros(256, 6, 2, device="cuda")
+    st = torch.zeros(256, 3, 2, device="cuda")
     with pytest.raises(RuntimeError, match="statistics forwarding"):  # only with the residual epilogue
         ops.gemm(A, W, None, xb, ops.EPI_BF16, xb_out=xb, stats_out=st)
     with pytest.raises(RuntimeError, match="forwarded LayerNorm"):  # not with the residual epilogue

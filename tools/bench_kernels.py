@@ -94,7 +94,7 @@ def main():
     # epilogue) against the three-launch sequence residual GEMM, LayerNorm, GEMM
     if not a.only or "fwd" in a.only:
         from duoformer_tcga_b200 import engine
-        st = torch.empty(M, D // 128, 2, device=dev)
+        st = torch.empty(M, D // 256, 2, device=dev)
         for name, K, N2, epi2 in (("proj", D, 4 * D, ops.EPI_GELU_BF16), ("fc2", 4 * D, 3 * D, ops.EPI_BF16)):
             A = (torch.randn(M, K, device=dev) * 0.5).to(torch.bfloat16)
             W = (torch.randn(D, K, device=dev) * 0.02).to(torch.bfloat16)

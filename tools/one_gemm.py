@@ -15,7 +15,7 @@ torch.manual_seed(0)
 g, b = torch.ones(D, device=dev), torch.zeros(D, device=dev)
 x = torch.randn(M, D, device=dev) * 3
 xb = x.to(torch.bfloat16)
-parts = x.view(M, D // 128, 128)
+parts = x.view(M, D // 256, 256)
 pm = parts.mean(dim=2)
 st = torch.stack([pm, ((parts - pm[:, :, None]) ** 2).sum(dim=2)], dim=2).contiguous()
 N = {"qkv": 3 * D, "qkv_ln": 3 * D, "fc1_gelu": 4 * D, "fc1_gelu_ln": 4 * D}.get(which, D)
