@@ -68,7 +68,6 @@ class GemmArgs(Structure):
         ("xb_out", c_void_p),
         ("stats_out", c_void_p),
         ("ln_stats", c_void_p),
-        ("ln_colsum", c_void_p),
     ]
 
 

@@ -93,7 +93,6 @@ struct GemmParams {
   float2* stats_out;        // [M, N / 256] (mean, M2) of the updated rows, per 256-column part
   // statistics forwarding, consumer side (kEpiBf16Ln / kEpiGeluBf16Ln)
   const float2* ln_stats;   // [M, K / 256]
-  const float* ln_colsum;   // [N] sum_k W'[n, k]
   float ln_eps;
   int32_t relu;           // BF16 / F32 epilogues: clamp at zero
   const int32_t* row_map;
@@ -108,9 +107,10 @@ struct GemmParams {
 };
 
 // Forwarded LayerNorm, consumer side.  The A operand of this GEMM is the UN-normalised bf16 copy of the
-// residual stream and W' = W * diag(ln_gamma); with (mean, rstd) of the row,
-//   LN(x) W^T + b = rstd * (x W'^T - mean * colsum(W')) + (W ln_beta + b)
-// so the epilogue computes  ln_a * acc + (ln_c * colsum[n] + bias'[n])  with ln_a = rstd, ln_c = -mean * rstd.
+// residual stream and W'' = W * diag(ln_gamma) with every ROW CENTRED (sum_k W''[n, k] = 0, engine.pack_ln_linear):
+// the mean of x then cancels inside the tensor-core product, x W''^T = (x - mean) (W diag(gamma))^T, and
+//   LN(x) W^T + b = rstd * (x W''^T) + (W ln_beta + b)
+// so the epilogue computes  ln_a * acc + bias'[n]  with ln_a = rstd — one FMA where the plain epilogue has an add.
 // The (mean, M2) pairs of the row's K / 256 column parts (written by the producing residual GEMM from the
 // fp32 row) are merged with Chan's formula.
 constexpr int kMaxStatParts = 4;  // K <= 1024
@@ -127,7 +127,7 @@ __device__ __forceinline__ void ln_stats_load(const GemmParams& p, int64_t row, 
   for (int i = 0; i < kMaxStatParts; ++i)
     st.s[i] = (valid && i < parts) ? __ldg(src + i) : make_float2(0.f, 0.f);
 }
-__device__ __forceinline__ void ln_stats_finish(const GemmParams& p, const LnRowStats& st, float& ln_a, float& ln_c) {
+__device__ __forceinline__ void ln_stats_finish(const GemmParams& p, const LnRowStats& st, float& ln_a) {
   const int parts = p.K / kStatCols;
   float mean = 0.f, m2 = 0.f;
 #pragma unroll
@@ -140,9 +140,7 @@ __device__ __forceinline__ void ln_stats_finish(const GemmParams& p, const LnRow
       m2 += st.s[i].y + static_cast<float>(kStatCols) * d * d;
     }
   }
-  const float rstd = rsqrtf(m2 / static_cast<float>(p.K) + p.ln_eps);
-  ln_a = rstd;
-  ln_c = -mean * rstd;
+  ln_a = rsqrtf(m2 / static_cast<float>(p.K) + p.ln_eps);
 }
 
 // Bias slice [col, col + 4 * NQ) -> registers; issued BEFORE waiting on the TMEM load so both latencies overlap.
@@ -155,26 +153,6 @@ __device__ __forceinline__ void epilogue_bias_load(const GemmParams& p, int col,
   } else {
 #pragma unroll
     for (int j = 0; j < NQ; ++j) b[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-}
-
-// colsum(W') slice [col, col + 4 * NQ) (forwarded LayerNorm only)
-template <int NQ>
-__device__ __forceinline__ void epilogue_colsum_load(const GemmParams& p, int col, float4 (&cs)[NQ]) {
-  const float4* c4 = reinterpret_cast<const float4*>(p.ln_colsum + col);
-#pragma unroll
-  for (int j = 0; j < NQ; ++j) cs[j] = __ldg(c4 + j);
-}
-
-// Forwarded LayerNorm: b <- ln_c * colsum + b  (the per-row, per-column additive term)
-template <int NQ>
-__device__ __forceinline__ void epilogue_ln_fold_bias(float ln_c, const float4 (&cs)[NQ], float4 (&b)[NQ]) {
-#pragma unroll
-  for (int j = 0; j < NQ; ++j) {
-    uint64_t lo = fma2(pack2(ln_c, ln_c), pack2(cs[j].x, cs[j].y), pack2(b[j].x, b[j].y));
-    uint64_t hi = fma2(pack2(ln_c, ln_c), pack2(cs[j].z, cs[j].w), pack2(b[j].z, b[j].w));
-    unpack2(lo, b[j].x, b[j].y);
-    unpack2(hi, b[j].z, b[j].w);
   }
 }
 
@@ -303,7 +281,7 @@ template <int EPI, int NBUF, int SUBCOLS = 32, typename ReleaseFn>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtensorMap* tmap_out,
                                               uint32_t taddr, int row0, int lane, int n0, int c_begin,
                                               int c_end, uint32_t stg, uint32_t& stg_buf,
-                                              float ln_a, float ln_c, ReleaseFn release) {
+                                              float ln_a, ReleaseFn release) {
   using ET = EpiTraits<EPI>;
   const int64_t row = static_cast<int64_t>(row0) + lane;
   const bool valid = row < p.M;
@@ -323,11 +301,6 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
         float4 bia[4];
         ptx::tmem_ld_32x16(taddr + static_cast<uint32_t>(c + 16 * h), v);
         epilogue_bias_load(p, n0 + c + 16 * h, bia);
-        if constexpr (ET::kLnApply) {
-          float4 cs[4];
-          epilogue_colsum_load(p, n0 + c + 16 * h, cs);
-          epilogue_ln_fold_bias(ln_c, cs, bia);
-        }
         ptx::tmem_ld_wait();
         if (h == 3 && c + 64 >= c_end) {  // accumulator fully read: hand the TMEM buffer back early
           ptx::tc_fence_before();
@@ -363,11 +336,6 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
         float4 bia[8];
         ptx::tmem_ld_32x32(taddr + static_cast<uint32_t>(c + 32 * h), v);
         epilogue_bias_load(p, n0 + c + 32 * h, bia);
-        if constexpr (ET::kLnApply) {
-          float4 cs[8];
-          epilogue_colsum_load(p, n0 + c + 32 * h, cs);
-          epilogue_ln_fold_bias(ln_c, cs, bia);
-        }
         ptx::tmem_ld_wait();
         if (h == 1 && c + 64 >= c_end) {  // accumulator fully read: hand the TMEM buffer back early
           ptx::tc_fence_before();
@@ -661,9 +629,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const int n_blk = static_cast<int>(tile - static_cast<int64_t>(m_blk) * p.num_n_blocks);
       const int row0 = m_blk * kBlockM + quarter * 32;  // first row of this warp's slab
       const int n0 = n_blk * BLOCK_N;
-      float ln_a = 1.f, ln_c = 0.f;
+      float ln_a = 1.f;
       if constexpr (ET::kLnApply) {
-        ln_stats_finish(p, ln_next, ln_a, ln_c);
+        ln_stats_finish(p, ln_next, ln_a);
         const int64_t nt = tile + gridDim.x;
         if (nt < num_tiles) ln_stats_load(p, (nt / p.num_n_blocks) * kBlockM + quarter * 32 + lane, ln_next);
       }
@@ -672,7 +640,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const uint32_t taddr =
           tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
 
-      epilogue_tile<EPI, 2>(p, &tmap_out, taddr, row0, lane, n0, 0, BLOCK_N, stg, stg_buf, ln_a, ln_c,
+      epilogue_tile<EPI, 2>(p, &tmap_out, taddr, row0, lane, n0, 0, BLOCK_N, stg, stg_buf, ln_a,
                          [&]() {
                            __syncwarp();
                            if (lane == 0) ptx::mbar_arrive(tmem_empty_bar(acc));
@@ -710,10 +678,10 @@ constexpr int kPairBlockN = 256;
 constexpr uint32_t kFwdXBytes = 32 * 128;  // 32 rows x 32 fp32, SWIZZLE_128B
 constexpr uint32_t kFwdBBytes = 32 * 64;   // 32 rows x 32 bf16, SWIZZLE_64B
 // EPI_WARPS epilogue warps: 4 (one per TMEM lane quarter, all 256 columns, 6 operand stages), 8 (two per
-// quarter, 128 columns each, 5 operand stages: token scatter) or 16 (four per quarter, 64 columns each in
-// 16-column steps so that a thread needs < 112 registers: the GELU epilogues, which are bound by dependent-issue
-// latency — ncu: issue slots 40 % busy, top stall `wait` — and need four warps per scheduler to keep up with
-// the MMAs of a K = 768 tile).
+// quarter, 128 columns each, 5 operand stages: GELU, token scatter) or 16 (four per quarter, 64 columns each in
+// 16-column steps, < 96 registers per thread; a tuning variant of the GELU epilogue: fc1 + GELU 0.967 ms per 64
+// images against 0.950 ms with 8 warps — the epilogue is bound by the MUFU pipe (ncu: XU 60 % busy, stalls `wait` /
+// `mio_throttle`), not by the number of warps in flight).
 template <int EPI, int EPI_WARPS>
 struct PairCfg {
   using ET = EpiTraits<EPI>;
@@ -1043,9 +1011,9 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
       for (int64_t it = 0; pair_tile(it, pair_idx, pair_stride, p.num_m_blocks, p.num_n_blocks, m_blk, n_blk); ++it) {
         const int row0 = m_blk * (2 * kBlockM) + static_cast<int>(cta_rank) * kBlockM + quarter * 32;
         const int n0 = n_blk * BLOCK_N;
-        float ln_a = 1.f, ln_c = 0.f;
+        float ln_a = 1.f;
         if constexpr (ET::kLnApply) {
-          ln_stats_finish(p, ln_next, ln_a, ln_c);
+          ln_stats_finish(p, ln_next, ln_a);
           ln_prefetch(it + 1);
         }
         ptx::mbar_wait(tmem_full_bar(acc), acc_phase);
@@ -1054,7 +1022,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
             tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
         const uint32_t leader_empty = ptx::mapa(tmem_empty_bar(acc), 0);
         epilogue_tile<EPI, C::kStagingBufs, (EPI_WARPS == 16 ? 16 : 32)>(p, &tmap_out, taddr, row0, lane, n0, col_part * kColsPerWarp,
-                                            (col_part + 1) * kColsPerWarp, stg, stg_buf, ln_a, ln_c,
+                                            (col_part + 1) * kColsPerWarp, stg, stg_buf, ln_a,
                            [&]() {
                              __syncwarp();
                              if (lane == 0) ptx::mbar_arrive_cluster(leader_empty);
@@ -1203,13 +1171,13 @@ int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
   return DUO_OK;
 }
 
-// Epilogue warps of the pair kernel: 16 for the GELU epilogues, 8 for the token scatter, 4 otherwise.
+// Epilogue warps of the pair kernel: 8 for the GELU epilogues and the token scatter, 4 otherwise.
 int dispatch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tx,
                   const GemmParams& p, int epi, cudaStream_t st) {
   switch (epi) {
     case DUO_EPI_BF16: return launch_pair<DUO_EPI_BF16, 4>(ta, tb, to, tx, p, st);
 #ifndef DUO_GELU_WARPS
-#define DUO_GELU_WARPS 16  // tuning builds (csrc/Makefile `tuning`) compare 8
+#define DUO_GELU_WARPS 8  // 16 (four warps per scheduler, 16-column TMEM loads) measured 2 % slower: csrc/Makefile `tuning`
 #endif
     case DUO_EPI_GELU_BF16: return launch_pair<DUO_EPI_GELU_BF16, DUO_GELU_WARPS>(ta, tb, to, tx, p, st);
     case kEpiBf16Ln: return launch_pair<kEpiBf16Ln, 4>(ta, tb, to, tx, p, st);
@@ -1264,13 +1232,12 @@ extern "C" int duo_gemm(const duo_gemm_args* a, duo_stream_t stream) {
                   "duo_gemm: xb_out must be 16-byte aligned, stats_out 8-byte aligned");
   }
   // consumer side: LayerNorm applied in the epilogue from forwarded statistics
-  const bool ln_apply = a->ln_stats != nullptr || a->ln_colsum != nullptr;
+  const bool ln_apply = a->ln_stats != nullptr;
   if (ln_apply) {
-    DUO_CHECK_ARG((epi == DUO_EPI_BF16 || epi == DUO_EPI_GELU_BF16) && a->split3 == 0 && !a->relu && a->ln_stats && a->ln_colsum,
-                  "duo_gemm: a forwarded LayerNorm needs the BF16 / GELU_BF16 epilogue, plain bf16 operands, ln_stats and ln_colsum");
+    DUO_CHECK_ARG((epi == DUO_EPI_BF16 || epi == DUO_EPI_GELU_BF16) && a->split3 == 0 && !a->relu,
+                  "duo_gemm: a forwarded LayerNorm needs the BF16 / GELU_BF16 epilogue and plain bf16 operands");
     DUO_CHECK_ARG(a->K % kStatCols == 0 && a->K <= kStatCols * kMaxStatParts, "duo_gemm: a forwarded LayerNorm needs K %% 256 == 0, K <= 1024 (K=%d)", a->K);
-    DUO_CHECK_ARG((reinterpret_cast<uintptr_t>(a->ln_stats) & 7) == 0 && (reinterpret_cast<uintptr_t>(a->ln_colsum) & 15) == 0,
-                  "duo_gemm: ln_stats must be 8-byte aligned, ln_colsum 16-byte aligned");
+    DUO_CHECK_ARG((reinterpret_cast<uintptr_t>(a->ln_stats) & 7) == 0, "duo_gemm: ln_stats must be 8-byte aligned");
     epi = epi == DUO_EPI_BF16 ? kEpiBf16Ln : kEpiGeluBf16Ln;
   }
 #ifndef DUO_FWD_LONGK_FROM
@@ -1313,7 +1280,6 @@ extern "C" int duo_gemm(const duo_gemm_args* a, duo_stream_t stream) {
   GemmParams p;
   p.stats_out = reinterpret_cast<float2*>(a->stats_out);
   p.ln_stats = reinterpret_cast<const float2*>(a->ln_stats);
-  p.ln_colsum = a->ln_colsum;
   p.ln_eps = a->ln_eps;
   p.relu = a->relu;
   p.bias = a->bias;

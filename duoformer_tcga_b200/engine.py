@@ -89,7 +89,7 @@ def _align(n: int, a: int = 1024) -> int:
 
 # bf16 mode: LayerNorm statistics forwarding (duo_gemm's xb_out / stats_out / ln_stats).  Every residual GEMM
 # (proj, fc2) also writes the bf16 copy of the updated rows and their per-row partial statistics; the GEMM that
-# follows (fc1, next block's QKV) runs on W * diag(ln_weight) and applies mean / rstd in its epilogue, so no
+# follows (fc1, next block's QKV) runs on the row-centred W * diag(ln_weight) and applies rstd in its epilogue, so no
 # LayerNorm kernel re-reads the fp32 stream (only block 0's norm1 and the live rows of the last block run as
 # standalone launches).  Precision study: tests/diag_ln_forwarding.py (same error as LayerNorm-then-round for
 # |row mean| <= row spread; fp32 mode keeps the standalone LayerNorm).  Needs D % 256 == 0.
@@ -101,15 +101,27 @@ STAT_COLS = 256  # columns per forwarded (mean, M2) pair (csrc/gemm_tcgen05.cu k
 
 
 def pack_ln_linear(weight: torch.Tensor, bias: Optional[torch.Tensor], ln_weight: torch.Tensor, ln_bias: torch.Tensor):
-    """Linear(LayerNorm(x)) with the affine part of the norm folded in (consumer side of the statistics forwarding):
-    W' = bf16(W * ln_weight), bias' = W ln_bias + b (fp32, exact W), colsum[n] = sum_k W'[n, k] of the ROUNDED values
-    (it must cancel against the tensor-core product of the same values)."""
+    """Linear(LayerNorm(x)) with the norm folded into the operands (consumer side of the statistics forwarding).
+
+    W'' = W * ln_weight with every row centred: sum_k W''[n, k] = 0 makes the row mean of x cancel inside the
+    tensor-core product (x W''^T = (x - mean) W'^T), so the GEMM epilogue only scales by rstd.  The centring must hold
+    for the bf16 values the MMA actually multiplies: after rounding, the residual row sum (~sqrt(K) ulps) is absorbed
+    by the row's smallest element, whose fine ulp leaves |sum_k W''[n, k]| ~ 1e-6 of a typical weight — the leftover
+    mean leakage is then < 1e-5 of the output scale even for |mean| = 10 x the row spread.
+    bias' = W ln_bias + b (fp32, exact W)."""
     w = weight.detach().to(torch.float32)
-    wp = (w * ln_weight.detach().to(torch.float32)[None, :]).to(torch.bfloat16).contiguous()
+    wg = w * ln_weight.detach().to(torch.float32)[None, :]
+    wg = wg - wg.mean(dim=1, keepdim=True)
+    wp = wg.to(torch.bfloat16)
+    for _ in range(2):
+        resid = wp.to(torch.float64).sum(dim=1)  # exact row sums of the rounded values
+        k = wp.abs().argmin(dim=1, keepdim=True)
+        fixed = (wp.gather(1, k).to(torch.float64) - resid[:, None]).to(torch.bfloat16)
+        wp.scatter_(1, k, fixed)
     b = w @ ln_bias.detach().to(torch.float32)
     if bias is not None:
         b = b + bias.detach().to(torch.float32)
-    return wp, b.contiguous(), wp.to(torch.float32).sum(dim=1).contiguous()
+    return wp.contiguous(), b.contiguous()
 
 
 def pack_scale_block(precision: str, n1w, n1b, n2w, n2b, qkv, proj, fc1, fc2, g1=None, g2=None) -> Dict:
@@ -155,8 +167,8 @@ def _scale_chunk(X, b0, nb, buf, blocks, num_heads, scale, eps, precision, captu
         """One scale block; have_ln1: Ha / ST hold this block's forwarded norm1 input.  Returns the same for the next."""
         last = i == L - 1
         if have_ln1:
-            w, b, cs = blk["qkv_ln"]
-            ops.gemm(Ha, w, b, QKV, ops.EPI_BF16, ln_stats=ST, ln_colsum=cs, ln_eps=eps)
+            w, b = blk["qkv_ln"]
+            ops.gemm(Ha, w, b, QKV, ops.EPI_BF16, ln_stats=ST, ln_eps=eps)
         else:
             ops.layernorm(Xc, blk["n1w"], blk["n1b"], Ha, eps)
             ops.gemm(Ha, blk["qkv"][0], blk["qkv"][1], QKV, ops.EPI_F32 if fp32 else ops.EPI_BF16, split3=fp32)
@@ -181,8 +193,8 @@ def _scale_chunk(X, b0, nb, buf, blocks, num_heads, scale, eps, precision, captu
         ops.group_attention(QKV, Hb, S, num_heads, scale, algo=attn_algo)
         if fwd2:
             ops.gemm(Hb, blk["proj"][0], blk["proj"][1], Xc, ops.EPI_RESIDUAL_F32, gamma=blk["g1"], xb_out=Ha, stats_out=ST)
-            w, b, cs = blk["fc1_ln"]
-            ops.gemm(Ha, w, b, HID, gelu, ln_stats=ST, ln_colsum=cs, ln_eps=eps)
+            w, b = blk["fc1_ln"]
+            ops.gemm(Ha, w, b, HID, gelu, ln_stats=ST, ln_eps=eps)
         else:
             ops.gemm(Hb, blk["proj"][0], blk["proj"][1], Xc, ops.EPI_RESIDUAL_F32, gamma=blk["g1"], split3=fp32)
             ops.layernorm(Xc, blk["n2w"], blk["n2b"], Ha, eps)

@@ -108,7 +108,6 @@ def gemm(
     xb_out: Optional[torch.Tensor] = None,
     stats_out: Optional[torch.Tensor] = None,
     ln_stats: Optional[torch.Tensor] = None,
-    ln_colsum: Optional[torch.Tensor] = None,
     ln_eps: float = 1e-6,
 ) -> torch.Tensor:
     """out = epilogue(A @ W.T + bias).  A [M,K] / W [N,K] bf16 (or [.,2K] split when split3).
@@ -116,8 +115,8 @@ def gemm(
     LayerNorm statistics forwarding (include/duoformer_sm100.h):
       producer  EPI_RESIDUAL_F32 with xb_out (bf16 [M,N]) + stats_out (fp32 [M, N/256, 2]): the updated rows are
                 also written un-normalised in bf16 together with their per-256-column (mean, M2) pairs;
-      consumer  EPI_BF16 / EPI_GELU_BF16 with ln_stats + ln_colsum: A is such a copy, W = W * ln_weight,
-                bias = W ln_bias + b; the epilogue applies mean / rstd."""
+      consumer  EPI_BF16 / EPI_GELU_BF16 with ln_stats: A is such a copy, W = W * ln_weight with centred rows
+                (engine.pack_ln_linear), bias = W ln_bias + b; the epilogue applies rstd."""
     split3 = int(split3)  # 0 plain, 1 both operands split (hi|lo), 2 only W split (A exact bf16)
     assert A.dim() == 2 and W.dim() == 2 and W.dtype == A.dtype, "A and W must share one 16-bit format"
     assert A.dtype == torch.bfloat16 or (A.dtype == torch.float16 and split3 == 0), "operands must be bf16 (or fp16 in plain mode)"
@@ -141,10 +140,9 @@ def gemm(
         assert xb_out.dtype == torch.bfloat16 and xb_out.is_contiguous() and xb_out.numel() == M * N
         assert stats_out.dtype == torch.float32 and stats_out.is_contiguous() and stats_out.numel() >= M * (N // 256) * 2
         a.xb_out, a.stats_out = _ptr(xb_out), _ptr(stats_out)
-    if ln_stats is not None or ln_colsum is not None:
+    if ln_stats is not None:
         assert ln_stats.dtype == torch.float32 and ln_stats.is_contiguous() and ln_stats.numel() >= M * (K // 256) * 2
-        assert ln_colsum.dtype == torch.float32 and ln_colsum.is_contiguous() and ln_colsum.numel() == N
-        a.ln_stats, a.ln_colsum, a.ln_eps = _ptr(ln_stats), _ptr(ln_colsum), float(ln_eps)
+        a.ln_stats, a.ln_eps = _ptr(ln_stats), float(ln_eps)
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() == N
     if row_map is not None:

@@ -110,16 +110,16 @@ typedef struct duo_gemm_args {
    *     xb_out    bf16 [M, N] dense: the updated, un-normalised rows (A operand of the next GEMM), and
    *     stats_out float [M, N / 256, 2]: (mean, sum of squared deviations) of every 256-column part of
    *               the updated fp32 row.
-   * consumer (BF16 / GELU_BF16, bf16 operands, K % 256 == 0, K <= 1024, both pointers set): A is such an un-normalised
-   *   copy, W holds W * diag(ln_weight) and bias holds W ln_bias + b; the epilogue merges the row's K / 256
-   *   partial statistics (ln_stats, same layout as stats_out) into mean / rstd and computes
-   *     out = rstd * (acc - mean * ln_colsum[n]) + bias[n],   ln_colsum[n] = sum_k W'[n, k] (of the bf16 values),
+   * consumer (BF16 / GELU_BF16, bf16 operands, K % 256 == 0, K <= 1024, ln_stats set): A is such an un-normalised
+   *   copy, W holds W * diag(ln_weight) with every row CENTRED (sum_k W[n, k] = 0: the row mean of x then cancels
+   *   inside the product, x W^T = (x - mean) W^T) and bias holds W ln_bias + b; the epilogue merges the row's K / 256
+   *   partial statistics (ln_stats, same layout as stats_out) into rstd and computes
+   *     out = rstd * acc + bias[n],
    *   which equals Linear(LayerNorm(x)) up to operand rounding.
    */
   void* xb_out;
   float* stats_out;
   const float* ln_stats;
-  const float* ln_colsum;
 } duo_gemm_args;
 int duo_gemm(const duo_gemm_args* args, duo_stream_t stream);
 

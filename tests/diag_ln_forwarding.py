@@ -6,6 +6,8 @@ batch 2, |token| up to O(10^2)) with three ways of feeding the QKV / fc1 GEMMs:
   ln_round   (round 1)  A = bf16(LN(x) * g + b), W = bf16(W)
   forward    A = bf16(x), W' = bf16(W * g); out = rstd * (A W'^T - mu * colsum(W')) + (W b_ln + bias)
   forward_shift  as `forward` with A = bf16(x - c_row), c_row = row mean of the block-0 input (fixed per row)
+  centred    (the product path) A = bf16(x), W'' = engine.pack_ln_linear: bf16(W * g) with centred rows, so the mean
+             cancels inside the product; out = rstd * (A W''^T) + (W b_ln + bias)
 
 and reports the relative max-norm error of every scale block's output and of the logits against the fp32
 oracle.  Statistics always come from the fp32 stream (the residual epilogue holds the fp32 row).
@@ -28,6 +30,9 @@ def bf(t):
     return t.to(torch.bfloat16).to(torch.float32)
 
 
+MEAN_OFFSET = 0.0  # stress: constant added to every row before rounding (LayerNorm is invariant to it)
+
+
 def lin_ln(x, sd, lnp, linp, mode, shift):
     g, b = sd[lnp + "weight"], sd[lnp + "bias"]
     W, bias = sd[linp + "weight"], sd[linp + "bias"]
@@ -37,6 +42,11 @@ def lin_ln(x, sd, lnp, linp, mode, shift):
     if mode == "ln_round":
         a = bf((x - mu) * rstd * g + b)
         return a @ bf(W).t() + bias
+    if mode == "centred":
+        from duoformer_tcga_b200 import engine
+
+        wp, bp = engine.pack_ln_linear(W, bias, g, b)
+        return rstd * (bf(x + MEAN_OFFSET) @ wp.float().t()) + bp
     Wp = bf(W * g)
     cs = Wp.sum(-1)
     c = shift if mode == "forward_shift" else torch.zeros_like(mu)
@@ -94,7 +104,7 @@ def main():
     with torch.no_grad():
         yo = oracle_forward(case, x, sd, capture=ocap)
         tokens = ocap["tokens"]
-        for mode in ("ln_round", "forward", "forward_shift"):
+        for mode in ("ln_round", "forward", "forward_shift", "centred"):
             xs, outs, stats = scale_stage(tokens.clone(), sd, case["depth"], COMMON["num_heads"], mode)
             y = tail(xs, sd, case["depth"], COMMON["num_heads"])
             errs = [relerr(o, ocap[f"scale_block_{i}"]) for i, o in enumerate(outs)]

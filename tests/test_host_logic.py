@@ -27,9 +27,9 @@ def test_c_abi_library_loads_and_exports_every_declared_symbol():
 
 
 def test_gemm_args_struct_layout_matches_header():
-    # 7 pointers, 4 int64, 7 int32 + float + 2 int32, 4 pointers -> 8*7 + 8*4 + 4*10 + 8*4 = 160 bytes
-    assert ctypes.sizeof(_lib.GemmArgs) == 160
-    assert _lib.GemmArgs.xb_out.offset == 128 and _lib.GemmArgs.ln_colsum.offset == 152
+    # 7 pointers, 4 int64, 7 int32 + float + 2 int32, 3 pointers -> 8*7 + 8*4 + 4*10 + 8*3 = 152 bytes
+    assert ctypes.sizeof(_lib.GemmArgs) == 152
+    assert _lib.GemmArgs.xb_out.offset == 128 and _lib.GemmArgs.ln_stats.offset == 144
     assert _lib.GemmArgs.M.offset == 56 and _lib.GemmArgs.N.offset == 88
 
 

@@ -326,10 +326,10 @@ def test_gemm_forwarded_layernorm_consumer(M, N, epi):
     parts = x.view(M, K // 256, 256)
     pm = parts.mean(dim=2)
     st = torch.stack([pm, ((parts - pm[:, :, None]) ** 2).sum(dim=2)], dim=2).contiguous()
-    wp, bp, cs = engine.pack_ln_linear(W, bias, lw, lb)
+    wp, bp = engine.pack_ln_linear(W, bias, lw, lb)
     out = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
     ops.gemm(x.to(torch.bfloat16), wp, bp, out, ops.EPI_GELU_BF16 if epi == "gelu" else ops.EPI_BF16,
-             ln_stats=st, ln_colsum=cs, ln_eps=1e-6)
+             ln_stats=st, ln_eps=1e-6)
     assert relerr(out, ref) < 1.5e-2
 
 
@@ -358,9 +358,9 @@ def test_gemm_statistics_forwarding_chain_matches_layernorm_path():
     xb = torch.empty(M, D, dtype=torch.bfloat16, device="cuda")
     st = torch.empty(M, D // 256, 2, device="cuda")
     ops.gemm(A, Wp, bp, X2, ops.EPI_RESIDUAL_F32, xb_out=xb, stats_out=st)
-    w, b, cs = engine.pack_ln_linear(W1, b1, lw, lb)
+    w, b = engine.pack_ln_linear(W1, b1, lw, lb)
     h2 = torch.empty(M, Hd, dtype=torch.bfloat16, device="cuda")
-    ops.gemm(xb, w, b, h2, ops.EPI_GELU_BF16, ln_stats=st, ln_colsum=cs, ln_eps=1e-6)
+    ops.gemm(xb, w, b, h2, ops.EPI_GELU_BF16, ln_stats=st, ln_eps=1e-6)
     assert relerr(X2, X1) < 1e-5
     ref = torch.nn.functional.gelu(torch.nn.functional.layer_norm(X1, (D,), lw, lb, 1e-6) @ W1.t() + b1)
     e1, e2 = relerr(h1, ref), relerr(h2, ref)
@@ -376,7 +376,7 @@ def test_gemm_forwarding_argument_checks():
     with pytest.raises(RuntimeError, match="statistics forwarding"):  # only with the residual epilogue
         ops.gemm(A, W, None, xb, ops.EPI_BF16, xb_out=xb, stats_out=st)
     with pytest.raises(RuntimeError, match="forwarded LayerNorm"):  # not with the residual epilogue
-        ops.gemm(A, W, None, X, ops.EPI_RESIDUAL_F32, ln_stats=st, ln_colsum=torch.zeros(768, device="cuda"))
+        ops.gemm(A, W, None, X, ops.EPI_RESIDUAL_F32, ln_stats=st)
 
 
 @pytest.mark.parametrize("M,N,K", [(300, 768, 256), (256 * 150 + 3, 768, 512)])

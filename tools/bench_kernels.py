@@ -101,21 +101,21 @@ def main():
             bias = torch.zeros(D, device=dev)
             W2 = torch.randn(N2, D, device=dev) * 0.02
             b2 = torch.zeros(N2, device=dev)
-            w2p, b2p, cs = engine.pack_ln_linear(W2, b2, g, b)
+            w2p, b2p = engine.pack_ln_linear(W2, b2, g, b)
             W2b = W2.to(torch.bfloat16)
             out2 = torch.empty(M, N2, dtype=torch.bfloat16, device=dev)
             ms, best = timeit(lambda: ops.gemm(A, W, bias, x, ops.EPI_RESIDUAL_F32, xb_out=hn, stats_out=st))
             emit(f"gemm_{name}_residual_fwd", ms, best, flops=2.0 * M * D * K, nbytes=M * (K * 2 + D * 10))
             ms, best = timeit(lambda: ops.gemm(A, W, bias, x, ops.EPI_RESIDUAL_F32))
             emit(f"gemm_{name}_residual", ms, best, flops=2.0 * M * D * K, nbytes=M * (K * 2 + D * 8))
-            ms, best = timeit(lambda: ops.gemm(hn, w2p, b2p, out2, epi2, ln_stats=st, ln_colsum=cs))
+            ms, best = timeit(lambda: ops.gemm(hn, w2p, b2p, out2, epi2, ln_stats=st))
             emit(f"gemm_after_{name}_ln_applied", ms, best, flops=2.0 * M * N2 * D)
             ms, best = timeit(lambda: ops.gemm(hn, W2b, b2, out2, epi2))
             emit(f"gemm_after_{name}_plain", ms, best, flops=2.0 * M * N2 * D)
 
             def fwd_seq():
                 ops.gemm(A, W, bias, x, ops.EPI_RESIDUAL_F32, xb_out=hn, stats_out=st)
-                ops.gemm(hn, w2p, b2p, out2, epi2, ln_stats=st, ln_colsum=cs)
+                ops.gemm(hn, w2p, b2p, out2, epi2, ln_stats=st)
 
             def ln_seq():
                 ops.gemm(A, W, bias, x, ops.EPI_RESIDUAL_F32)

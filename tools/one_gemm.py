@@ -25,9 +25,9 @@ bias = torch.zeros(N, device=dev)
 A = xb if K == D else (torch.randn(M, K, device=dev) * 0.5).to(torch.bfloat16)
 Wb = W.to(torch.bfloat16)
 if which in ("qkv_ln", "fc1_gelu_ln"):
-    w, bb, cs = engine.pack_ln_linear(W, bias, g, b)
+    w, bb = engine.pack_ln_linear(W, bias, g, b)
     out = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
-    fn = lambda: ops.gemm(A, w, bb, out, ops.EPI_GELU_BF16 if "gelu" in which else ops.EPI_BF16, ln_stats=st, ln_colsum=cs)
+    fn = lambda: ops.gemm(A, w, bb, out, ops.EPI_GELU_BF16 if "gelu" in which else ops.EPI_BF16, ln_stats=st)
 elif which in ("qkv", "fc1_gelu"):
     out = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
     fn = lambda: ops.gemm(A, Wb, bias, out, ops.EPI_GELU_BF16 if "gelu" in which else ops.EPI_BF16)
