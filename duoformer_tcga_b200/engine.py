@@ -97,6 +97,9 @@ FORWARD_LN_STATS = True
 # which LayerNorms are forwarded when FORWARD_LN_STATS is on: "norm1" (fc2 -> next block's QKV), "norm2" (proj -> fc1)
 FORWARD_LINKS = ("norm1", "norm2")
 
+# Token rows per chunk of the scale stage (engine.scale_stage).
+SCALE_CHUNK_TOKENS = 1 << 21
+
 STAT_COLS = 256  # columns per forwarded (mean, M2) pair (csrc/gemm_tcgen05.cu kStatCols)
 
 
@@ -138,8 +141,8 @@ def pack_scale_block(precision: str, n1w, n1b, n2w, n2b, qkv, proj, fc1, fc2, g1
     return d
 
 
-def _scale_chunk(X, b0, nb, buf, blocks, num_heads, scale, eps, precision, capture, attn_algo, live_only_last):
-    """All scale blocks for images [b0, b0+nb).
+def _scale_chunk(X, g0, ng, buf, blocks, num_heads, scale, eps, precision, capture, attn_algo, live_only_last):
+    """All scale blocks for the patches (groups of S token rows) [g0, g0+ng) of the flattened batch.
 
     bf16 mode with statistics forwarding, per block (5 launches): QKV GEMM (LayerNorm applied in its epilogue),
     attention, proj GEMM (+residual, emits bf16 rows + statistics), fc1 GEMM (LayerNorm in the epilogue, +GELU),
@@ -151,9 +154,9 @@ def _scale_chunk(X, b0, nb, buf, blocks, num_heads, scale, eps, precision, captu
     fwd1, fwd2 = fwd and "norm1" in FORWARD_LINKS, fwd and "norm2" in FORWARD_LINKS
     kd = 2 if fp32 else 1
     hidden = blocks[0]["fc1"][0].shape[0]
-    T = nb * P * S
+    T = ng * S
     hn_bytes = _align(T * kd * D * 2)
-    Xc = X[b0 : b0 + nb].view(T, D)
+    Xc = X.view(B * P * S, D)[g0 * S : (g0 + ng) * S]
     Ha = Workspace.view(buf, 0, (T, kd * D), torch.bfloat16)             # LayerNorm output / bf16 copy of the stream
     Hb = Workspace.view(buf, hn_bytes, (T, kd * D), torch.bfloat16)      # attention output
     QKV = Workspace.view(buf, 2 * hn_bytes, (T, 3 * D), torch.float32 if fp32 else torch.bfloat16)
@@ -177,7 +180,7 @@ def _scale_chunk(X, b0, nb, buf, blocks, num_heads, scale, eps, precision, captu
             # (scale_attention.py:183-185), so K/V are needed for all tokens but the query,
             # attention output, proj, MLP and both residual updates only for the s = 0 rows
             # (SURVEY.md App. A.3).  X0 is the strided view of those rows inside X.
-            R = nb * P
+            R = ng
             X0 = Xc.view(R, S, D)[:, 0, :]
             A0 = Workspace.view(buf, hn_bytes, (R, kd * D), torch.bfloat16)
             N0 = Workspace.view(buf, 0, (R, kd * D), torch.bfloat16)
@@ -214,8 +217,8 @@ def _scale_chunk(X, b0, nb, buf, blocks, num_heads, scale, eps, precision, captu
             have_ln1 = run_block(i, blk, have_ln1)
 
 
-def _chunk_workspace_bytes(nb, P, S, D, hidden, fp32):
-    T = nb * P * S
+def _chunk_workspace_bytes(ng, S, D, hidden, fp32):
+    T = ng * S
     kd = 2 if fp32 else 1
     stats = 0 if fp32 else _align(T * (D // STAT_COLS) * 8)
     return 2 * _align(T * kd * D * 2) + _align(max(T * 3 * D * (4 if fp32 else 2), T * kd * hidden * 2)) + stats
@@ -231,12 +234,15 @@ def scale_stage(
     ws: Workspace,
     capture: Optional[Dict[str, torch.Tensor]] = None,
     attn_algo: int = 0,
-    max_chunk_tokens: int = 1 << 21,
+    max_chunk_tokens: Optional[int] = None,
     live_only_last: bool = False,
 ) -> torch.Tensor:
     """L x { X += g1*Attn(LN1 X) ; X += g2*MLP(LN2 X) } in place on the fp32 token tensor
     X [B, P, S, D]  (scale_attention.py:90-93 / multiscale_attn.py:282-285).
 
+    The batch is walked in chunks of whole patches (all blocks for one chunk, then the next chunk; every token row
+    only interacts with the S rows of its own patch): max_chunk_tokens (default SCALE_CHUNK_TOKENS) bounds the
+    workspace and decides whether the activations a kernel hands to the next one are still in L2.
     live_only_last: whole-model callers only — the LAST block updates just the s = 0 row of every patch
     (all that MultiscaleFormer / MultiscaleTransformer consume afterwards); the other rows keep their
     pre-block values."""
@@ -245,13 +251,13 @@ def scale_stage(
         return X
     fp32 = precision == "fp32"
     hidden = blocks[0]["fc1"][0].shape[0]
-    tokens_per_image = P * S
-    chunk_images = max(1, min(B, max_chunk_tokens // tokens_per_image))
+    groups = B * P
+    chunk_groups = max(1, min(groups, (max_chunk_tokens or SCALE_CHUNK_TOKENS) // S))
     if capture is not None:
-        chunk_images = B  # captures want whole-batch tensors after every block
-    buf = ws.get(_chunk_workspace_bytes(chunk_images, P, S, D, hidden, fp32))
-    for b0 in range(0, B, chunk_images):
-        _scale_chunk(X, b0, min(chunk_images, B - b0), buf, blocks, num_heads, scale, eps, precision, capture,
+        chunk_groups = groups  # captures want whole-batch tensors after every block
+    buf = ws.get(_chunk_workspace_bytes(chunk_groups, S, D, hidden, fp32))
+    for g0 in range(0, groups, chunk_groups):
+        _scale_chunk(X, g0, min(chunk_groups, groups - g0), buf, blocks, num_heads, scale, eps, precision, capture,
                      attn_algo, live_only_last)
     return X
 

@@ -18,19 +18,23 @@ def env_rank_world() -> Tuple[int, int, int]:
     return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
 
 
-def init_distributed(backend: Optional[str] = None) -> Tuple[int, int, int]:
-    """Initialise torch.distributed from torchrun's environment (no-op for a single process)."""
+def init_distributed(backend: Optional[str] = None, timeout_s: Optional[float] = None) -> Tuple[int, int, int]:
+    """Initialise torch.distributed from torchrun's environment (no-op for a single process).
+    timeout_s: collective timeout (tests use a short one so that a mismatched collective fails fast)."""
     rank, local_rank, world = env_rank_world()
     if world > 1 and not dist.is_initialized():
+        import datetime
+
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
         if backend is None:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
+        kw = {} if timeout_s is None else {"timeout": datetime.timedelta(seconds=timeout_s)}
         if backend == "nccl":
             torch.cuda.set_device(local_rank)
-            dist.init_process_group(backend, rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+            dist.init_process_group(backend, rank=rank, world_size=world, device_id=torch.device("cuda", local_rank), **kw)
         else:
-            dist.init_process_group(backend, rank=rank, world_size=world)
+            dist.init_process_group(backend, rank=rank, world_size=world, **kw)
     return rank, local_rank, world
 
 
@@ -46,18 +50,31 @@ def shard_batch(x: torch.Tensor, rank: int, world: int) -> torch.Tensor:
     return x[lo:hi]
 
 
-def all_gather_logits(local_logits: torch.Tensor, global_batch: Optional[int] = None) -> torch.Tensor:
-    """[B_r, C] per rank -> [sum_r B_r, C] on every rank, rank-major.  Equal shards use one
-    all_gather_into_tensor; ragged shards are padded to the largest shard and trimmed."""
+def all_gather_logits(local_logits: torch.Tensor, global_batch: Optional[int] = None,
+                      ragged: bool = False) -> torch.Tensor:
+    """[B_r, C] per rank -> [sum_r B_r, C] on every rank, rank-major.  Equal shards (the default assumption when
+    global_batch is None) use one all_gather_into_tensor.  Ragged shards are padded to the largest shard and
+    trimmed: their sizes follow from global_batch (shard_bounds), or — ragged=True, sizes only known to their
+    owners — are exchanged first (one extra tiny collective and a host read of the sizes)."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return local_logits
     world = dist.get_world_size()
     C = local_logits.shape[1]
-    if global_batch is None or global_batch % world == 0:
+    if ragged and global_batch is None:
+        mine = torch.tensor([local_logits.shape[0]], dtype=torch.int64, device=local_logits.device)
+        every = torch.empty(world, dtype=torch.int64, device=local_logits.device)
+        dist.all_gather_into_tensor(every, mine)
+        counts = every.tolist()
+        sizes, lo = [], 0
+        for n in counts:
+            sizes.append((lo, lo + n))
+            lo += n
+    elif global_batch is None or global_batch % world == 0:
         out = torch.empty(world * local_logits.shape[0], C, dtype=local_logits.dtype, device=local_logits.device)
         dist.all_gather_into_tensor(out, local_logits.contiguous())
         return out
-    sizes = [shard_bounds(global_batch, r, world) for r in range(world)]
+    else:
+        sizes = [shard_bounds(global_batch, r, world) for r in range(world)]
     mx = max(hi - lo for lo, hi in sizes)
     pad = torch.zeros(mx, C, dtype=local_logits.dtype, device=local_logits.device)
     pad[: local_logits.shape[0]] = local_logits
@@ -91,18 +108,20 @@ class HostPipeline:
     i+1 runs on its own stream while batch i is computed (two device input buffers); the logits of every
     batch are copied to pinned host memory as soon as they exist and handed out one step late, so the
     launch queue of the GPU never drains between batches.  On several GPUs every rank feeds its own
-    shard and receives the gathered logits of the whole step.
+    shard and receives the gathered logits of the whole step (equal shard sizes on all ranks unless ragged=True).
 
         pipe = HostPipeline(model)            # model: cuda, eval
         for logits in pipe.run(batches):      # batches: iterable of (ideally pinned) host tensors [b,3,H,W]
             ...                               # logits: host fp32 [b * world, num_classes]
     """
 
-    def __init__(self, model: torch.nn.Module, device: Optional[torch.device] = None, gather: bool = True):
+    def __init__(self, model: torch.nn.Module, device: Optional[torch.device] = None, gather: bool = True,
+                 ragged: bool = False):
         self.model = model
         self.device = device if device is not None else next(model.parameters()).device
         assert self.device.type == "cuda", "HostPipeline feeds a CUDA model"
         self.gather = gather
+        self.ragged = ragged  # ranks may feed shards of different sizes in one step (sizes exchanged per step)
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self._bufs = [None, None]
         self._consumed = [None, None]  # event: the forward that read buffer k has been enqueued and finished
@@ -153,7 +172,7 @@ class HostPipeline:
             if y.dim() == 1:
                 y = y.unsqueeze(0)
             if self.gather and dist.is_initialized() and dist.get_world_size() > 1:
-                y = all_gather_logits(y)
+                y = all_gather_logits(y, ragged=self.ragged)
             y = y.float()
             y_host = torch.empty(y.shape, dtype=y.dtype, pin_memory=True)
             y_host.copy_(y, non_blocking=True)  # device -> host read of this step's result

@@ -16,7 +16,7 @@ from oracle import synth  # noqa: E402
 
 def main():
     out_dir, batch = sys.argv[1], int(sys.argv[2])
-    rank, local_rank, world = parallel.init_distributed("nccl")
+    rank, local_rank, world = parallel.init_distributed("nccl", timeout_s=120)
     torch.cuda.set_device(local_rank)
     gold = load_golden("wo4_d2")
     model = build_product(gold["case"])
@@ -27,7 +27,7 @@ def main():
     assert y.shape == (batch, 10) and y.is_cuda
     # host-pipeline path too: every rank feeds its own shard, receives the gathered logits
     lo, hi = parallel.shard_bounds(batch, rank, world)
-    piped = list(parallel.HostPipeline(model).run([x[lo:hi].cpu().pin_memory()]))
+    piped = list(parallel.HostPipeline(model, ragged=(batch % world != 0)).run([x[lo:hi].cpu().pin_memory()]))
     torch.save({"y": y.float().cpu(), "piped": piped[0], "device": torch.cuda.current_device()},
                os.path.join(out_dir, f"rank{rank}.pt"))
     torch.distributed.barrier()

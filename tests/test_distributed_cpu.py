@@ -36,6 +36,9 @@ def _worker(rank, world, port, batch, out_dir):
     torch.save(y, os.path.join(out_dir, f"y{rank}.pt"))
     lo, hi = parallel.shard_bounds(batch, rank, world)
     assert parallel.shard_batch(x, rank, world).shape[0] == hi - lo
+    # shard sizes known only to their owners (HostPipeline(ragged=True)): exchanged, padded, trimmed
+    y2 = parallel.all_gather_logits(_ToyModel()(x[lo:hi]), ragged=True)
+    assert torch.equal(y2, y)
     dist.barrier()
     dist.destroy_process_group()
 

@@ -30,7 +30,7 @@ def test_nccl_gathered_logits_equal_single_gpu_rank_major(tmp_path, batch):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
            os.path.join(ROOT, "tests", "dist_worker.py"), str(tmp_path), str(batch)]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=400)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     gold = load_golden("wo4_d2")
     model = build_product(gold["case"])
