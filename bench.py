@@ -217,10 +217,12 @@ def main():
         ops.launch_count_reset()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        torch.cuda.nvtx.range_push("duo/bench_timed")  # ncu --nvtx --nvtx-include "duo/bench_timed/" profiles exactly this region
         e0.record()
         for _ in range(steps):
             y = step_resident()
         e1.record()
+        torch.cuda.nvtx.range_pop()
         barrier()
         launches = ops.launch_count()
         clocks = sampler.stop() if rank == 0 else None

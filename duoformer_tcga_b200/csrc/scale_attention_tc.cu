@@ -200,22 +200,28 @@ scale_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfl
       for (int j = 0; j < 32; ++j)
         if (64 + j < S) mx = fmaxf(mx, __uint_as_float(v2[j]));
       const float off = mx * scale_log2e;
-      float sum = 0.f;
-      // probabilities, 8 keys (one 16-byte chunk of the P row) at a time
+      // probabilities, 8 keys (one 16-byte chunk of the P row) at a time; the scaling and the row sum run on packed
+      // fp32 pairs (FFMA2 / FADD2: half the issue slots of the scalar form — the kernel is issue / latency bound at
+      // the ~1.1 GHz the power-capped step runs at)
+      const uint64_t sc2 = pack2(scale_log2e, scale_log2e), noff2 = pack2(-off, -off);
+      uint64_t sum2 = pack2(0.f, 0.f);
       auto emit = [&](const uint32_t (&v)[32], int key0, uint32_t tile) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          float p[8];
+          uint32_t w[4];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int key = key0 + 8 * c + j;
-            p[j] = key < S ? ex2_approx(fmaf(__uint_as_float(v[8 * c + j]), scale_log2e, -off)) : 0.f;
-            sum += p[j];
+          for (int j = 0; j < 4; ++j) {
+            const int key = key0 + 8 * c + 2 * j;
+            float e0, e1;
+            unpack2(fma2(pack2(__uint_as_float(v[8 * c + 2 * j]), __uint_as_float(v[8 * c + 2 * j + 1])), sc2, noff2), e0, e1);
+            const float p0 = key < S ? ex2_approx(e0) : 0.f;
+            const float p1 = key + 1 < S ? ex2_approx(e1) : 0.f;
+            sum2 = add2(sum2, pack2(p0, p1));
+            w[j] = pack_bf16x2(p0, p1);
           }
           const uint32_t kc = static_cast<uint32_t>(((key0 & 63) >> 3) + c);
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile + static_cast<uint32_t>(r) * 128u + ((kc ^ x7) << 4)),
-                       "r"(pack_bf16x2(p[0], p[1])), "r"(pack_bf16x2(p[2], p[3])), "r"(pack_bf16x2(p[4], p[5])),
-                       "r"(pack_bf16x2(p[6], p[7]))
+                       "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
                        : "memory");
         }
       };
@@ -235,21 +241,23 @@ scale_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfl
       ptx::tc_fence_before();
       {
         // O row -> this thread's (dead) P row, then the warp stores four complete 128-byte rows per instruction
-        const float inv = 1.0f / sum;
+        float sum_a, sum_b;
+        unpack2(sum2, sum_a, sum_b);
+        const float inv = 1.0f / (sum_a + sum_b);
+        const uint64_t inv2 = pack2(inv, inv);
         const uint32_t my_row = p_base + static_cast<uint32_t>(r) * 128u;
+        auto scaled = [&](const uint32_t (&v)[32], int i) {  // bf16x2 of (v[i], v[i+1]) * inv
+          float a, b;
+          unpack2(mul2(pack2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), inv2), a, b);
+          return pack_bf16x2(a, b);
+        };
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + ((static_cast<uint32_t>(c) ^ x7) << 4)),
-                       "r"(pack_bf16x2(__uint_as_float(v0[8 * c + 0]) * inv, __uint_as_float(v0[8 * c + 1]) * inv)),
-                       "r"(pack_bf16x2(__uint_as_float(v0[8 * c + 2]) * inv, __uint_as_float(v0[8 * c + 3]) * inv)),
-                       "r"(pack_bf16x2(__uint_as_float(v0[8 * c + 4]) * inv, __uint_as_float(v0[8 * c + 5]) * inv)),
-                       "r"(pack_bf16x2(__uint_as_float(v0[8 * c + 6]) * inv, __uint_as_float(v0[8 * c + 7]) * inv))
+                       "r"(scaled(v0, 8 * c)), "r"(scaled(v0, 8 * c + 2)), "r"(scaled(v0, 8 * c + 4)), "r"(scaled(v0, 8 * c + 6))
                        : "memory");
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + ((static_cast<uint32_t>(4 + c) ^ x7) << 4)),
-                       "r"(pack_bf16x2(__uint_as_float(v1[8 * c + 0]) * inv, __uint_as_float(v1[8 * c + 1]) * inv)),
-                       "r"(pack_bf16x2(__uint_as_float(v1[8 * c + 2]) * inv, __uint_as_float(v1[8 * c + 3]) * inv)),
-                       "r"(pack_bf16x2(__uint_as_float(v1[8 * c + 4]) * inv, __uint_as_float(v1[8 * c + 5]) * inv)),
-                       "r"(pack_bf16x2(__uint_as_float(v1[8 * c + 6]) * inv, __uint_as_float(v1[8 * c + 7]) * inv))
+                       "r"(scaled(v1, 8 * c)), "r"(scaled(v1, 8 * c + 2)), "r"(scaled(v1, 8 * c + 4)), "r"(scaled(v1, 8 * c + 6))
                        : "memory");
         }
         __syncwarp();
