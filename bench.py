@@ -217,7 +217,7 @@ def main():
         ops.launch_count_reset()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
-        torch.cuda.nvtx.range_push("duo/bench_timed")  # ncu --nvtx --nvtx-include "duo/bench_timed/" profiles exactly this region
+        torch.cuda.nvtx.range_push("duo.bench_timed")  # ncu --nvtx --nvtx-include "duo.bench_timed/" profiles exactly this region
         e0.record()
         for _ in range(steps):
             y = step_resident()

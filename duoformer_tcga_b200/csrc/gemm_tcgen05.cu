@@ -889,15 +889,8 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const uint32_t s = gi % kFwdSlots;
         const uint32_t bar = x_bar(warp_idx * kFwdSlots + static_cast<int>(s));
         ptx::mbar_arrive_expect_tx(bar, kFwdXBytes);
-#ifndef DUO_FWD_X_EVICT_FIRST
-#define DUO_FWD_X_EVICT_FIRST 1
-#endif
-        // X is read exactly once per launch: L2 evict-first keeps it from displacing the A panels the N tiles of a
-        // row panel share (ncu, fc2: 13.0 GB of DRAM reads against 9.9 GB algorithmic without the hint)
-        if (DUO_FWD_X_EVICT_FIRST)
-          ptx::tma_load_2d_hint(xbuf0 + s * kFwdXBytes, &tmap_out, bar, c, r, 0x12F0000000000000ull);
-        else
-          ptx::tma_load_2d(xbuf0 + s * kFwdXBytes, &tmap_out, bar, c, r);
+        // (an L2 evict-first hint on these read-once loads was measured: proj 0.424 -> 0.481 ms per 64 images, fc2 unchanged)
+        ptx::tma_load_2d(xbuf0 + s * kFwdXBytes, &tmap_out, bar, c, r);
       };
       if (lane == 0) {
 #pragma unroll

@@ -27,7 +27,7 @@ PRECISIONS = ("bf16", "fp32")
 def nvtx(name: str):
     """NVTX range around a stage of the forward (trunk / token builder / scale block i / patch stage / head): shows
     up on the timeline of nsys / ncu --nvtx; a host-side marker only (safe under CUDA-graph capture, ~100 ns idle)."""
-    torch.cuda.nvtx.range_push("duo/" + name)
+    torch.cuda.nvtx.range_push("duo." + name)
     try:
         yield
     finally:

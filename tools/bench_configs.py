@@ -13,6 +13,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import duoformer_tcga_b200 as duo  # noqa: E402
+from duoformer_tcga_b200 import ops  # noqa: E402
 
 COMMON = dict(embed_dim=768, num_heads=12, num_classes=10, proj_dim=768)
 
@@ -53,8 +54,23 @@ def main():
         m = m.cuda().eval().set_precision(prec)
         x = torch.randn(B, 3, size, size, device="cuda")
         ms, y = timeit(m, x)
+        # one profiled forward: CUDA events around every GEMM / LayerNorm / attention launch of the library
+        prof = []
+        ops.PROFILE = prof
+        with torch.no_grad():
+            m(x)
+        ops.PROFILE = None
+        torch.cuda.synchronize()
+        by_tag = {}
+        for a, b, kind, fl, nb, tag in prof:
+            t = by_tag.setdefault(f"{kind}:{tag}", [0.0, 0])
+            t[0] += a.elapsed_time(b)
+            t[1] += 1
+        top = sorted(by_tag.items(), key=lambda kv: -kv[1][0])[:8]
         r = {"config": name, "batch": B, "ms_per_forward": round(ms, 3), "images_per_s": round(B / ms * 1000, 1),
-             "finite": bool(torch.isfinite(y).all()), "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2**30, 2)}
+             "finite": bool(torch.isfinite(y).all()), "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2**30, 2),
+             "library_ms_by_launch_kind": {k: {"ms": round(v[0], 3), "launches": v[1]} for k, v in top},
+             "library_ms_total": round(sum(v[0] for v in by_tag.values()), 3)}
         print(json.dumps(r), flush=True)
         out.append(r)
         del m, x, y

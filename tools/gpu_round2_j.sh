@@ -10,7 +10,7 @@ for v in "" _fwd_nohint; do
   timeout 300 python tools/bench_kernels.py --images 64 --only fwd --lib duoformer_tcga_b200/libduoformer_sm100$v.so --tag _j2$v > gpurun_out/j2_bench_kernels$v.log 2>&1
 done
 B="bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-library-bar"
-timeout 900 ncu --nvtx --nvtx-include "duo/bench_timed/" --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02_launches.csv python $B > gpurun_out/j_ncu_launches.log 2>&1; echo "ncu_launches rc=$?" >> $S
+timeout 900 ncu --nvtx --nvtx-include "duo.bench_timed/" --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02_launches.csv python $B > gpurun_out/j_ncu_launches.log 2>&1; echo "ncu_launches rc=$?" >> $S
 timeout 900 python bench.py > gpurun_out/j_bench.json 2> gpurun_out/j_bench.err; echo "bench rc=$?" >> $S
 cat $S; tail -3 gpurun_out/j_kernels.log
 for f in j_bench_kernels j_bench_kernels_fwd_nohint j2_bench_kernels j2_bench_kernels_fwd_nohint; do echo "== $f"; grep -E "residual|attention" gpurun_out/$f.log | python -c "
