@@ -663,6 +663,156 @@ int launch_mma(const void* qkv, void* out, int64_t groups, int S, int H, float s
   return DUO_OK;
 }
 
+
+// =============================== algo 4: small groups (S <= 8) ==============================
+// The 2-scale model's scale attention: S = 6 tokens per patch.  One WARP per (patch, head) problem, eight problems
+// per CTA pass, persistent grid-stride loop.  Everything lives in registers between two warp-level steps:
+//   * the head slices of Q, K, V (S rows x 128 B each, 2.3 KB per problem) come in with coalesced 16-byte cp.async
+//     into the warp's private 4 KB of shared memory (Q padded to 16 rows, K / V to 8 rows; the padding rows are
+//     zeroed once and never written);
+//   * scores = Q K^T as 4 x mma.sync.m16n8k16 (one 8-key tile), softmax on the accumulator fragment — the 6 scores
+//     of a row sit in one quad (3 lanes x 2), so max and sum are two xor-shuffles each —, the probabilities become
+//     the A fragment of O = P V (8 x m16n8k16 whose upper k half is zero) without leaving registers;
+//   * the 6 x 64 output is transposed through the warp's (dead) Q rows and stored as complete 128-byte rows.
+// ~120 instructions per problem (the generic FMA kernel: ~650, with 26 of 32 lanes idle in the score phase), so
+// the kernel is bound by its 2.3 KB + 0.8 KB of HBM traffic per problem: 24 warps per SM keep ~55 KB in flight.
+constexpr int kSmallWarps = 8;
+constexpr uint32_t kSmallWarpBytes = 4096;  // Q: 16 rows | K: 8 rows | V: 8 rows, 128 B each
+
+__device__ __forceinline__ void mma_bf16_16816_lo(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+  // A columns 8..15 and B rows 8..15 are zero (keys 8..15 do not exist)
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %6}, "
+      "{%7, %6}, {%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(0u), "r"(b0));
+}
+
+template <int S_CT>
+__global__ void __launch_bounds__(kSmallWarps * 32, 3)
+group_attention_small_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
+                             int64_t problems, int S_rt, int H, float scale_log2e, int q_rows) {
+  const int S = S_CT > 0 ? S_CT : S_rt;
+  __shared__ __align__(128) uint8_t smem[kSmallWarps * kSmallWarpBytes];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t sQ = static_cast<uint32_t>(__cvta_generic_to_shared(smem)) + static_cast<uint32_t>(warp) * kSmallWarpBytes;
+  const uint32_t sK = sQ + 16 * 128;
+  const uint32_t sV = sK + 8 * 128;
+  for (uint32_t off = static_cast<uint32_t>(lane) * 16; off < kSmallWarpBytes; off += 32 * 16)
+    asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(sQ + off), "r"(0u) : "memory");
+  __syncwarp();
+
+  const int D = H * kHeadDim;
+  const int64_t ld = 3 * static_cast<int64_t>(D);
+  const int gq = lane >> 2;  // fragment row (query) / B column (key or output dim)
+  const int tq = lane & 3;   // fragment column pair
+  const uint32_t x7 = static_cast<uint32_t>(lane & 7);
+  // ldmatrix lane addresses (row & 7 == lane & 7 for all of them)
+  uint32_t q_off[4], k_off[2], v_off[2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)  // Q, k-step i: matrices (rows 0-7 | 8-15) x (chunk 2i | 2i+1)
+    q_off[i] = static_cast<uint32_t>(((lane & 7) + ((lane >> 3) & 1) * 8) * 128) + (((2 * i + (lane >> 4)) ^ x7) << 4);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {  // K: chunks 4i .. 4i+3 of keys 0-7 (k-steps 2i, 2i+1); V (transposed): the same
+    k_off[i] = static_cast<uint32_t>((lane & 7) * 128) + (((4 * i + (lane >> 3)) ^ x7) << 4);
+    v_off[i] = k_off[i];
+  }
+  const int stage_chunks = 24 * S;  // 3 slices x S rows x 8 chunks of 16 bytes
+  const int out_chunks = 8 * q_rows;
+
+  for (int64_t prob = static_cast<int64_t>(blockIdx.x) * kSmallWarps + warp; prob < problems;
+       prob += static_cast<int64_t>(gridDim.x) * kSmallWarps) {
+    const int64_t g = prob / H;
+    const int h = static_cast<int>(prob - g * H);
+    const __nv_bfloat16* base = qkv + (g * S) * ld + h * kHeadDim;
+    for (int idx = lane; idx < stage_chunks; idx += 32) {
+      const int which = idx / (8 * S);
+      const int rem = idx - which * 8 * S;
+      const int r = rem >> 3, c = rem & 7;
+      const uint32_t dst = (which == 0 ? sQ : (which == 1 ? sK : sV)) + swz(r, c);
+      cp_async_16(dst, base + which * D + static_cast<int64_t>(r) * ld + c * 8);
+    }
+    cp_async_wait_all();
+    __syncwarp();
+
+    // ---- scores = Q K^T: one 8-key tile, 4 k-steps ----
+    float sc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int kp = 0; kp < 2; ++kp) {
+      uint32_t kb0, kb1, kb2, kb3;  // (k-step 2kp: b0, b1), (k-step 2kp+1: b0, b1)
+      ldmatrix_x4(sK + k_off[kp], kb0, kb1, kb2, kb3);
+      uint32_t qa[4];
+      ldmatrix_x4(sQ + q_off[2 * kp], qa[0], qa[1], qa[2], qa[3]);
+      mma_bf16_16816(sc, qa, kb0, kb1);
+      ldmatrix_x4(sQ + q_off[2 * kp + 1], qa[0], qa[1], qa[2], qa[3]);
+      mma_bf16_16816(sc, qa, kb2, kb3);
+    }
+    // ---- softmax over the keys of row gq (sc[0], sc[1]); rows 8..15 (sc[2], sc[3]) are padding queries ----
+    const int col = 2 * tq;
+    float s0 = col < S ? sc[0] : -INFINITY;
+    float s1 = col + 1 < S ? sc[1] : -INFINITY;
+    float mx = fmaxf(s0, s1);
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    const float off = mx * scale_log2e;
+    const float p0 = col < S ? ex2_approx(fmaf(s0, scale_log2e, -off)) : 0.f;
+    const float p1 = col + 1 < S ? ex2_approx(fmaf(s1, scale_log2e, -off)) : 0.f;
+    float sum = p0 + p1;
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    const float inv = 1.0f / sum;
+    const uint32_t pa0 = pack_bf16x2(p0, p1);  // A fragment of P: row gq, keys 2tq, 2tq+1 (rows 8..15: unused)
+
+    // ---- O = P V: 8 output tiles of 8 dims, keys 0..7 only ----
+    float o[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
+#pragma unroll
+    for (int dq = 0; dq < 2; ++dq) {
+      uint32_t vb0, vb1, vb2, vb3;  // keys 0-7 x dims of chunks 4dq .. 4dq+3, transposed
+      ldmatrix_x4_trans(sV + v_off[dq], vb0, vb1, vb2, vb3);
+      mma_bf16_16816_lo(o[4 * dq + 0], pa0, 0u, vb0);
+      mma_bf16_16816_lo(o[4 * dq + 1], pa0, 0u, vb1);
+      mma_bf16_16816_lo(o[4 * dq + 2], pa0, 0u, vb2);
+      mma_bf16_16816_lo(o[4 * dq + 3], pa0, 0u, vb3);
+    }
+    // ---- row gq of O -> the warp's Q row gq (dead), then complete 128-byte rows to global ----
+    __syncwarp();
+    if (gq < S) {
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(sQ + swz(gq, nt) + 4u * static_cast<uint32_t>(tq)),
+                     "r"(pack_bf16x2(o[nt][0] * inv, o[nt][1] * inv))
+                     : "memory");
+    }
+    __syncwarp();
+    __nv_bfloat16* obase = out + (g * q_rows) * D + h * kHeadDim;
+    for (int idx = lane; idx < out_chunks; idx += 32) {
+      const int r = idx >> 3, c = idx & 7;
+      uint32_t w0, w1, w2, w3;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(sQ + swz(r, c)));
+      *reinterpret_cast<uint4*>(obase + static_cast<int64_t>(r) * D + c * 8) = make_uint4(w0, w1, w2, w3);
+    }
+    __syncwarp();  // the staging rows are free for the next problem's loads
+  }
+}
+
+int launch_small(const void* qkv, void* out, int64_t groups, int S, int H, float scale, int q_rows, cudaStream_t st) {
+  const int64_t problems = groups * H;
+  const int64_t ctas_needed = (problems + kSmallWarps - 1) / kSmallWarps;
+  const int64_t ctas_max = 3LL * device_sm_count();
+  const unsigned grid = static_cast<unsigned>(ctas_needed < ctas_max ? ctas_needed : ctas_max);
+  const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(qkv);
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+  if (S == 6)
+    group_attention_small_kernel<6><<<grid, kSmallWarps * 32, 0, st>>>(q, o, problems, S, H, scale * 1.4426950408889634f, q_rows);
+  else
+    group_attention_small_kernel<0><<<grid, kSmallWarps * 32, 0, st>>>(q, o, problems, S, H, scale * 1.4426950408889634f, q_rows);
+  DUO_LAUNCH_CHECK("group_attention_small_kernel");
+  return DUO_OK;
+}
+
 }  // namespace
 }  // namespace duo
 
@@ -693,8 +843,14 @@ extern "C" int duo_group_attention(const void* qkv, int32_t in_kind, void* out, 
     return launch_patch_attention_tc(qkv, out, num_groups, S, num_heads, scale, st);
   }
   const bool mma_ok = in_kind == DUO_ACT_BF16 && out_kind == DUO_ACT_BF16 && S > 16 && S <= 96;
-  // auto: tcgen05 kernel for the 4-scale group size, mma.sync kernel for the other tensor-core sizes
-  if (algo == 0) algo = (mma_ok && S > 64 && q_rows == S) ? 3 : (mma_ok ? 2 : 1);
+  const bool small_ok = in_kind == DUO_ACT_BF16 && out_kind == DUO_ACT_BF16 && S <= 8;
+  // auto: tcgen05 kernel for the 4-scale group size, mma.sync kernel for the other tensor-core sizes, the
+  // warp-per-(patch, head) register kernel for the 2-scale group size
+  if (algo == 0) algo = (mma_ok && S > 64 && q_rows == S) ? 3 : (mma_ok ? 2 : (small_ok ? 4 : 1));
+  if (algo == 4) {
+    DUO_CHECK_ARG(small_ok, "duo_group_attention: algo 4 needs bf16 in/out and S <= 8 (S=%d)", S);
+    return launch_small(qkv, out, num_groups, S, num_heads, scale, q_rows, st);
+  }
   if (algo == 3) {  // tcgen05 / TMEM kernel (scale_attention_tc.cu)
     DUO_CHECK_ARG(mma_ok && S > 64 && q_rows == S,
                   "duo_group_attention: algo 3 needs bf16 in/out, 64 < S <= 96 and q_rows == S (S=%d q_rows=%d)", S, q_rows);

@@ -147,7 +147,9 @@ int duo_layernorm(const float* x, const float* gamma, const float* beta, void* o
  * algo: 0 = auto, 1 = warp-per-(group,head) register/shuffle FMA kernel (any S <= 160),
  *       2 = warp-level tensor-core (mma.sync) kernel (bf16 in, bf16 out, 16 < S <= 96),
  *       3 = tcgen05 / TMEM kernel (bf16 in, bf16 out, 64 < S <= 96, q_rows == S: the 4-scale
- *           group size S = 86; auto picks it whenever it applies).
+ *           group size S = 86; auto picks it whenever it applies),
+ *       4 = warp-per-(group, head) register kernel for S <= 8 (bf16 in, bf16 out: the 2-scale group size S = 6;
+ *           mma.sync fragments in registers, softmax by quad shuffles; auto picks it whenever it applies).
  * q_rows: only the first q_rows query rows of every group are computed and `out` is the dense
  *       [num_groups * q_rows, D] matrix of those rows (q_rows = S: everything; q_rows = 1: the
  *       scale-token / CLS query only — all that the reference consumes after the LAST scale

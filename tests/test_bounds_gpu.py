@@ -87,7 +87,7 @@ def test_token_scatter_stays_inside_the_token_tensor(B):
     assert not bool((X.t.view(torch.uint8) == SENTINEL).view(B, -1).all(dim=1).any())  # but no image is left untouched)
 
 
-@pytest.mark.parametrize("S,G,algo,q_rows", [(86, 49 * 3 + 1, 3, 0), (86, 5, 2, 0), (86, 5, 2, 1), (22, 51, 2, 0), (6, 99, 1, 0),
+@pytest.mark.parametrize("S,G,algo,q_rows", [(86, 49 * 3 + 1, 3, 0), (86, 5, 2, 0), (86, 5, 2, 1), (22, 51, 2, 0), (6, 99, 1, 0), (6, 99, 4, 0), (6, 13, 4, 1), (3, 7, 4, 0),
                                              (50, 3, 1, 1), (145, 2, 1, 0)])
 def test_attention_outputs_stay_inside(S, G, algo, q_rows):
     D, H = 768, 12

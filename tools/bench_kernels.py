@@ -147,8 +147,10 @@ def main():
 
     qkv = (torch.randn(M, 3 * D, device=dev)).to(torch.bfloat16)
     ao = torch.empty(M, D, dtype=torch.bfloat16, device=dev)
-    for algo in (3, 2, 1):
+    for algo in (4, 3, 2, 1):
         if a.only and "attn" not in a.only:
+            continue
+        if algo == 4 and S > 8:
             continue
         if algo == 2 and not (16 < S <= 96):
             continue
