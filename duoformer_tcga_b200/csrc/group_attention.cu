@@ -675,9 +675,11 @@ int launch_mma(const void* qkv, void* out, int64_t groups, int S, int H, float s
 //     the A fragment of O = P V (8 x m16n8k16 whose upper k half is zero) without leaving registers;
 //   * the 6 x 64 output is transposed through the warp's (dead) Q rows and stored as complete 128-byte rows.
 // ~120 instructions per problem (the generic FMA kernel: ~650, with 26 of 32 lanes idle in the score phase), so
-// the kernel is bound by its 2.3 KB + 0.8 KB of HBM traffic per problem: 24 warps per SM keep ~55 KB in flight.
+// the kernel is bound by its 2.3 KB + 0.8 KB of HBM traffic per problem: every warp double-buffers its staging
+// area (the next problem's cp.async loads fly while the current one is computed), 24 warps per SM.
 constexpr int kSmallWarps = 8;
-constexpr uint32_t kSmallWarpBytes = 4096;  // Q: 16 rows | K: 8 rows | V: 8 rows, 128 B each
+constexpr uint32_t kSmallBufBytes = 4096;   // Q: 16 rows | K: 8 rows | V: 8 rows, 128 B each
+constexpr uint32_t kSmallWarpBytes = 2 * kSmallBufBytes;
 
 __device__ __forceinline__ void mma_bf16_16816_lo(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
   // A columns 8..15 and B rows 8..15 are zero (keys 8..15 do not exist)
@@ -693,14 +695,12 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 3)
 group_attention_small_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
                              int64_t problems, int S_rt, int H, float scale_log2e, int q_rows) {
   const int S = S_CT > 0 ? S_CT : S_rt;
-  __shared__ __align__(128) uint8_t smem[kSmallWarps * kSmallWarpBytes];
+  extern __shared__ __align__(128) uint8_t smem_small[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t sQ = static_cast<uint32_t>(__cvta_generic_to_shared(smem)) + static_cast<uint32_t>(warp) * kSmallWarpBytes;
-  const uint32_t sK = sQ + 16 * 128;
-  const uint32_t sV = sK + 8 * 128;
+  const uint32_t s_warp = static_cast<uint32_t>(__cvta_generic_to_shared(smem_small)) + static_cast<uint32_t>(warp) * kSmallWarpBytes;
   for (uint32_t off = static_cast<uint32_t>(lane) * 16; off < kSmallWarpBytes; off += 32 * 16)
-    asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(sQ + off), "r"(0u) : "memory");
+    asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(s_warp + off), "r"(0u) : "memory");
   __syncwarp();
 
   const int D = H * kHeadDim;
@@ -720,20 +720,36 @@ group_attention_small_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat1
   }
   const int stage_chunks = 24 * S;  // 3 slices x S rows x 8 chunks of 16 bytes
   const int out_chunks = 8 * q_rows;
-
-  for (int64_t prob = static_cast<int64_t>(blockIdx.x) * kSmallWarps + warp; prob < problems;
-       prob += static_cast<int64_t>(gridDim.x) * kSmallWarps) {
-    const int64_t g = prob / H;
-    const int h = static_cast<int>(prob - g * H);
-    const __nv_bfloat16* base = qkv + (g * S) * ld + h * kHeadDim;
+  auto stage = [&](int64_t pr, uint32_t buf) {  // cp.async the Q | K | V head slices of problem pr into buffer buf
+    const int64_t pg = pr / H;
+    const int ph = static_cast<int>(pr - pg * H);
+    const __nv_bfloat16* src = qkv + (pg * S) * ld + ph * kHeadDim;
     for (int idx = lane; idx < stage_chunks; idx += 32) {
       const int which = idx / (8 * S);
       const int rem = idx - which * 8 * S;
       const int r = rem >> 3, c = rem & 7;
-      const uint32_t dst = (which == 0 ? sQ : (which == 1 ? sK : sV)) + swz(r, c);
-      cp_async_16(dst, base + which * D + static_cast<int64_t>(r) * ld + c * 8);
+      const uint32_t dst = buf + (which == 0 ? 0u : (which == 1 ? 16u * 128u : 24u * 128u)) + swz(r, c);
+      cp_async_16(dst, src + which * D + static_cast<int64_t>(r) * ld + c * 8);
     }
-    cp_async_wait_all();
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  const int64_t first = static_cast<int64_t>(blockIdx.x) * kSmallWarps + warp;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * kSmallWarps;
+  if (first < problems) stage(first, s_warp);
+  uint32_t cur = 0;
+
+  for (int64_t prob = first; prob < problems; prob += stride, cur ^= 1u) {
+    const int64_t g = prob / H;
+    const int h = static_cast<int>(prob - g * H);
+    const uint32_t sQ = s_warp + cur * kSmallBufBytes;
+    const uint32_t sK = sQ + 16 * 128;
+    const uint32_t sV = sK + 8 * 128;
+    if (prob + stride < problems) {  // the other buffer's previous user finished with the __syncwarp below
+      stage(prob + stride, s_warp + (cur ^ 1u) * kSmallBufBytes);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
     __syncwarp();
 
     // ---- scores = Q K^T: one 8-key tile, 4 k-steps ----
@@ -805,10 +821,16 @@ int launch_small(const void* qkv, void* out, int64_t groups, int S, int H, float
   const unsigned grid = static_cast<unsigned>(ctas_needed < ctas_max ? ctas_needed : ctas_max);
   const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(qkv);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+  constexpr int kSmem = kSmallWarps * kSmallWarpBytes;  // 64 KB: three CTAs per SM
+  static uint64_t configured = 0;  // per device
+  if (first_use_on_device(configured)) {
+    DUO_CUDA(cudaFuncSetAttribute(group_attention_small_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    DUO_CUDA(cudaFuncSetAttribute(group_attention_small_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+  }
   if (S == 6)
-    group_attention_small_kernel<6><<<grid, kSmallWarps * 32, 0, st>>>(q, o, problems, S, H, scale * 1.4426950408889634f, q_rows);
+    group_attention_small_kernel<6><<<grid, kSmallWarps * 32, kSmem, st>>>(q, o, problems, S, H, scale * 1.4426950408889634f, q_rows);
   else
-    group_attention_small_kernel<0><<<grid, kSmallWarps * 32, 0, st>>>(q, o, problems, S, H, scale * 1.4426950408889634f, q_rows);
+    group_attention_small_kernel<0><<<grid, kSmallWarps * 32, kSmem, st>>>(q, o, problems, S, H, scale * 1.4426950408889634f, q_rows);
   DUO_LAUNCH_CHECK("group_attention_small_kernel");
   return DUO_OK;
 }
