@@ -2,15 +2,19 @@
 // group and head_dim 64 — the S = 86 case of the 4-scale model (scale_attention.py:28-45,
 // multiscale_attn.py:149-166: softmax(q k^T * scale) v inside every (patch, head)).
 //
-// One persistent CTA of eight warps walks (group, head) problems; two CTAs share an SM.
+// One persistent CTA of four warps walks (group, head) problems; two CTAs share an SM.
 //   warp 3   : lane 0 issues TMA loads (Q, K, V head slices, one box of S rows x 128 B each,
-//              double-buffered) and all tcgen05.mma; the whole warp transposes V (keys 0..47) into the K-major
-//              V^T operand (ldmatrix.trans -> st.shared) while the scores are being computed; warp 7 does keys 48..95.
-//   warps 0-2, 4-6: two threads per query row (see the kernel).  scores from TMEM (tcgen05.ld) -> softmax in
-//              registers -> P (bf16) into shared memory -> after the second MMA, O from TMEM, scaled by 1/sum,
-//              transposed through the thread's own (dead) P columns and stored as 64-byte half rows.
+//              double-buffered) and all tcgen05.mma; the whole warp transposes V into the K-major
+//              V^T operand (ldmatrix.trans -> st.shared) while the scores are being computed.
+//   warps 0-2: thread = query row.  scores from TMEM (tcgen05.ld) -> softmax in registers (no
+//              shuffles) -> P (bf16) into shared memory -> after the second MMA, O from TMEM,
+//              scaled by 1/sum, transposed through the warp's (dead) P rows and stored as full
+//              128-byte lines.
 // Loads run two problems ahead: a buffer is refilled as soon as its Q/K have been multiplied and
 // its V transposed.
+// (Measured and dropped in round 2: two threads per query row — eight warps per CTA splitting the score / output
+// columns, a named barrier per row quarter for the maximum, a helper warp for half of the V transpose: 0.303 ms per 64
+// images against 0.270 alone, 22.4 against 17.8 ms per step.)
 //   MMA 1    : S[128 x 96] = Q[128 x 64] K^T          4 x UMMA 128x96x16, accumulator columns [0, 96)
 //   MMA 2    : O[128 x 64] = P[128 x 96] V^T^T        ceil(S/16) x UMMA 128x64x16, columns [128, 192)
 // Rows >= S of the M = 128 operands are whatever follows them in shared memory: they only feed
@@ -41,29 +45,9 @@ __device__ __forceinline__ void ldmatrix_x4_t(uint32_t addr, uint32_t& r0, uint3
                : "r"(addr));
 }
 
-// Named barrier of the two warps (64 threads) that share row quarter q (immediate ids 1..3: the kernel then reserves
-// four hardware barriers, not all sixteen).
-__device__ __forceinline__ void pair_barrier_sync(int q) {
-  if (q == 0)
-    asm volatile("bar.sync 1, 64;" ::: "memory");
-  else if (q == 1)
-    asm volatile("bar.sync 2, 64;" ::: "memory");
-  else
-    asm volatile("bar.sync 3, 64;" ::: "memory");
-}
-
 // S_CT > 0: S known at compile time (the model's 86); 0: runtime S.
-//
-// 256 threads.  Softmax / output warps come in pairs (w, w + 4), w = 0..2: both own TMEM lanes (query rows)
-// [32w, 32w + 32) — the lane quarter a warp may read is warp_id % 4 — and split the columns: the "low" warp takes
-// keys [0, 32) + [64, 80) and output dims [0, 32), the "high" warp keys [32, 64) + [80, 96) and dims [32, 64).  With one
-// row per thread the kernel was bound by dependent-issue latency at the ~1.1 GHz of the power-capped step (ncu: issue
-// slots 38 % busy, 2 warps per scheduler); two threads per row halve every thread's chain and double the warps in
-// flight.  The pair meets once per problem (named barrier) to agree on the row maximum; the partial row sums are
-// exchanged through the same 16-byte slot (unused columns of the second P tile) and ordered by the p_ready / o_full
-// barriers.  Warp 3 is the control warp (TMA, MMA issue, V^T of keys [0, 48)), warp 7 transposes keys [48, 96).
 template <int S_CT>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(128, 2)
 scale_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __restrict__ out,
                           int S_rt, int H, int64_t problems, float scale_log2e) {
   const int S = S_CT > 0 ? S_CT : S_rt;
@@ -74,7 +58,7 @@ scale_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfl
   const uint32_t vt_base = p_base + kPBytes;
   const uint32_t bar_base = base + kSmemData;
   const uint32_t full_bar0 = bar_base, s_full = bar_base + 16, p_ready = bar_base + 24, o_full = bar_base + 32;
-  const uint32_t tmem_slot = bar_base + 40, vt_ready = bar_base + 48;
+  const uint32_t tmem_slot = bar_base + 40;
   uint32_t* tmem_slot_generic = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5;
@@ -84,7 +68,7 @@ scale_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfl
   const int nk = (S + 15) >> 4;  // 16-key steps of the second MMA
 
   // V padding rows of both buffers: zero once
-  for (int i = threadIdx.x; i < 2 * (kKeysPad - S) * 8; i += blockDim.x) {
+  for (int i = threadIdx.x; i < 2 * (kKeysPad - S) * 8; i += 128) {
     const int b = i / ((kKeysPad - S) * 8);
     const int j = i - b * (kKeysPad - S) * 8;
     const uint32_t dst = base + b * kBuf + 2 * kTile + static_cast<uint32_t>((S + (j >> 3)) * 128 + ((j & 7) << 4));
@@ -96,9 +80,8 @@ scale_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfl
       ptx::mbar_init(full_bar0, 1);
       ptx::mbar_init(full_bar0 + 8, 1);
       ptx::mbar_init(s_full, 1);
-      ptx::mbar_init(p_ready, 6);  // one arrival per softmax warp
+      ptx::mbar_init(p_ready, 3);  // one arrival per softmax warp
       ptx::mbar_init(o_full, 1);
-      ptx::mbar_init(vt_ready, 1);  // warp 7: its half of V^T is in place
       ptx::fence_barrier_init();
     }
     __syncwarp();
@@ -121,34 +104,12 @@ scale_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfl
     ptx::tma_load_2d(dst + kTile, &tmap_qkv, bar, D + h * kDh, row);
     ptx::tma_load_2d(dst + 2 * kTile, &tmap_qkv, bar, 2 * D + h * kDh, row);
   };
-  // V[key][d] -> V^T[d][key] (K-major, 128B swizzle, two blocks of 64 keys) for the 8-key groups [kb_begin, kb_end)
-  auto transpose_v = [&](uint32_t buf, int kb_begin, int kb_end) {
-    const uint32_t v_tile = buf + 2 * kTile;
-#pragma unroll 2
-    for (int kb = kb_begin; kb < kb_end; ++kb) {
-      const int key = 8 * kb + (lane & 7);
-      const uint32_t dst_blk = vt_base + static_cast<uint32_t>(kb >> 3) * kVtBlock;
-      const int kc = kb & 7;
-#pragma unroll
-      for (int cq = 0; cq < 2; ++cq) {
-        const int chunk = 4 * cq + (lane >> 3);
-        uint32_t r[4];
-        ldmatrix_x4_t(v_tile + static_cast<uint32_t>(key * 128 + ((chunk ^ (key & 7)) << 4)), r[0], r[1], r[2], r[3]);
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          const int d = 8 * (4 * cq + m) + (lane >> 2);
-          const uint32_t dst = dst_blk + static_cast<uint32_t>(d * 128 + ((kc ^ (d & 7)) << 4) + 4 * (lane & 3));
-          asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst), "r"(r[m]) : "memory");
-        }
-      }
-    }
-  };
 
   const int64_t first = blockIdx.x;
   const int64_t stride = gridDim.x;
 
   if (warp == 3) {
-    // ===================== control warp: TMA, MMA issue, V transpose (keys 0..47) =====================
+    // ===================== control warp: TMA, MMA issue, V transpose =====================
     constexpr uint32_t idesc_s = ptx::make_idesc_bf16(128, kKeysPad);
     constexpr uint32_t idesc_o = ptx::make_idesc_bf16(128, kDh);
     if (lane == 0) {
@@ -174,11 +135,31 @@ scale_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfl
       }
       // the previous problem's second MMA has consumed V^T
       if (it > 0) ptx::mbar_wait(o_full, static_cast<uint32_t>((it - 1) & 1));
-      transpose_v(buf, 0, kKeysPad / 16);
+      // ---- V[key][d] -> V^T[d][key] (K-major, 128B swizzle, two blocks of 64 keys) ----
+      {
+        const uint32_t v_tile = buf + 2 * kTile;
+#pragma unroll 2
+        for (int kb = 0; kb < kKeysPad / 8; ++kb) {
+          const int key = 8 * kb + (lane & 7);
+          const uint32_t dst_blk = vt_base + static_cast<uint32_t>(kb >> 3) * kVtBlock;
+          const int kc = kb & 7;
+#pragma unroll
+          for (int cq = 0; cq < 2; ++cq) {
+            const int chunk = 4 * cq + (lane >> 3);
+            uint32_t r[4];
+            ldmatrix_x4_t(v_tile + static_cast<uint32_t>(key * 128 + ((chunk ^ (key & 7)) << 4)), r[0], r[1], r[2], r[3]);
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+              const int d = 8 * (4 * cq + m) + (lane >> 2);
+              const uint32_t dst = dst_blk + static_cast<uint32_t>(d * 128 + ((kc ^ (d & 7)) << 4) + 4 * (lane & 3));
+              asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst), "r"(r[m]) : "memory");
+            }
+          }
+        }
+      }
       ptx::fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
-        ptx::mbar_wait(vt_ready, static_cast<uint32_t>(it & 1));  // warp 7's half of V^T
         // this buffer is free once Q K^T has completed (V is already transposed): refill it two problems ahead
         if (prob + 2 * stride < problems) {
           ptx::mbar_wait(s_full, static_cast<uint32_t>(it & 1));
@@ -199,87 +180,57 @@ scale_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfl
       }
       __syncwarp();
     }
-  } else if (warp == 7) {
-    // ===================== helper warp: V transpose (keys 48..95) =====================
-    uint32_t full_phase = 0;
-    int it = 0;
-    for (int64_t prob = first; prob < problems; prob += stride, ++it) {
-      const int b = it & 1;
-      ptx::mbar_wait(full_bar0 + 8u * b, (full_phase >> b) & 1u);
-      full_phase ^= (1u << b);
-      if (it > 0) ptx::mbar_wait(o_full, static_cast<uint32_t>((it - 1) & 1));
-      transpose_v(base + b * kBuf, kKeysPad / 16, kKeysPad / 8);
-      ptx::fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(vt_ready);
-    }
   } else {
-    // ===================== softmax / output warps: two threads per query row =====================
-    const int quarter = warp & 3;   // TMEM lane quarter = query rows [32 * quarter, +32)
-    const int half = warp >> 2;     // 0: keys [0,32) + [64,80), dims [0,32);  1: keys [32,64) + [80,96), dims [32,64)
-    const int r = quarter * 32 + lane;
+    // ===================== softmax / output warps: thread = query row =====================
+    const int r = warp * 32 + lane;
     const uint32_t x7 = static_cast<uint32_t>(r & 7);
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    // 16-byte exchange slot of the row: {max low, max high, sum low, sum high} in logical chunk 4 of the second P tile
-    // (the second MMA only reads its logical chunks 0..3: keys 64..95)
-    const uint32_t slot = p_base + kTile + static_cast<uint32_t>(r) * 128u + ((4u ^ x7) << 4);
-    const uint32_t p_row0 = p_base + static_cast<uint32_t>(r) * 128u;            // keys 0..63
-    const uint32_t p_row1 = p_base + kTile + static_cast<uint32_t>(r) * 128u;    // keys 64..95
-    const int key_a = 32 * half;        // first block of 32 keys
-    const int key_b = 64 + 16 * half;   // second block of 16 keys
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
     int it = 0;
     for (int64_t prob = first; prob < problems; prob += stride, ++it) {
       const int64_t g = prob / H;
       const int h = static_cast<int>(prob - g * H);
       ptx::mbar_wait(s_full, static_cast<uint32_t>(it & 1));
       ptx::tc_fence_after();
-      uint32_t va[32], vb[16];
-      ptx::tmem_ld_32x32(taddr + kColS + static_cast<uint32_t>(key_a), va);
-      ptx::tmem_ld_32x16(taddr + kColS + static_cast<uint32_t>(key_b), vb);
+      uint32_t v0[32], v1[32], v2[32];
+      ptx::tmem_ld_32x32(taddr + kColS, v0);
+      ptx::tmem_ld_32x32(taddr + kColS + 32, v1);
+      ptx::tmem_ld_32x32(taddr + kColS + 64, v2);
       ptx::tmem_ld_wait();
       float mx = -INFINITY;
 #pragma unroll
-      for (int j = 0; j < 32; j += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(va[j]), __uint_as_float(va[j + 1])));
+      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaxf(__uint_as_float(v0[j]), __uint_as_float(v1[j])));
 #pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (key_b + j < S) mx = fmaxf(mx, __uint_as_float(vb[j]));
-      asm volatile("st.shared.f32 [%0], %1;" ::"r"(slot + 4u * static_cast<uint32_t>(half)), "f"(mx) : "memory");
-      pair_barrier_sync(quarter);  // the two warps of this row quarter
-      {
-        float other;
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(slot + 4u * static_cast<uint32_t>(half ^ 1)) : "memory");
-        mx = fmaxf(mx, other);
-      }
+      for (int j = 0; j < 32; ++j)
+        if (64 + j < S) mx = fmaxf(mx, __uint_as_float(v2[j]));
       const float off = mx * scale_log2e;
-      // probabilities, 8 keys (one 16-byte chunk of the P row) at a time, on packed fp32 pairs (FFMA2 / FADD2)
+      // probabilities, 8 keys (one 16-byte chunk of the P row) at a time; the scaling and the row sum run on packed
+      // fp32 pairs (FFMA2 / FADD2: half the issue slots of the scalar form — the kernel is issue / latency bound at
+      // the ~1.1 GHz the power-capped step runs at)
       const uint64_t sc2 = pack2(scale_log2e, scale_log2e), noff2 = pack2(-off, -off);
       uint64_t sum2 = pack2(0.f, 0.f);
-      auto chunk8 = [&](const uint32_t* v, int key0, uint32_t row_base) {  // keys key0 .. key0+7 -> one P chunk
-        uint32_t w[4];
+      auto emit = [&](const uint32_t (&v)[32], int key0, uint32_t tile) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int key = key0 + 2 * j;
-          float e0, e1;
-          unpack2(fma2(pack2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), sc2, noff2), e0, e1);
-          const float p0 = key < S ? ex2_approx(e0) : 0.f;
-          const float p1 = key + 1 < S ? ex2_approx(e1) : 0.f;
-          sum2 = add2(sum2, pack2(p0, p1));
-          w[j] = pack_bf16x2(p0, p1);
+        for (int c = 0; c < 4; ++c) {
+          uint32_t w[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int key = key0 + 8 * c + 2 * j;
+            float e0, e1;
+            unpack2(fma2(pack2(__uint_as_float(v[8 * c + 2 * j]), __uint_as_float(v[8 * c + 2 * j + 1])), sc2, noff2), e0, e1);
+            const float p0 = key < S ? ex2_approx(e0) : 0.f;
+            const float p1 = key + 1 < S ? ex2_approx(e1) : 0.f;
+            sum2 = add2(sum2, pack2(p0, p1));
+            w[j] = pack_bf16x2(p0, p1);
+          }
+          const uint32_t kc = static_cast<uint32_t>(((key0 & 63) >> 3) + c);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile + static_cast<uint32_t>(r) * 128u + ((kc ^ x7) << 4)),
+                       "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
+                       : "memory");
         }
-        const uint32_t kc = static_cast<uint32_t>((key0 & 63) >> 3);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_base + ((kc ^ x7) << 4)), "r"(w[0]), "r"(w[1]),
-                     "r"(w[2]), "r"(w[3])
-                     : "memory");
       };
-#pragma unroll
-      for (int c = 0; c < 4; ++c) chunk8(va + 8 * c, key_a + 8 * c, p_row0);
-#pragma unroll
-      for (int c = 0; c < 2; ++c) chunk8(vb + 8 * c, key_b + 8 * c, p_row1);
-      {
-        float sa, sb;
-        unpack2(sum2, sa, sb);
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(slot + 8u + 4u * static_cast<uint32_t>(half)), "f"(sa + sb) : "memory");
-      }
+      emit(v0, 0, p_base);
+      emit(v1, 32, p_base);
+      emit(v2, 64, p_base + kTile);
       ptx::fence_proxy_async();
       ptx::tc_fence_before();
       __syncwarp();
@@ -287,39 +238,43 @@ scale_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfl
 
       ptx::mbar_wait(o_full, static_cast<uint32_t>(it & 1));
       ptx::tc_fence_after();
-      ptx::tmem_ld_32x32(taddr + kColO + static_cast<uint32_t>(32 * half), va);
+      ptx::tmem_ld_32x32(taddr + kColO, v0);
+      ptx::tmem_ld_32x32(taddr + kColO + 32, v1);
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
       {
-        // this thread's 32 output dims -> its own P columns of the row (chunks 4 * half .. +3 of the first tile, dead
-        // after the second MMA), then the warp stores 64-byte half rows: 8 rows x 4 lanes per instruction
-        float sl, sh;
-        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(sl), "=f"(sh) : "r"(slot + 8u) : "memory");
-        const float inv = 1.0f / (sl + sh);
+        // O row -> this thread's (dead) P row, then the warp stores four complete 128-byte rows per instruction
+        float sum_a, sum_b;
+        unpack2(sum2, sum_a, sum_b);
+        const float inv = 1.0f / (sum_a + sum_b);
         const uint64_t inv2 = pack2(inv, inv);
-        auto scaled = [&](int i) {  // bf16x2 of (va[i], va[i+1]) * inv
+        const uint32_t my_row = p_base + static_cast<uint32_t>(r) * 128u;
+        auto scaled = [&](const uint32_t (&v)[32], int i) {  // bf16x2 of (v[i], v[i+1]) * inv
           float a, b;
-          unpack2(mul2(pack2(__uint_as_float(va[i]), __uint_as_float(va[i + 1])), inv2), a, b);
+          unpack2(mul2(pack2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), inv2), a, b);
           return pack_bf16x2(a, b);
         };
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row0 + ((static_cast<uint32_t>(4 * half + c) ^ x7) << 4)),
-                       "r"(scaled(8 * c)), "r"(scaled(8 * c + 2)), "r"(scaled(8 * c + 4)), "r"(scaled(8 * c + 6))
+        for (int c = 0; c < 4; ++c) {
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + ((static_cast<uint32_t>(c) ^ x7) << 4)),
+                       "r"(scaled(v0, 8 * c)), "r"(scaled(v0, 8 * c + 2)), "r"(scaled(v0, 8 * c + 4)), "r"(scaled(v0, 8 * c + 6))
                        : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + ((static_cast<uint32_t>(4 + c) ^ x7) << 4)),
+                       "r"(scaled(v1, 8 * c)), "r"(scaled(v1, 8 * c + 2)), "r"(scaled(v1, 8 * c + 4)), "r"(scaled(v1, 8 * c + 6))
+                       : "memory");
+        }
         __syncwarp();
-        const int cc = 4 * half + (lane & 3);  // logical chunk this lane stores
-        __nv_bfloat16* obase = out + (g * S) * D + h * kDh + cc * 8;
+        __nv_bfloat16* obase = out + (g * S) * D + h * kDh + (lane & 7) * 8;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int rr = quarter * 32 + 8 * i + (lane >> 2);
+        for (int i = 0; i < 8; ++i) {
+          const int rr = warp * 32 + 4 * i + (lane >> 3);
           uint32_t w0, w1, w2, w3;
           asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                        : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
-                       : "r"(p_base + static_cast<uint32_t>(rr * 128 + ((cc ^ (rr & 7)) << 4))));
+                       : "r"(p_base + static_cast<uint32_t>(rr * 128 + (((lane & 7) ^ (rr & 7)) << 4))));
           if (rr < S) *reinterpret_cast<uint4*>(obase + static_cast<int64_t>(rr) * D) = make_uint4(w0, w1, w2, w3);
         }
-        __syncwarp();  // this warp's P columns are free for the next problem
+        __syncwarp();  // rows are free for the next problem's P
       }
     }
   }
@@ -380,10 +335,10 @@ int launch_scale_attention_tc(const void* qkv, void* out, int64_t groups, int S,
   const int64_t max_ctas = 2LL * device_sm_count();
   const unsigned grid = static_cast<unsigned>(problems < max_ctas ? problems : max_ctas);
   if (S == 86)
-    scale_attention_tc_kernel<86><<<grid, 256, kSmemBytes, st>>>(tm, reinterpret_cast<__nv_bfloat16*>(out), S, H, problems,
+    scale_attention_tc_kernel<86><<<grid, 128, kSmemBytes, st>>>(tm, reinterpret_cast<__nv_bfloat16*>(out), S, H, problems,
                                                                  scale * 1.4426950408889634f);
   else
-    scale_attention_tc_kernel<0><<<grid, 256, kSmemBytes, st>>>(tm, reinterpret_cast<__nv_bfloat16*>(out), S, H, problems,
+    scale_attention_tc_kernel<0><<<grid, 128, kSmemBytes, st>>>(tm, reinterpret_cast<__nv_bfloat16*>(out), S, H, problems,
                                                                 scale * 1.4426950408889634f);
   DUO_LAUNCH_CHECK("scale_attention_tc_kernel");
   return DUO_OK;
