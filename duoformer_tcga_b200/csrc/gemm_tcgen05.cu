@@ -687,9 +687,13 @@ struct PairCfg {
   using ET = EpiTraits<EPI>;
   static constexpr bool FWD = ET::kFwd;
   static constexpr int kFwdSlots = ET::kFwdSlots;
-  static constexpr int kStages = FWD ? ET::kFwdStages : (EPI_WARPS >= 8 ? 5 : 6);
+#ifndef DUO_GELU_SINGLE_STAGING
+#define DUO_GELU_SINGLE_STAGING 0  // tuning: 8-warp GELU epilogue with ONE staging tile per warp -> a sixth operand stage
+#endif
+  static constexpr bool kSingleStaging = EPI_WARPS == 16 || (EPI_WARPS == 8 && ET::kGelu && DUO_GELU_SINGLE_STAGING);
+  static constexpr int kStages = FWD ? ET::kFwdStages : (EPI_WARPS >= 8 && !(EPI_WARPS == 8 && kSingleStaging) ? 5 : 6);
   static constexpr int kThreads = 64 + 32 * EPI_WARPS;
-  static constexpr int kStagingBufs = EPI_WARPS == 16 ? 1 : 2;  // 64 KB of staging for 8 and for 16 warps
+  static constexpr int kStagingBufs = kSingleStaging ? 1 : 2;  // 64 KB of staging for 8 and for 16 warps
   static constexpr uint32_t kABytes = kBlockM * kBlockK * 2;          // 16 KB (this CTA's 128 rows)
   static constexpr uint32_t kBBytes = (kPairBlockN / 2) * kBlockK * 2;  // 16 KB (this CTA's N half)
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;

@@ -10,6 +10,12 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200, sm_100a)")
+    # test infrastructure only: run the suite against a tuning build of the library (csrc/Makefile `tuning`)
+    alt = os.environ.get("DUO_TEST_LIB")
+    if alt:
+        from duoformer_tcga_b200 import _lib
+
+        _lib.LIB_PATH = os.path.abspath(alt)
 
 
 def pytest_collection_modifyitems(config, items):
