@@ -356,7 +356,13 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
       ptx::fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
-        ptx::tma_store_2d(tmap_out, stg + stg_buf * (32u * 128u), n0 + c, row0);
+#ifndef DUO_STORE_EVICT_FIRST
+#define DUO_STORE_EVICT_FIRST 0  // tuning: bf16 output tiles with an L2 evict-first hint
+#endif
+        if (DUO_STORE_EVICT_FIRST)
+          ptx::tma_store_2d_hint(tmap_out, stg + stg_buf * (32u * 128u), n0 + c, row0, 0x12F0000000000000ull);
+        else
+          ptx::tma_store_2d(tmap_out, stg + stg_buf * (32u * 128u), n0 + c, row0);
         ptx::tma_store_commit();
       }
       stg_buf = (NBUF == 1) ? 0u : (stg_buf ^ 1u);

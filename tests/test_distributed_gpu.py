@@ -51,3 +51,27 @@ def test_nccl_gathered_logits_equal_single_gpu_rank_major(tmp_path, batch):
         assert torch.equal(d["piped"], ref), f"rank {rk}: HostPipeline gathered logits differ"
         assert relerr(d["y"], whole) < 5e-3  # whole-batch forward: cuDNN may differ by an fp16 ulp with batch position
     assert len(devices) == world
+
+
+def test_model_on_second_device_while_first_is_current():
+    """The library launches on the CURRENT device; ops switch to the operands' device first (a model on
+    cuda:1 with cuda:0 current used to launch device-0 kernels on device-1 pointers)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    gold = load_golden("wo4_d2")
+    model = build_product(gold["case"])
+    model.load_state_dict(synth.synth_state_dict(model.state_dict(), seed=gold["weight_seed"]))
+    x = synth.synth_images(gold["case"]["batch"], seed=gold["input_seed"])
+    torch.cuda.set_device(0)
+    with torch.no_grad():
+        y0 = model.to("cuda:0").eval()(x.to("cuda:0")).float().cpu()
+        assert torch.cuda.current_device() == 0
+        y1 = model.to("cuda:1")(x.to("cuda:1"))
+        assert y1.device.index == 1 and torch.cuda.current_device() == 0
+    assert torch.equal(y1.float().cpu(), y0)
+    assert relerr(y0, gold["logits"]) < 2e-2
+    with pytest.raises(RuntimeError, match="different devices"):
+        from duoformer_tcga_b200 import ops
+
+        ops.layernorm(torch.zeros(4, 768, device="cuda:0"), torch.ones(768, device="cuda:1"), torch.zeros(768, device="cuda:0"),
+                      torch.empty(4, 768, dtype=torch.bfloat16, device="cuda:0"), 1e-6)
