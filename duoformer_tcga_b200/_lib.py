@@ -68,6 +68,7 @@ class GemmArgs(Structure):
         ("xb_out", c_void_p),
         ("stats_out", c_void_p),
         ("ln_stats", c_void_p),
+        ("shift_stats", c_void_p),
     ]
 
 
@@ -106,7 +107,7 @@ def load() -> ctypes.CDLL:
     lib.duo_gemm.restype = c_int32
     lib.duo_gemm.argtypes = [POINTER(GemmArgs), c_void_p]
     lib.duo_layernorm.restype = c_int32
-    lib.duo_layernorm.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int32, c_int64, c_float, c_void_p]
+    lib.duo_layernorm.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int32, c_int64, c_float, c_void_p, c_void_p]
     lib.duo_group_attention.restype = c_int32
     lib.duo_group_attention.argtypes = [c_void_p, c_int32, c_void_p, c_int32, c_int64, c_int32, c_int32, c_float, c_int32, c_int32, c_void_p]
     lib.duo_fill_scale_token.restype = c_int32

@@ -91,6 +91,7 @@ struct GemmParams {
   const float* gamma;
   // statistics forwarding, producer side (kEpiResidualFwd)
   float2* stats_out;        // [M, N / 256] (mean, M2) of the updated rows, per 256-column part
+  const float2* shift_stats;  // [M, N / 256] statistics of the rows BEFORE this update (or NULL): the bf16 copy is x - mean_old
   // statistics forwarding, consumer side (kEpiBf16Ln / kEpiGeluBf16Ln)
   const float2* ln_stats;   // [M, K / 256]
   float ln_eps;
@@ -356,13 +357,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
       ptx::fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
-#ifndef DUO_STORE_EVICT_FIRST
-#define DUO_STORE_EVICT_FIRST 0  // tuning: bf16 output tiles with an L2 evict-first hint
-#endif
-        if (DUO_STORE_EVICT_FIRST)
-          ptx::tma_store_2d_hint(tmap_out, stg + stg_buf * (32u * 128u), n0 + c, row0, 0x12F0000000000000ull);
-        else
-          ptx::tma_store_2d(tmap_out, stg + stg_buf * (32u * 128u), n0 + c, row0);
+        // (an L2 evict-first hint on these stores: no difference, ABAB 194.4 vs 194.6 ms per step)
+        ptx::tma_store_2d(tmap_out, stg + stg_buf * (32u * 128u), n0 + c, row0);
         ptx::tma_store_commit();
       }
       stg_buf = (NBUF == 1) ? 0u : (stg_buf ^ 1u);
@@ -693,11 +689,9 @@ struct PairCfg {
   using ET = EpiTraits<EPI>;
   static constexpr bool FWD = ET::kFwd;
   static constexpr int kFwdSlots = ET::kFwdSlots;
-#ifndef DUO_GELU_SINGLE_STAGING
-#define DUO_GELU_SINGLE_STAGING 0  // tuning: 8-warp GELU epilogue with ONE staging tile per warp -> a sixth operand stage
-#endif
-  static constexpr bool kSingleStaging = EPI_WARPS == 16 || (EPI_WARPS == 8 && ET::kGelu && DUO_GELU_SINGLE_STAGING);
-  static constexpr int kStages = FWD ? ET::kFwdStages : (EPI_WARPS >= 8 && !(EPI_WARPS == 8 && kSingleStaging) ? 5 : 6);
+  // (8 warps with ONE staging tile each and a sixth operand stage: no difference for fc1 + GELU, ABAB 194.4 vs 196.3 ms per step)
+  static constexpr bool kSingleStaging = EPI_WARPS == 16;
+  static constexpr int kStages = FWD ? ET::kFwdStages : (EPI_WARPS >= 8 ? 5 : 6);
   static constexpr int kThreads = 64 + 32 * EPI_WARPS;
   static constexpr int kStagingBufs = kSingleStaging ? 1 : 2;  // 64 KB of staging for 8 and for 16 warps
   static constexpr uint32_t kABytes = kBlockM * kBlockK * 2;          // 16 KB (this CTA's 128 rows)
@@ -914,6 +908,14 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const int n0 = n_blk * BLOCK_N;
         const int64_t row = static_cast<int64_t>(row0) + lane;
         const bool valid = row < p.M;
+        // Row shift of the bf16 copy: the row mean as of the PREVIOUS statistics.  The consumer's weights are
+        // row-centred, so any per-row constant drops out of its product; subtracting (an estimate of) the mean before
+        // rounding keeps the bf16 rounding error relative to the row's spread instead of its offset.
+        float shift = 0.f;
+        if (p.shift_stats != nullptr && valid) {
+          for (int i = 0; i < parts; ++i) shift += __ldg(p.shift_stats + row * parts + i).x;
+          shift *= 1.0f / static_cast<float>(parts);
+        }
         ptx::mbar_wait(tmem_full_bar(acc), acc_phase);
         ptx::tc_fence_after();
         const uint32_t taddr =
@@ -988,10 +990,10 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
             st_shared_v4(xrow + ((static_cast<uint32_t>(j) ^ sw128) << 4), __float_as_uint(f[4 * j + 0]),
                          __float_as_uint(f[4 * j + 1]), __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3]));
 #pragma unroll
-          for (int j = 0; j < 4; ++j)  // bf16 copy (A operand of the next GEMM)
+          for (int j = 0; j < 4; ++j)  // bf16 copy of x - shift (A operand of the next GEMM)
             st_shared_v4(brow + ((static_cast<uint32_t>(j) ^ sw64) << 4),
-                         pack_bf16x2(f[8 * j + 0], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                         pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+                         pack_bf16x2(f[8 * j + 0] - shift, f[8 * j + 1] - shift), pack_bf16x2(f[8 * j + 2] - shift, f[8 * j + 3] - shift),
+                         pack_bf16x2(f[8 * j + 4] - shift, f[8 * j + 5] - shift), pack_bf16x2(f[8 * j + 6] - shift, f[8 * j + 7] - shift));
           ptx::fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
@@ -1235,10 +1237,12 @@ extern "C" int duo_gemm(const duo_gemm_args* a, duo_stream_t stream) {
   int epi = a->epilogue;
   // statistics forwarding, producer side: residual update that also emits the bf16 copy + row statistics
   const bool fwd = a->xb_out != nullptr || a->stats_out != nullptr;
+  DUO_CHECK_ARG(fwd || a->shift_stats == nullptr, "duo_gemm: shift_stats only applies to statistics forwarding (xb_out / stats_out)");
   if (fwd) {
     DUO_CHECK_ARG(epi == DUO_EPI_RESIDUAL_F32 && a->split3 == 0 && a->xb_out && a->stats_out,
                   "duo_gemm: statistics forwarding needs the plain-bf16 residual epilogue and both xb_out and stats_out");
     DUO_CHECK_ARG(a->N % kPairBlockN == 0, "duo_gemm: statistics forwarding needs N %% 256 == 0 (N=%d)", a->N);
+    DUO_CHECK_ARG(a->shift_stats != a->stats_out, "duo_gemm: shift_stats must not alias stats_out (other CTAs still read it)");
     DUO_CHECK_ARG((reinterpret_cast<uintptr_t>(a->xb_out) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->stats_out) & 7) == 0,
                   "duo_gemm: xb_out must be 16-byte aligned, stats_out 8-byte aligned");
   }
@@ -1290,6 +1294,7 @@ extern "C" int duo_gemm(const duo_gemm_args* a, duo_stream_t stream) {
   }
   GemmParams p;
   p.stats_out = reinterpret_cast<float2*>(a->stats_out);
+  p.shift_stats = reinterpret_cast<const float2*>(a->shift_stats);
   p.ln_stats = reinterpret_cast<const float2*>(a->ln_stats);
   p.ln_eps = a->ln_eps;
   p.relu = a->relu;

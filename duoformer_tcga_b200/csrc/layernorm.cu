@@ -22,7 +22,7 @@ template <int NV, int OUT_KIND>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                  const float* __restrict__ beta, void* __restrict__ out, int64_t rows, int64_t ldx,
-                 float eps) {
+                 float eps, float2* __restrict__ stats_out) {
   constexpr int D = NV * 128;
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * kWarpsPerCta + (threadIdx.x >> 5);
@@ -44,6 +44,22 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
     q += (a * a + b * b) + (c * c + d * d);
   }
   const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+
+  // optional: (mean, sum of squared deviations) of every 256-column part, the layout duo_gemm's statistics forwarding
+  // exchanges (a 256-column part = float4 vectors 64p .. 64p+63 = v[2p], v[2p+1] of every lane)
+  if constexpr (NV % 2 == 0) {
+    if (stats_out != nullptr) {
+#pragma unroll
+      for (int pt = 0; pt < NV / 2; ++pt) {
+        const float4 a = v[2 * pt], b = v[2 * pt + 1];
+        const float pm = warp_sum((a.x + a.y) + (a.z + a.w) + (b.x + b.y) + (b.z + b.w)) * (1.0f / 256.0f);
+        float dq = (a.x - pm) * (a.x - pm) + (a.y - pm) * (a.y - pm) + (a.z - pm) * (a.z - pm) + (a.w - pm) * (a.w - pm);
+        dq += (b.x - pm) * (b.x - pm) + (b.y - pm) * (b.y - pm) + (b.z - pm) * (b.z - pm) + (b.w - pm) * (b.w - pm);
+        dq = warp_sum(dq);
+        if (lane == 0) stats_out[row * (NV / 2) + pt] = make_float2(pm, dq);
+      }
+    }
+  }
 
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
   const float4* b4 = reinterpret_cast<const float4*>(beta);
@@ -74,14 +90,14 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
 
 template <int NV>
 int launch_ln(const float* x, const float* g, const float* b, void* out, int out_kind,
-              int64_t rows, int64_t ldx, float eps, cudaStream_t st) {
+              int64_t rows, int64_t ldx, float eps, float2* stats, cudaStream_t st) {
   const int64_t grid = (rows + kWarpsPerCta - 1) / kWarpsPerCta;
   if (out_kind == DUO_ACT_BF16)
     layernorm_kernel<NV, DUO_ACT_BF16><<<static_cast<unsigned>(grid), kWarpsPerCta * 32, 0, st>>>(
-        x, g, b, out, rows, ldx, eps);
+        x, g, b, out, rows, ldx, eps, stats);
   else
     layernorm_kernel<NV, DUO_ACT_SPLIT><<<static_cast<unsigned>(grid), kWarpsPerCta * 32, 0, st>>>(
-        x, g, b, out, rows, ldx, eps);
+        x, g, b, out, rows, ldx, eps, stats);
   DUO_LAUNCH_CHECK("layernorm_kernel");
   return DUO_OK;
 }
@@ -91,7 +107,7 @@ int launch_ln(const float* x, const float* g, const float* b, void* out, int out
 
 extern "C" int duo_layernorm(const float* x, const float* gamma, const float* beta, void* out,
                              int32_t out_kind, int64_t rows, int32_t dim, int64_t ldx,
-                             float eps, duo_stream_t stream) {
+                             float eps, float* stats_out, duo_stream_t stream) {
   using namespace duo;
   DUO_CHECK_ARG(x && gamma && beta && out, "duo_layernorm: NULL pointer");
   DUO_CHECK_ARG(rows > 0, "duo_layernorm: rows=%lld", (long long)rows);
@@ -103,15 +119,18 @@ extern "C" int duo_layernorm(const float* x, const float* gamma, const float* be
                 (long long)ldx);
   DUO_CHECK_ARG((rows + kWarpsPerCta - 1) / kWarpsPerCta < (int64_t(1) << 31),
                 "duo_layernorm: too many rows");
+  DUO_CHECK_ARG(stats_out == nullptr || (dim % 256 == 0 && (reinterpret_cast<uintptr_t>(stats_out) & 7) == 0),
+                "duo_layernorm: stats_out needs dim %% 256 == 0 and 8-byte alignment (dim=%d)", dim);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  float2* stats = reinterpret_cast<float2*>(stats_out);
   switch (dim / 128) {
-    case 1: return launch_ln<1>(x, gamma, beta, out, out_kind, rows, ldx, eps, st);
-    case 2: return launch_ln<2>(x, gamma, beta, out, out_kind, rows, ldx, eps, st);
-    case 3: return launch_ln<3>(x, gamma, beta, out, out_kind, rows, ldx, eps, st);
-    case 4: return launch_ln<4>(x, gamma, beta, out, out_kind, rows, ldx, eps, st);
-    case 5: return launch_ln<5>(x, gamma, beta, out, out_kind, rows, ldx, eps, st);
-    case 6: return launch_ln<6>(x, gamma, beta, out, out_kind, rows, ldx, eps, st);
-    case 7: return launch_ln<7>(x, gamma, beta, out, out_kind, rows, ldx, eps, st);
-    default: return launch_ln<8>(x, gamma, beta, out, out_kind, rows, ldx, eps, st);
+    case 1: return launch_ln<1>(x, gamma, beta, out, out_kind, rows, ldx, eps, stats, st);
+    case 2: return launch_ln<2>(x, gamma, beta, out, out_kind, rows, ldx, eps, stats, st);
+    case 3: return launch_ln<3>(x, gamma, beta, out, out_kind, rows, ldx, eps, stats, st);
+    case 4: return launch_ln<4>(x, gamma, beta, out, out_kind, rows, ldx, eps, stats, st);
+    case 5: return launch_ln<5>(x, gamma, beta, out, out_kind, rows, ldx, eps, stats, st);
+    case 6: return launch_ln<6>(x, gamma, beta, out, out_kind, rows, ldx, eps, stats, st);
+    case 7: return launch_ln<7>(x, gamma, beta, out, out_kind, rows, ldx, eps, stats, st);
+    default: return launch_ln<8>(x, gamma, beta, out, out_kind, rows, ldx, eps, stats, st);
   }
 }

@@ -88,12 +88,6 @@ __device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t smem_src
                ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src), "r"(c0), "r"(c1)
                : "memory");
 }
-__device__ __forceinline__ void tma_store_2d_hint(const void* tmap, uint32_t smem_src, int32_t c0, int32_t c1,
-                                                  uint64_t hint) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
-               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src), "r"(c0), "r"(c1), "l"(hint)
-               : "memory");
-}
 // 2D tiled reduce-add shared -> global (element type from the tensor map; f32 here).
 __device__ __forceinline__ void tma_reduce_add_2d(const void* tmap, uint32_t smem_src, int32_t c0,
                                                   int32_t c1) {

@@ -162,7 +162,20 @@ def _scale_chunk(X, g0, ng, buf, blocks, num_heads, scale, eps, precision, captu
     QKV = Workspace.view(buf, 2 * hn_bytes, (T, 3 * D), torch.float32 if fp32 else torch.bfloat16)
     HID = Workspace.view(buf, 2 * hn_bytes, (T, kd * hidden), torch.bfloat16)  # aliases QKV (dead after attention)
     big = _align(max(T * 3 * D * (4 if fp32 else 2), T * kd * hidden * 2))
-    ST = Workspace.view(buf, 2 * hn_bytes + big, (T, D // STAT_COLS, 2), torch.float32) if fwd else None
+    # two statistics buffers, written alternately: a forwarding GEMM writes the new statistics into one while its CTAs
+    # still read the rows' previous ones (the shift of the bf16 copy) from the other
+    st_bytes = _align(T * (D // STAT_COLS) * 8)
+    STS = [Workspace.view(buf, 2 * hn_bytes + big + k * st_bytes, (T, D // STAT_COLS, 2), torch.float32) for k in (0, 1)] if fwd else None
+    st_cur = [0]  # index of the buffer holding the most recent statistics of Xc
+
+    def forward_residual(A, blk, key, gamma_key):
+        """Xc += gamma * (A W^T + b) with statistics forwarding: bf16(Xc - previous row mean) -> Ha, new statistics."""
+        prev, nxt = STS[st_cur[0]], STS[st_cur[0] ^ 1]
+        ops.gemm(A, blk[key][0], blk[key][1], Xc, ops.EPI_RESIDUAL_F32, gamma=blk[gamma_key], xb_out=Ha, stats_out=nxt,
+                 shift_stats=prev)
+        st_cur[0] ^= 1
+        return nxt
+
     gelu = ops.EPI_GELU_SPLIT_BF16 if fp32 else ops.EPI_GELU_BF16
     L = len(blocks)
 
@@ -171,9 +184,10 @@ def _scale_chunk(X, g0, ng, buf, blocks, num_heads, scale, eps, precision, captu
         last = i == L - 1
         if have_ln1:
             w, b = blk["qkv_ln"]
-            ops.gemm(Ha, w, b, QKV, ops.EPI_BF16, ln_stats=ST, ln_eps=eps)
+            ops.gemm(Ha, w, b, QKV, ops.EPI_BF16, ln_stats=STS[st_cur[0]], ln_eps=eps)
         else:
-            ops.layernorm(Xc, blk["n1w"], blk["n1b"], Ha, eps)
+            # (in forwarding mode the LayerNorm launch also leaves the row statistics: the next producer's shift)
+            ops.layernorm(Xc, blk["n1w"], blk["n1b"], Ha, eps, stats_out=STS[st_cur[0]] if fwd else None)
             ops.gemm(Ha, blk["qkv"][0], blk["qkv"][1], QKV, ops.EPI_F32 if fp32 else ops.EPI_BF16, split3=fp32)
         if live_only_last and last:
             # Last scale block: only the scale token (s = 0) of every patch is consumed downstream
@@ -195,16 +209,16 @@ def _scale_chunk(X, g0, ng, buf, blocks, num_heads, scale, eps, precision, captu
             return False
         ops.group_attention(QKV, Hb, S, num_heads, scale, algo=attn_algo)
         if fwd2:
-            ops.gemm(Hb, blk["proj"][0], blk["proj"][1], Xc, ops.EPI_RESIDUAL_F32, gamma=blk["g1"], xb_out=Ha, stats_out=ST)
+            st = forward_residual(Hb, blk, "proj", "g1")
             w, b = blk["fc1_ln"]
-            ops.gemm(Ha, w, b, HID, gelu, ln_stats=ST, ln_eps=eps)
+            ops.gemm(Ha, w, b, HID, gelu, ln_stats=st, ln_eps=eps)
         else:
             ops.gemm(Hb, blk["proj"][0], blk["proj"][1], Xc, ops.EPI_RESIDUAL_F32, gamma=blk["g1"], split3=fp32)
-            ops.layernorm(Xc, blk["n2w"], blk["n2b"], Ha, eps)
+            ops.layernorm(Xc, blk["n2w"], blk["n2b"], Ha, eps, stats_out=STS[st_cur[0]] if fwd else None)
             ops.gemm(Ha, blk["fc1"][0], blk["fc1"][1], HID, gelu, split3=fp32)
         forward_next = fwd1 and not last
         if forward_next:
-            ops.gemm(HID, blk["fc2"][0], blk["fc2"][1], Xc, ops.EPI_RESIDUAL_F32, gamma=blk["g2"], xb_out=Ha, stats_out=ST)
+            forward_residual(HID, blk, "fc2", "g2")
         else:
             ops.gemm(HID, blk["fc2"][0], blk["fc2"][1], Xc, ops.EPI_RESIDUAL_F32, gamma=blk["g2"], split3=fp32)
         if capture is not None:
@@ -220,7 +234,7 @@ def _scale_chunk(X, g0, ng, buf, blocks, num_heads, scale, eps, precision, captu
 def _chunk_workspace_bytes(ng, S, D, hidden, fp32):
     T = ng * S
     kd = 2 if fp32 else 1
-    stats = 0 if fp32 else _align(T * (D // STAT_COLS) * 8)
+    stats = 0 if fp32 else 2 * _align(T * (D // STAT_COLS) * 8)
     return 2 * _align(T * kd * D * 2) + _align(max(T * 3 * D * (4 if fp32 else 2), T * kd * hidden * 2)) + stats
 
 

@@ -109,12 +109,14 @@ def gemm(
     stats_out: Optional[torch.Tensor] = None,
     ln_stats: Optional[torch.Tensor] = None,
     ln_eps: float = 1e-6,
+    shift_stats: Optional[torch.Tensor] = None,
 ) -> torch.Tensor:
     """out = epilogue(A @ W.T + bias).  A [M,K] / W [N,K] bf16 (or [.,2K] split when split3).
 
     LayerNorm statistics forwarding (include/duoformer_sm100.h):
       producer  EPI_RESIDUAL_F32 with xb_out (bf16 [M,N]) + stats_out (fp32 [M, N/256, 2]): the updated rows are
-                also written un-normalised in bf16 together with their per-256-column (mean, M2) pairs;
+                also written un-normalised in bf16 together with their per-256-column (mean, M2) pairs; with
+                shift_stats (the rows' PREVIOUS statistics, same layout) the copy is bf16(x - previous row mean);
       consumer  EPI_BF16 / EPI_GELU_BF16 with ln_stats: A is such a copy, W = W * ln_weight with centred rows
                 (engine.pack_ln_linear), bias = W ln_bias + b; the epilogue applies rstd."""
     split3 = int(split3)  # 0 plain, 1 both operands split (hi|lo), 2 only W split (A exact bf16)
@@ -140,6 +142,10 @@ def gemm(
         assert xb_out.dtype == torch.bfloat16 and xb_out.is_contiguous() and xb_out.numel() == M * N
         assert stats_out.dtype == torch.float32 and stats_out.is_contiguous() and stats_out.numel() >= M * (N // 256) * 2
         a.xb_out, a.stats_out = _ptr(xb_out), _ptr(stats_out)
+        if shift_stats is not None:
+            assert shift_stats.dtype == torch.float32 and shift_stats.is_contiguous() and shift_stats.numel() >= M * (N // 256) * 2
+            assert shift_stats.data_ptr() != stats_out.data_ptr()
+            a.shift_stats = _ptr(shift_stats)
     if ln_stats is not None:
         assert ln_stats.dtype == torch.float32 and ln_stats.is_contiguous() and ln_stats.numel() >= M * (K // 256) * 2
         a.ln_stats, a.ln_eps = _ptr(ln_stats), float(ln_eps)
@@ -159,9 +165,11 @@ def gemm(
 
 
 @_on_operand_device
-def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out: torch.Tensor, eps: float) -> torch.Tensor:
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out: torch.Tensor, eps: float,
+              stats_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out (bf16 [rows,D] or split bf16 [rows,2D], dense) = LayerNorm(x fp32 [rows,D]).
-    x may be a 2-D row-strided view (e.g. the s = 0 token of every patch)."""
+    x may be a 2-D row-strided view (e.g. the s = 0 token of every patch).
+    stats_out (fp32 [rows, D/256, 2]): also the per-256-column (mean, M2) pairs of every row."""
     D = x.shape[-1]
     assert x.dtype == torch.float32 and out.is_contiguous() and x.stride(-1) == 1
     if x.is_contiguous():
@@ -171,9 +179,12 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out: tor
         rows, ldx = x.shape[0], x.stride(0)
     kind = _act_kind(out, D)
     assert kind in (ACT_BF16, ACT_SPLIT)
+    if stats_out is not None:
+        assert stats_out.dtype == torch.float32 and stats_out.is_contiguous() and stats_out.numel() >= rows * (D // 256) * 2
     e0 = _prof_begin()
     _lib.check(
-        _lib.load().duo_layernorm(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(out), kind, rows, D, ldx, float(eps), _stream()),
+        _lib.load().duo_layernorm(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(out), kind, rows, D, ldx, float(eps),
+                                  _ptr(stats_out), _stream()),
         "duo_layernorm",
     )
     _prof_end(e0, "layernorm", 0.0, rows * (D * 4 + out.shape[-1] * 2), f"layernorm:{rows}x{D}")

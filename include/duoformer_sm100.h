@@ -120,6 +120,11 @@ typedef struct duo_gemm_args {
   void* xb_out;
   float* stats_out;
   const float* ln_stats;
+  /* producer, optional: statistics (same layout) of the rows BEFORE this update — the previous forwarding GEMM's      */
+  /* stats_out or duo_layernorm's.  xb_out then holds bf16(x - m), m = the row mean according to these statistics: the */
+  /* consumer's row-centred weights make any per-row constant drop out of its product, and rounding x - m instead of  */
+  /* x keeps the bf16 error relative to the row's spread when |mean| >> spread.  Must not alias stats_out.            */
+  const float* shift_stats;
 } duo_gemm_args;
 int duo_gemm(const duo_gemm_args* args, duo_stream_t stream);
 
@@ -128,10 +133,12 @@ int duo_gemm(const duo_gemm_args* args, duo_stream_t stream);
  * Replaces nn.LayerNorm(eps=1e-6): scale_attention.py:65,78,91-92; multiscale_attn.py:282-285.
  * dim % 128 == 0, dim <= 1024.  ldx = input row stride in elements (>= dim; rows of a strided view,
  * e.g. the s = 0 token of every patch, can be normalised without a gather); out is dense.
+ * stats_out (optional, dim % 256 == 0): float [rows, dim / 256, 2], (mean, sum of squared deviations) of every
+ * 256-column part of the row — the layout of duo_gemm's statistics forwarding (used as its shift_stats).
  */
 int duo_layernorm(const float* x, const float* gamma, const float* beta, void* out,
                   int32_t out_kind, int64_t rows, int32_t dim, int64_t ldx, float eps,
-                  duo_stream_t stream);
+                  float* stats_out, duo_stream_t stream);
 
 /*
  * Grouped multi-head attention over S consecutive rows of a fused qkv matrix:

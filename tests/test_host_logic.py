@@ -27,9 +27,9 @@ def test_c_abi_library_loads_and_exports_every_declared_symbol():
 
 
 def test_gemm_args_struct_layout_matches_header():
-    # 7 pointers, 4 int64, 7 int32 + float + 2 int32, 3 pointers -> 8*7 + 8*4 + 4*10 + 8*3 = 152 bytes
-    assert ctypes.sizeof(_lib.GemmArgs) == 152
-    assert _lib.GemmArgs.xb_out.offset == 128 and _lib.GemmArgs.ln_stats.offset == 144
+    # 7 pointers, 4 int64, 7 int32 + float + 2 int32, 4 pointers -> 8*7 + 8*4 + 4*10 + 8*4 = 160 bytes
+    assert ctypes.sizeof(_lib.GemmArgs) == 160
+    assert _lib.GemmArgs.xb_out.offset == 128 and _lib.GemmArgs.ln_stats.offset == 144 and _lib.GemmArgs.shift_stats.offset == 152
     assert _lib.GemmArgs.M.offset == 56 and _lib.GemmArgs.N.offset == 88
 
 
@@ -188,3 +188,34 @@ def test_token_row_maps_properties_over_random_grids():
             assert torch.equal((m.long() // S).view(G, G), patch_of_pixel)
 
     check()
+
+
+def test_pack_ln_linear_centres_the_rounded_rows_and_matches_layernorm_linear():
+    """Consumer-side operands of the LayerNorm statistics forwarding (engine.pack_ln_linear), emulated on the CPU:
+    the bf16 VALUES of every weight row sum to ~0 (so a per-row constant in x — its mean, or the producer's shift —
+    drops out of x W''^T), and rstd * (bf16(x - shift) W''^T) + bias' reproduces Linear(LayerNorm(x)) within bf16
+    rounding even when the row mean is 100x the row spread, provided the shift is near the mean."""
+    from duoformer_tcga_b200 import engine
+
+    g = torch.Generator().manual_seed(0)
+    K, N = 768, 3072
+    W = torch.randn(N, K, generator=g) * 0.02
+    b = torch.randn(N, generator=g) * 0.02
+    lw = 1 + 0.1 * torch.randn(K, generator=g)
+    lb = 0.05 * torch.randn(K, generator=g)
+    wp, bp = engine.pack_ln_linear(W, b, lw, lb)
+    assert wp.dtype == torch.bfloat16 and wp.shape == (N, K) and bp.shape == (N,)
+    row_sums = wp.double().sum(dim=1).abs().max().item()
+    naive = ((W * lw) - (W * lw).mean(dim=1, keepdim=True)).to(torch.bfloat16).double().sum(dim=1).abs().max().item()
+    assert row_sums < 1e-5 * wp.float().abs().mean().item() * K and row_sums < 1e-3 * naive
+    x = torch.randn(256, K, generator=g) * 3
+    for offset in (0.0, 30.0, 300.0):
+        xo = x + offset
+        ref = torch.nn.functional.layer_norm(xo, (K,), lw, lb, 1e-6) @ W.t() + b
+        rstd = torch.rsqrt(xo.var(dim=-1, unbiased=False, keepdim=True) + 1e-6)
+        shift = xo.mean(dim=-1, keepdim=True) + 0.3  # an estimate of the mean (the previous block's)
+        out = rstd * ((xo - shift).to(torch.bfloat16).float() @ wp.float().t()) + bp
+        ln_round = torch.nn.functional.layer_norm(xo, (K,), lw, lb, 1e-6).to(torch.bfloat16).float() @ W.to(torch.bfloat16).float().t() + b
+        e_fwd = ((out - ref).abs().max() / ref.abs().max()).item()
+        e_ln = ((ln_round - ref).abs().max() / ref.abs().max()).item()
+        assert e_fwd < 2.5 * e_ln + 1e-3, (offset, e_fwd, e_ln)

@@ -193,6 +193,23 @@ def test_group_attention_leading_query_rows(S, G, algo, q_rows):
     assert relerr(out, ref) < 1.5e-2
 
 
+@pytest.mark.parametrize("rows,D", [(1000, 768), (77, 256), (33, 1024)])
+def test_layernorm_statistics_output(rows, D):
+    """duo_layernorm's optional stats_out: (mean, sum of squared deviations) of every 256-column part of the row — the
+    layout the forwarding GEMMs exchange (used as the first producer's shift_stats)."""
+    x = _gen((rows, D), 301, 3.0) + 20.0
+    g, b = _gen((D,), 302) + 1.0, _gen((D,), 303)
+    out = torch.empty(rows, D, dtype=torch.bfloat16, device="cuda")
+    st = torch.full((rows, D // 256, 2), float("nan"), device="cuda")
+    ops.layernorm(x, g, b, out, 1e-6, stats_out=st)
+    assert relerr(out, torch.nn.functional.layer_norm(x, (D,), g, b, 1e-6)) < 1e-2
+    parts = x.view(rows, D // 256, 256)
+    assert (st[:, :, 0] - parts.mean(dim=2)).abs().max().item() < 1e-4
+    assert relerr(st[:, :, 1], ((parts - parts.mean(dim=2, keepdim=True)) ** 2).sum(dim=2)) < 1e-4
+    mean, var = _merge_stats(st, D)
+    assert relerr(var, x.var(dim=1, unbiased=False)) < 1e-4
+
+
 def test_layernorm_strided_rows_and_residual_into_strided_view():
     R, S, D = 300, 6, 768
     X = _gen((R, S, D), 95, 5.0)
@@ -310,6 +327,29 @@ def test_gemm_residual_statistics_forwarding_producer(M, K, with_gamma):
         assert relerr(st[:, :, 1], ((parts - parts.mean(dim=2, keepdim=True)) ** 2).sum(dim=2)) < 1e-3
 
 
+@pytest.mark.parametrize("M", [300, 256 * 60 + 77])
+def test_gemm_forwarding_row_shift(M):
+    """shift_stats: the bf16 copy is bf16(x - m), m = the row mean according to the PREVIOUS statistics; X and the new
+    statistics are unaffected."""
+    N = K = 768
+    A = _gen((M, K), 211).to(torch.bfloat16)
+    W = _gen((N, K), 212, 0.05).to(torch.bfloat16)
+    bias = _gen((N,), 213)
+    X = _gen((M, N), 214, 3.0) + 40.0
+    prev_parts = X.view(M, N // 256, 256)
+    prev = torch.stack([prev_parts.mean(dim=2) + 0.25, torch.ones(M, N // 256, device="cuda")], dim=2).contiguous()  # any estimate
+    Xr = X + A.float() @ W.float().t() + bias
+    xb = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    st = torch.empty(M, N // 256, 2, device="cuda")
+    ops.gemm(A, W, bias, X, ops.EPI_RESIDUAL_F32, xb_out=xb, stats_out=st, shift_stats=prev)
+    assert relerr(X, Xr) < 1e-4
+    shift = prev[:, :, 0].mean(dim=1, keepdim=True)
+    assert torch.equal(xb, (X - shift).to(torch.bfloat16))
+    assert (st[:, :, 0] - X.view(M, N // 256, 256).mean(dim=2)).abs().max().item() < 1e-3
+    with pytest.raises(AssertionError):  # the previous statistics must not be the buffer being written
+        ops.gemm(A, W, bias, X, ops.EPI_RESIDUAL_F32, xb_out=xb, stats_out=st, shift_stats=st)
+
+
 @pytest.mark.parametrize("M,N,epi", [(256 * 60 + 77, 2304, "bf16"), (256 * 60 + 77, 3072, "gelu"), (300, 2304, "bf16"),
                                      (300, 3072, "gelu"), (4214, 3072, "gelu"), (128 * 310 + 5, 768, "bf16")])
 def test_gemm_forwarded_layernorm_consumer(M, N, epi):
@@ -335,16 +375,19 @@ def test_gemm_forwarded_layernorm_consumer(M, N, epi):
     assert relerr(out, ref) < 1.5e-2
 
 
-def test_gemm_statistics_forwarding_chain_matches_layernorm_path():
+@pytest.mark.parametrize("offset", [0.0, 30.0, 300.0])
+def test_gemm_statistics_forwarding_chain_matches_layernorm_path(offset):
     """proj(+residual) -> fc1(+GELU) through the forwarding pair of epilogues equals residual GEMM -> LayerNorm
-    kernel -> fc1 GEMM (the round-1 sequence) within bf16 rounding."""
+    kernel -> fc1 GEMM (the round-1 sequence) within bf16 rounding — also when the rows carry a mean of 10x / 100x their
+    spread: the producer subtracts the previous row mean (shift_stats, here the LayerNorm kernel's statistics of the
+    rows before the update) before rounding, and the consumer's row-centred weights make the shift drop out."""
     from duoformer_tcga_b200 import engine
 
     M, D, Hd = 256 * 40 + 13, 768, 3072
     A = _gen((M, D), 141).to(torch.bfloat16)
     Wp = _gen((D, D), 142, 0.05).to(torch.bfloat16)
     bp = _gen((D,), 143)
-    X = _gen((M, D), 144, 3.0)
+    X = _gen((M, D), 144, 3.0) + offset
     lw, lb = _gen((D,), 145, 0.1) + 1.0, _gen((D,), 146, 0.05)
     W1 = _gen((Hd, D), 147, 0.03)
     b1 = _gen((Hd,), 148, 0.1)
@@ -355,11 +398,13 @@ def test_gemm_statistics_forwarding_chain_matches_layernorm_path():
     ops.layernorm(X1, lw, lb, hn, 1e-6)
     h1 = torch.empty(M, Hd, dtype=torch.bfloat16, device="cuda")
     ops.gemm(hn, W1.to(torch.bfloat16), b1, h1, ops.EPI_GELU_BF16)
-    # forwarding sequence
+    # forwarding sequence (the rows' previous statistics come from a LayerNorm launch, as in block 0 of the model)
     X2 = X.clone()
     xb = torch.empty(M, D, dtype=torch.bfloat16, device="cuda")
     st = torch.empty(M, D // 256, 2, device="cuda")
-    ops.gemm(A, Wp, bp, X2, ops.EPI_RESIDUAL_F32, xb_out=xb, stats_out=st)
+    st_prev = torch.empty(M, D // 256, 2, device="cuda")
+    ops.layernorm(X2, lw, lb, torch.empty(M, D, dtype=torch.bfloat16, device="cuda"), 1e-6, stats_out=st_prev)
+    ops.gemm(A, Wp, bp, X2, ops.EPI_RESIDUAL_F32, xb_out=xb, stats_out=st, shift_stats=st_prev)
     w, b = engine.pack_ln_linear(W1, b1, lw, lb)
     h2 = torch.empty(M, Hd, dtype=torch.bfloat16, device="cuda")
     ops.gemm(xb, w, b, h2, ops.EPI_GELU_BF16, ln_stats=st, ln_eps=1e-6)
