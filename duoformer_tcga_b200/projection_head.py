@@ -7,7 +7,9 @@ C_k -> proj_dim, kaiming-normal weight / N(0,1e-6) bias), `Channel_Projector_lay
 On the hot path `Projection` is never run as a convolution: its weights feed the fused
 tcgen05 GEMM + token-scatter kernel (see token_builder.py).  `Projection.forward` is kept for
 API parity and runs the same GEMM kernel with a plain fp32 epilogue.  The channel-token branch
-(3x3 convs + BN + ReLU + max-pools) stays on cuDNN via torch modules for now.
+(3x3 convs + BN + ReLU + max-pools) is declared here for the state_dict schema; in bf16 mode it runs as
+im2col + tcgen05 GEMM + pool-to-slice kernels (channel_branch.py), in fp32 mode through these
+torch modules (fp32 cuDNN, TF32 off).
 """
 from __future__ import annotations
 
