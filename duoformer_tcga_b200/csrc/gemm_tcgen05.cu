@@ -14,11 +14,16 @@
 //
 //   epilogue warps 0..3 (0..7 for the GELU epilogue of the pair kernel): tcgen05.ld the fp32
 //               accumulator (one TMEM lane quarter per warp, one output row per thread), fuse
-//               bias / GELU(erf) / LayerScale, then
+//               bias / GELU(erf) / LayerScale / a forwarded LayerNorm (rstd of the row, merged from the
+//               statistics the producing GEMM left; W is then the row-centred W * diag(ln_weight)), then
 //                 * bf16 outputs: rows staged in a per-warp 128B-swizzled shared-memory tile and
 //                   written with TMA stores (full-line, coalesced);
 //                 * residual (X += ...): staged fp32 tile + TMA reduce-add into the fp32 residual
 //                   stream (the read-modify-write happens in L2, no SM-side loads);
+//                 * residual with statistics forwarding (pair kernel): X chunks TMA-loaded into a per-warp
+//                   ring, updated in place, TMA-stored together with bf16(x - previous row mean) and the
+//                   row's (mean, M2) over the tile's 256 columns — the LayerNorm that follows needs no pass
+//                   over X of its own;
 //                 * token scatter: rows transposed through the staging tile, four complete
 //                   128-byte lines per store instruction;
 //                 * fp32 / hi-lo split outputs (fp32 mode only): direct 16-byte global stores.
@@ -32,7 +37,6 @@
 // split3 mode (fp32-accuracy path): A and W hold bf16 hi|lo halves; the K loop runs three
 // segments (Ah*Wh, Ah*Wl, Al*Wh) into the same accumulator.
 #include <cuda.h>
-#include <stdlib.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
