@@ -164,6 +164,29 @@ __device__ __forceinline__ uint64_t gelu_erf_sigmoid_p2(uint64_t x) {
   return mul2(x, pack2(rcp_approx(da), rcp_approx(db)));
 #undef DUO_C2
 }
+// Same function in tanh form: gelu(x) = hx + hx * tanh(x * q(x^2)), hx = x / 2, q an even degree-4 polynomial fitted
+// (minimax on the gelu error) to 2.5e-5 absolute against the exact erf-GELU; ONE MUFU (tanh.approx) per element
+// instead of ex2 + rcp and one FMA less.  q turns negative beyond |x| = 11.1, so x^2 is clamped at 100 (|x| = 10:
+// tanh has saturated to +-1 in fp32 long before).
+__device__ __forceinline__ float tanh_approx(float x) {
+  float r;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ uint64_t gelu_erf_tanh_p2(uint64_t x) {
+#define DUO_C2(v) pack2((v), (v))
+  float ua, ub;
+  unpack2(mul2(x, x), ua, ub);
+  const uint64_t u = pack2(fminf(ua, 100.0f), fminf(ub, 100.0f));
+  uint64_t r = fma2(DUO_C2(-3.51516791e-04f), u, DUO_C2(3.70056460e-02f));
+  r = fma2(r, u, DUO_C2(7.97507884e-01f));
+  float ea, eb;
+  unpack2(mul2(x, r), ea, eb);
+  const uint64_t t = pack2(tanh_approx(ea), tanh_approx(eb));
+  const uint64_t hx = mul2(x, DUO_C2(0.5f));
+  return fma2(hx, t, hx);
+#undef DUO_C2
+}
 __device__ __forceinline__ void gelu_erf_sigmoid_x2(float& a, float& b) {
   unpack2(gelu_erf_sigmoid_p2(pack2(a, b)), a, b);
 }

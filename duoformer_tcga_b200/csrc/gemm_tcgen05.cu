@@ -178,27 +178,37 @@ __device__ __forceinline__ void epilogue_math(const GemmParams& p, int col, cons
         lo = add2(pack2(__uint_as_float(v[4 * j + 0]), __uint_as_float(v[4 * j + 1])), pack2(b[j].x, b[j].y));
         hi = add2(pack2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), pack2(b[j].z, b[j].w));
       }
+#ifndef DUO_GELU_TANH_FORM
+#define DUO_GELU_TANH_FORM 0  // tuning: one-MUFU tanh form of the same erf-GELU fit (csrc/Makefile `tuning`)
+#endif
+#if DUO_GELU_TANH_FORM
+      unpack2(gelu_erf_tanh_p2(lo), f[4 * j + 0], f[4 * j + 1]);
+      unpack2(gelu_erf_tanh_p2(hi), f[4 * j + 2], f[4 * j + 3]);
+#else
       unpack2(gelu_erf_sigmoid_p2(lo), f[4 * j + 0], f[4 * j + 1]);
       unpack2(gelu_erf_sigmoid_p2(hi), f[4 * j + 2], f[4 * j + 3]);
+#endif
     }
     return;
   }
+  // (packed fp32 pairs: every thread-instruction of the epilogue costs energy the power-capped step pays in clock)
   if constexpr (ET::kLnApply) {
+    const uint64_t a2 = pack2(ln_a, ln_a);
 #pragma unroll
     for (int j = 0; j < NQ; ++j) {
-      f[4 * j + 0] = fmaf(ln_a, __uint_as_float(v[4 * j + 0]), b[j].x);
-      f[4 * j + 1] = fmaf(ln_a, __uint_as_float(v[4 * j + 1]), b[j].y);
-      f[4 * j + 2] = fmaf(ln_a, __uint_as_float(v[4 * j + 2]), b[j].z);
-      f[4 * j + 3] = fmaf(ln_a, __uint_as_float(v[4 * j + 3]), b[j].w);
+      unpack2(fma2(a2, pack2(__uint_as_float(v[4 * j + 0]), __uint_as_float(v[4 * j + 1])), pack2(b[j].x, b[j].y)),
+              f[4 * j + 0], f[4 * j + 1]);
+      unpack2(fma2(a2, pack2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), pack2(b[j].z, b[j].w)),
+              f[4 * j + 2], f[4 * j + 3]);
     }
     return;
   }
 #pragma unroll
   for (int j = 0; j < NQ; ++j) {
-    f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b[j].x;
-    f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b[j].y;
-    f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b[j].z;
-    f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b[j].w;
+    unpack2(add2(pack2(__uint_as_float(v[4 * j + 0]), __uint_as_float(v[4 * j + 1])), pack2(b[j].x, b[j].y)),
+            f[4 * j + 0], f[4 * j + 1]);
+    unpack2(add2(pack2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), pack2(b[j].z, b[j].w)),
+            f[4 * j + 2], f[4 * j + 3]);
   }
   if constexpr (EPI == DUO_EPI_BF16 || EPI == DUO_EPI_F32) {
     if (p.relu) {
@@ -949,19 +959,15 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
           for (int j = 0; j < 8; ++j) {
             float x0, x1, x2, x3;
             ld_shared_v4(xrow + ((static_cast<uint32_t>(j) ^ sw128) << 4), x0, x1, x2, x3);
-            float a0 = __uint_as_float(v[4 * j + 0]) + bia[j].x, a1 = __uint_as_float(v[4 * j + 1]) + bia[j].y;
-            float a2 = __uint_as_float(v[4 * j + 2]) + bia[j].z, a3 = __uint_as_float(v[4 * j + 3]) + bia[j].w;
+            const uint64_t alo = add2(pack2(__uint_as_float(v[4 * j + 0]), __uint_as_float(v[4 * j + 1])), pack2(bia[j].x, bia[j].y));
+            const uint64_t ahi = add2(pack2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), pack2(bia[j].z, bia[j].w));
             if (p.gamma != nullptr) {
               const float4 gm = __ldg(reinterpret_cast<const float4*>(p.gamma + n0 + c) + j);
-              f[4 * j + 0] = fmaf(gm.x, a0, x0);
-              f[4 * j + 1] = fmaf(gm.y, a1, x1);
-              f[4 * j + 2] = fmaf(gm.z, a2, x2);
-              f[4 * j + 3] = fmaf(gm.w, a3, x3);
+              unpack2(fma2(pack2(gm.x, gm.y), alo, pack2(x0, x1)), f[4 * j + 0], f[4 * j + 1]);
+              unpack2(fma2(pack2(gm.z, gm.w), ahi, pack2(x2, x3)), f[4 * j + 2], f[4 * j + 3]);
             } else {
-              f[4 * j + 0] = x0 + a0;
-              f[4 * j + 1] = x1 + a1;
-              f[4 * j + 2] = x2 + a2;
-              f[4 * j + 3] = x3 + a3;
+              unpack2(add2(pack2(x0, x1), alo), f[4 * j + 0], f[4 * j + 1]);
+              unpack2(add2(pack2(x2, x3), ahi), f[4 * j + 2], f[4 * j + 3]);
             }
           }
           // LayerNorm partial statistics of the updated fp32 row over the tile's 256 columns (8 chunks):
@@ -993,11 +999,18 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
           for (int j = 0; j < 8; ++j)  // updated fp32 chunk, in place
             st_shared_v4(xrow + ((static_cast<uint32_t>(j) ^ sw128) << 4), __float_as_uint(f[4 * j + 0]),
                          __float_as_uint(f[4 * j + 1]), __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3]));
+          {
+            const uint64_t ns = pack2(-shift, -shift);
+            auto shifted = [&](int i) {  // bf16x2 of (f[i] - shift, f[i+1] - shift)
+              float a, b;
+              unpack2(add2(pack2(f[i], f[i + 1]), ns), a, b);
+              return pack_bf16x2(a, b);
+            };
 #pragma unroll
-          for (int j = 0; j < 4; ++j)  // bf16 copy of x - shift (A operand of the next GEMM)
-            st_shared_v4(brow + ((static_cast<uint32_t>(j) ^ sw64) << 4),
-                         pack_bf16x2(f[8 * j + 0] - shift, f[8 * j + 1] - shift), pack_bf16x2(f[8 * j + 2] - shift, f[8 * j + 3] - shift),
-                         pack_bf16x2(f[8 * j + 4] - shift, f[8 * j + 5] - shift), pack_bf16x2(f[8 * j + 6] - shift, f[8 * j + 7] - shift));
+            for (int j = 0; j < 4; ++j)  // bf16 copy of x - shift (A operand of the next GEMM)
+              st_shared_v4(brow + ((static_cast<uint32_t>(j) ^ sw64) << 4), shifted(8 * j), shifted(8 * j + 2),
+                           shifted(8 * j + 4), shifted(8 * j + 6));
+          }
           ptx::fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
