@@ -179,8 +179,8 @@ __device__ __forceinline__ void epilogue_math(const GemmParams& p, int col, cons
         hi = add2(pack2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), pack2(b[j].z, b[j].w));
       }
 #ifndef DUO_GELU_TANH_FORM
-#define DUO_GELU_TANH_FORM 0  // tuning: one-MUFU tanh form of the same erf-GELU fit (csrc/Makefile `tuning`)
-#endif
+#define DUO_GELU_TANH_FORM 1  // one-MUFU tanh form; 0 = sigmoid form (ex2 + rcp), csrc/Makefile `tuning`: same speed alone
+#endif                        // (0.931 vs 0.933 ms per 64 images), 1.5 % slower inside the power-capped step (192.6 vs 189.6 ms)
 #if DUO_GELU_TANH_FORM
       unpack2(gelu_erf_tanh_p2(lo), f[4 * j + 0], f[4 * j + 1]);
       unpack2(gelu_erf_tanh_p2(hi), f[4 * j + 2], f[4 * j + 3]);
