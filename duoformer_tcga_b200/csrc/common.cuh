@@ -167,9 +167,8 @@ __device__ __forceinline__ uint64_t gelu_erf_sigmoid_p2(uint64_t x) {
 // Same function in tanh form (the GEMM epilogue's default): gelu(x) = hx + hx * tanh(x * q(x^2)), hx = x / 2, q an even
 // degree-4 polynomial fitted (minimax on the gelu error) to 2.5e-5 absolute against the exact erf-GELU; ONE MUFU
 // (tanh.approx, 2^-11 relative) per element instead of ex2 + rcp and one FMA less: 10 instead of 13 thread-instructions
-// per pair.  Alone the two forms run at the same speed; inside the power-capped step every epilogue instruction is paid
-// in clock (~15 pJ per thread-instruction against ~500 pJ of MMA per output element at K = 768) and the tanh form is
-// 1.5 % faster end to end.  q turns negative beyond |x| = 11.1, so x^2 is clamped at 100 (|x| = 10: tanh has saturated
+// per pair.  Alone the two forms run at the same speed (0.931 vs 0.933 ms per 64 images); for the whole forward two ABAB
+// sessions gave -1.5 % and 0.0 % (profiles/r02_notes.md).  q turns negative beyond |x| = 11.1, so x^2 is clamped at 100 (|x| = 10: tanh has saturated
 // to +-1 in fp32 long before).
 __device__ __forceinline__ float tanh_approx(float x) {
   float r;

@@ -180,7 +180,7 @@ __device__ __forceinline__ void epilogue_math(const GemmParams& p, int col, cons
       }
 #ifndef DUO_GELU_TANH_FORM
 #define DUO_GELU_TANH_FORM 1  // one-MUFU tanh form; 0 = sigmoid form (ex2 + rcp), csrc/Makefile `tuning`: same speed alone
-#endif                        // (0.931 vs 0.933 ms per 64 images), 1.5 % slower inside the power-capped step (192.6 vs 189.6 ms)
+#endif                        // (0.931 vs 0.933 ms per 64 images), 0 - 1.5 % slower inside the step (profiles/r02_notes.md)
 #if DUO_GELU_TANH_FORM
       unpack2(gelu_erf_tanh_p2(lo), f[4 * j + 0], f[4 * j + 1]);
       unpack2(gelu_erf_tanh_p2(hi), f[4 * j + 2], f[4 * j + 3]);
@@ -191,7 +191,7 @@ __device__ __forceinline__ void epilogue_math(const GemmParams& p, int col, cons
     }
     return;
   }
-  // (packed fp32 pairs: every thread-instruction of the epilogue costs energy the power-capped step pays in clock)
+  // (packed fp32 pairs: half the issue slots of the scalar form)
   if constexpr (ET::kLnApply) {
     const uint64_t a2 = pack2(ln_a, ln_a);
 #pragma unroll
@@ -935,8 +935,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const uint32_t taddr =
             tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
         const uint32_t leader_empty = ptx::mapa(tmem_empty_bar(acc), 0);
-        float pivot = 0.f;
-        uint64_t s1 = 0, s2 = 0;  // packed (even, odd) partial sums of (x - pivot), (x - pivot)^2
+        uint64_t s1 = 0, s2 = 0;  // packed (even, odd) partial sums of (x - shift), (x - shift)^2
 #pragma unroll 1
         for (int ci = 0; ci < kChunks; ++ci, ++g) {
           const int c = col_part * kColsPerWarp + ci * 32;  // first column of the chunk inside the tile
@@ -970,46 +969,41 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
               unpack2(add2(pack2(x2, x3), ahi), f[4 * j + 2], f[4 * j + 3]);
             }
           }
-          // LayerNorm partial statistics of the updated fp32 row over the tile's 256 columns (8 chunks):
-          // shifted sums around the first element (no cancellation for |mean| >> spread)
+#pragma unroll
+          for (int j = 0; j < 8; ++j)  // updated fp32 chunk, in place
+            st_shared_v4(xrow + ((static_cast<uint32_t>(j) ^ sw128) << 4), __float_as_uint(f[4 * j + 0]),
+                         __float_as_uint(f[4 * j + 1]), __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3]));
+          // d = x - shift feeds both the bf16 copy (A operand of the next GEMM) and the LayerNorm partial statistics
+          // of the row over the tile's 256 columns: sums of d and d^2 — the previous row mean is the ideal pivot of
+          // the shifted-data variance (no cancellation for |mean| >> spread); without shift_stats these are raw sums
           if (ci == 0) {
-            pivot = f[0];
             s1 = 0;
             s2 = 0;
           }
           {
-            const uint64_t np = pack2(-pivot, -pivot);
+            const uint64_t ns = pack2(-shift, -shift);
+            uint32_t w[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              const uint64_t d = add2(pack2(f[2 * j], f[2 * j + 1]), np);
+              const uint64_t d = add2(pack2(f[2 * j], f[2 * j + 1]), ns);
               s1 = add2(s1, d);
               s2 = fma2(d, d, s2);
+              float da, db;
+              unpack2(d, da, db);
+              w[j] = pack_bf16x2(da, db);
             }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              st_shared_v4(brow + ((static_cast<uint32_t>(j) ^ sw64) << 4), w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
           }
           if (ci == kChunks - 1) {
             float a, b, q, r;
             unpack2(s1, a, b);
             unpack2(s2, q, r);
             const float sum = a + b;
-            const float mean = fmaf(sum, 1.0f / kStatCols, pivot);
+            const float mean = fmaf(sum, 1.0f / kStatCols, shift);
             const float m2 = fmaxf((q + r) - sum * sum * (1.0f / kStatCols), 0.f);
             if (valid) p.stats_out[row * parts + (n0 + c) / kStatCols] = make_float2(mean, m2);
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j)  // updated fp32 chunk, in place
-            st_shared_v4(xrow + ((static_cast<uint32_t>(j) ^ sw128) << 4), __float_as_uint(f[4 * j + 0]),
-                         __float_as_uint(f[4 * j + 1]), __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3]));
-          {
-            const uint64_t ns = pack2(-shift, -shift);
-            auto shifted = [&](int i) {  // bf16x2 of (f[i] - shift, f[i+1] - shift)
-              float a, b;
-              unpack2(add2(pack2(f[i], f[i + 1]), ns), a, b);
-              return pack_bf16x2(a, b);
-            };
-#pragma unroll
-            for (int j = 0; j < 4; ++j)  // bf16 copy of x - shift (A operand of the next GEMM)
-              st_shared_v4(brow + ((static_cast<uint32_t>(j) ^ sw64) << 4), shifted(8 * j), shifted(8 * j + 2),
-                           shifted(8 * j + 4), shifted(8 * j + 6));
           }
           ptx::fence_proxy_async();
           __syncwarp();

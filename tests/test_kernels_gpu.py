@@ -321,10 +321,11 @@ def test_gemm_residual_statistics_forwarding_producer(M, K, with_gamma):
         mean, var = _merge_stats(st, N)
         assert torch.isfinite(st).all()
         assert (mean - X.mean(dim=1)).abs().max().item() < 1e-3
-        assert relerr(var, X.var(dim=1, unbiased=False)) < 1e-4
+        # (without shift_stats the sums are taken around 0: raw fp32 sums of x and x^2 at |mean| = 14 x spread)
+        assert relerr(var, X.var(dim=1, unbiased=False)) < 1e-3
         parts = X.view(M, N // 256, 256)
         assert (st[:, :, 0] - parts.mean(dim=2)).abs().max().item() < 1e-3
-        assert relerr(st[:, :, 1], ((parts - parts.mean(dim=2, keepdim=True)) ** 2).sum(dim=2)) < 1e-3
+        assert relerr(st[:, :, 1], ((parts - parts.mean(dim=2, keepdim=True)) ** 2).sum(dim=2)) < 2e-3
 
 
 @pytest.mark.parametrize("M", [300, 256 * 60 + 77])
@@ -349,7 +350,9 @@ def test_gemm_forwarding_row_shift(M):
     want = X - shift
     assert bool(((xb.float() - want).abs() <= want.abs() * 2.0 ** -8 + 3e-5).all())
     assert (xb.float() - X).abs().min().item() > 30.0  # and it is the shifted copy, not x itself
-    assert (st[:, :, 0] - X.view(M, N // 256, 256).mean(dim=2)).abs().max().item() < 1e-3
+    parts = X.view(M, N // 256, 256)
+    assert (st[:, :, 0] - parts.mean(dim=2)).abs().max().item() < 1e-4
+    assert relerr(st[:, :, 1], ((parts - parts.mean(dim=2, keepdim=True)) ** 2).sum(dim=2)) < 1e-4  # the shift is the pivot
     with pytest.raises(AssertionError):  # the previous statistics must not be the buffer being written
         ops.gemm(A, W, bias, X, ops.EPI_RESIDUAL_F32, xb_out=xb, stats_out=st, shift_stats=st)
 
