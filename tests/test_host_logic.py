@@ -219,3 +219,19 @@ def test_pack_ln_linear_centres_the_rounded_rows_and_matches_layernorm_linear():
         e_fwd = ((out - ref).abs().max() / ref.abs().max()).item()
         e_ln = ((ln_round - ref).abs().max() / ref.abs().max()).item()
         assert e_fwd < 2.5 * e_ln + 1e-3, (offset, e_fwd, e_ln)
+
+
+def test_library_sources_have_no_environment_switches_or_cpu_paths():
+    """The product library selects its code paths from its arguments only: no getenv-controlled variants (round-1
+    scaffolding), and the Python package never imports the oracle."""
+    import glob
+    import os
+
+    from common import ROOT
+
+    for path in glob.glob(os.path.join(ROOT, "duoformer_tcga_b200", "csrc", "*.cu*")):
+        text = open(path).read()
+        assert "getenv" not in text, f"{os.path.basename(path)} reads the environment"
+    for path in glob.glob(os.path.join(ROOT, "duoformer_tcga_b200", "*.py")):
+        text = open(path).read()
+        assert "import oracle" not in text and "from oracle" not in text, f"{os.path.basename(path)} imports the oracle"
