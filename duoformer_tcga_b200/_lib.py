@@ -19,7 +19,7 @@ EPI_BF16, EPI_GELU_BF16, EPI_RESIDUAL_F32, EPI_SCATTER_F32, EPI_F32, EPI_SPLIT_B
 ACT_BF16, ACT_SPLIT, ACT_F32, ACT_F16 = range(4)
 
 # every symbol include/duoformer_sm100.h declares
-ABI_VERSION = 3  # duo_abi_version() of the library this binding was written against
+ABI_VERSION = 4  # duo_abi_version() of the library this binding was written against
 
 EXPORTED_SYMBOLS = (
     "duo_last_error",
@@ -37,6 +37,9 @@ EXPORTED_SYMBOLS = (
     "duo_im2col3x3",
     "duo_pool_to_slice",
     "duo_maxpool3x3s2",
+    "duo_conv2d",
+    "duo_stem_pack",
+    "duo_stem_conv7x7",
 )
 
 
@@ -69,6 +72,28 @@ class GemmArgs(Structure):
         ("stats_out", c_void_p),
         ("ln_stats", c_void_p),
         ("shift_stats", c_void_p),
+    ]
+
+
+class Conv2dArgs(Structure):
+    """struct duo_conv2d_args"""
+
+    _fields_ = [
+        ("inp", c_void_p),
+        ("weight", c_void_p),
+        ("bias", c_void_p),
+        ("residual", c_void_p),
+        ("out", c_void_p),
+        ("B", c_int32),
+        ("H", c_int32),
+        ("W", c_int32),
+        ("Cin", c_int32),
+        ("Cout", c_int32),
+        ("ksize", c_int32),
+        ("stride", c_int32),
+        ("relu", c_int32),
+        ("fp16", c_int32),
+        ("out_fp16", c_int32),
     ]
 
 
@@ -126,6 +151,12 @@ def load() -> ctypes.CDLL:
     lib.duo_pool_to_slice.argtypes = [c_void_p, c_int32, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]
     lib.duo_maxpool3x3s2.restype = c_int32
     lib.duo_maxpool3x3s2.argtypes = [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]
+    lib.duo_conv2d.restype = c_int32
+    lib.duo_conv2d.argtypes = [POINTER(Conv2dArgs), c_void_p]
+    lib.duo_stem_pack.restype = c_int32
+    lib.duo_stem_pack.argtypes = [c_void_p, c_int64, c_int64, c_int64, c_int64, c_float, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]
+    lib.duo_stem_conv7x7.restype = c_int32
+    lib.duo_stem_conv7x7.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]
     _lib = lib
     return lib
 

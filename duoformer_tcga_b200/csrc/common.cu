@@ -47,6 +47,6 @@ bool first_use_on_device(uint64_t& mask) {
 }  // namespace duo
 
 extern "C" const char* duo_last_error(void) { return duo::g_err; }
-extern "C" int duo_abi_version(void) { return 3; }  // 3: duo_gemm_args statistics forwarding (xb_out / stats_out / ln_stats)
+extern "C" int duo_abi_version(void) { return 4; }  // 3: duo_gemm_args statistics forwarding; 4: duo_conv2d / duo_stem_*
 extern "C" int64_t duo_launch_count(void) { return duo::g_launches; }
 extern "C" void duo_launch_count_reset(void) { duo::g_launches = 0; }

@@ -343,6 +343,72 @@ def maxpool3x3s2(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@_on_operand_device
+def conv2d(x_nhwc: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], ksize: int, stride: int,
+           relu: bool, residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+           out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """Implicit-GEMM convolution (tcgen05, TMA box loads; include/duoformer_sm100.h duo_conv2d).
+    x_nhwc [B,H,W,Cin] fp16 / bf16 contiguous; weight [Cout, ksize*ksize*Cin] in (ky, kx, c) column order, same dtype;
+    bias fp32 [Cout] or None; residual / out NHWC [B,Ho,Wo,Cout] fp16 / bf16 (out_dtype, default = the input's);
+    padding ksize // 2."""
+    assert x_nhwc.dim() == 4 and x_nhwc.is_contiguous() and x_nhwc.dtype in (torch.float16, torch.bfloat16)
+    B, H, W, Cin = x_nhwc.shape
+    Cout = weight.shape[0]
+    assert weight.dtype == x_nhwc.dtype and weight.is_contiguous() and weight.shape == (Cout, ksize * ksize * Cin)
+    pad = ksize // 2
+    Ho, Wo = (H + 2 * pad - ksize) // stride + 1, (W + 2 * pad - ksize) // stride + 1
+    if out is None:
+        out = torch.empty(B, Ho, Wo, Cout, dtype=out_dtype or x_nhwc.dtype, device=x_nhwc.device)
+    assert out.shape == (B, Ho, Wo, Cout) and out.is_contiguous() and out.dtype in (torch.float16, torch.bfloat16)
+    if residual is not None:
+        assert residual.shape == out.shape and residual.is_contiguous() and residual.dtype == out.dtype
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == Cout and bias.is_contiguous()
+    a = _lib.Conv2dArgs()
+    a.inp, a.weight, a.bias, a.residual, a.out = _ptr(x_nhwc), _ptr(weight), _ptr(bias), _ptr(residual), _ptr(out)
+    a.B, a.H, a.W, a.Cin, a.Cout = B, H, W, Cin, Cout
+    a.ksize, a.stride, a.relu, a.fp16 = ksize, stride, 1 if relu else 0, 1 if x_nhwc.dtype == torch.float16 else 0
+    a.out_fp16 = 1 if out.dtype == torch.float16 else 0
+    e0 = _prof_begin()
+    _lib.check(_lib.load().duo_conv2d(ctypes.byref(a), _stream()), "duo_conv2d")
+    if e0 is not None:
+        rows = B * Ho * Wo
+        nbytes = x_nhwc.numel() * 2 + weight.numel() * 2 + rows * Cout * 2 * (2 if residual is not None else 1)
+        _prof_end(e0, "conv", 2.0 * rows * Cout * weight.shape[1], nbytes, f"conv{ksize}x{ksize}s{stride}:{Cin}->{Cout}@{Ho}")
+    return out
+
+
+@_on_operand_device
+def stem_pack(x: torch.Tensor, scale: float, dtype: torch.dtype) -> torch.Tensor:
+    """fp32 image [B,3,H,W] (any strides) * scale -> zero-padded NHWC8 [B, H, W + 8, 8] (duo_stem_pack)."""
+    assert x.dim() == 4 and x.shape[1] == 3 and x.dtype == torch.float32 and dtype in (torch.float16, torch.bfloat16)
+    B, _, H, W = x.shape
+    out = torch.empty(B, H, W + 8, 8, dtype=dtype, device=x.device)
+    _lib.check(_lib.load().duo_stem_pack(_ptr(x), x.stride(0), x.stride(1), x.stride(2), x.stride(3), float(scale), _ptr(out),
+                                         1 if dtype == torch.float16 else 0, B, H, W, _stream()), "duo_stem_pack")
+    return out
+
+
+@_on_operand_device
+def stem_conv7x7(packed: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], relu: bool = True) -> torch.Tensor:
+    """7x7 / stride 2 / padding 3 stem convolution of a stem_pack()ed image; weight [Cout, 7*64] (ky, kx(8), c(8))."""
+    assert packed.dim() == 4 and packed.is_contiguous() and packed.shape[3] == 8
+    B, H, Wp, _ = packed.shape
+    W = Wp - 8
+    Cout = weight.shape[0]
+    assert weight.shape == (Cout, 448) and weight.is_contiguous() and weight.dtype == packed.dtype
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == Cout and bias.is_contiguous()
+    out = torch.empty(B, H // 2, W // 2, Cout, dtype=packed.dtype, device=packed.device)
+    e0 = _prof_begin()
+    _lib.check(_lib.load().duo_stem_conv7x7(_ptr(packed), _ptr(weight), _ptr(bias), _ptr(out), B, H, W, Cout, 1 if relu else 0,
+                                            1 if packed.dtype == torch.float16 else 0, _stream()), "duo_stem_conv7x7")
+    if e0 is not None:
+        rows = B * (H // 2) * (W // 2)
+        _prof_end(e0, "conv", 2.0 * rows * Cout * 448, packed.numel() * 2 + rows * Cout * 2, f"stem7x7:{Cout}@{H // 2}")
+    return out
+
+
 def launch_count() -> int:
     return int(_lib.load().duo_launch_count())
 

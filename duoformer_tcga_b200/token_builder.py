@@ -17,7 +17,7 @@ from typing import Dict, List, Optional, Tuple
 import torch
 from torch import nn
 
-from . import engine, ops
+from . import engine, ops, trunk_convs
 from .index_tables import num_scale_tokens, stages_used, token_row_maps
 
 
@@ -120,13 +120,19 @@ _FP16_TARGET_MAX = 1024.0  # rescaled activations peak near this value
 
 
 class TrunkRunner:
-    """Runs the torch/cuDNN ResNet trunk in the precision of the path (fp16 channels-last BN-folded copy of the fp32
-    master weights, re-made when they change) and returns the tapped stage maps, scaled by `act_scale`."""
+    """Runs the ResNet trunk in the precision of the path (fp16 channels-last BN-folded copy of the fp32 master
+    weights, re-made when they change) and returns the tapped stage maps, scaled by `act_scale`.
+
+    bf16 mode, ResNet-50-style trunks: every convolution runs on the package's own implicit-GEMM kernel
+    (trunk_convs.OwnTrunk, csrc/conv_tcgen05.cu); `backend = "cudnn"` selects the fused cuDNN calls instead (other
+    trunks — the r18 BasicBlocks — always use them).  fp32 mode stays on cuDNN fp32 modules."""
 
     def __init__(self):
         self._sig = None
         self._trunk: Optional[nn.Module] = None
-        self._verified = False  # fused cuDNN path checked against the plain module path for this weight set
+        self._own: Optional[trunk_convs.OwnTrunk] = None
+        self.backend = "own"    # "own": conv_tcgen05 kernels where the trunk is eligible; "cudnn": fused cuDNN calls
+        self._verified = False  # fast path checked against the plain module path for this weight set
         # dtype of the cuDNN trunk in bf16 mode: "fp16" (default: same speed as bf16, 11-bit mantissa —
         # the ~50 stacked convolutions otherwise contribute ~1e-2 of the 2e-2 bf16 error budget before
         # the first transformer block), "bf16", or "fp32"
@@ -157,7 +163,7 @@ class TrunkRunner:
 
     def _packed_trunk(self, trunk: nn.Module, precision: str, x: torch.Tensor, by_scale: bool) -> nn.Module:
         dt = self._dtype(precision)
-        sig = engine.param_signature(trunk, precision + str(dt) + str(self.act_scale_override))
+        sig = engine.param_signature(trunk, precision + str(dt) + str(self.act_scale_override) + self.backend)
         if self._trunk is None or self._sig != sig:
             t = copy.deepcopy(trunk).eval().float()
             scale = 1.0
@@ -178,10 +184,13 @@ class TrunkRunner:
                     for m in t.modules():
                         if isinstance(m, nn.Conv2d) and m.bias is not None:
                             m.bias.data.mul_(scale)
+            own = None
+            if dt != torch.float32 and self.backend == "own" and trunk_convs.eligible(t, by_scale):
+                own = trunk_convs.OwnTrunk(t, by_scale, dt)  # packed from the fp32 folded weights: fp32 biases
             t = t.to(dtype=dt, memory_format=torch.channels_last)
             for p in t.parameters():
                 p.requires_grad_(False)
-            self._trunk, self._sig, self.act_scale, self._verified = t, sig, scale, False
+            self._trunk, self._own, self._sig, self.act_scale, self._verified = t, own, sig, scale, False
         return self._trunk
 
     @torch.no_grad()
@@ -189,18 +198,24 @@ class TrunkRunner:
         """Stage maps 0..3, each multiplied by `self.act_scale` (1.0 unless the fp16 range guard engaged)."""
         t = self._packed_trunk(trunk, precision, x, by_scale)
         dt = self._dtype(precision)
-        if self.act_scale != 1.0:
-            x = x * self.act_scale
-        x = x.to(dtype=dt).contiguous(memory_format=torch.channels_last)
+        x_in = x
+        if self._own is None or not self._verified:
+            if self.act_scale != 1.0:
+                x = x * self.act_scale
+            x = x.to(dtype=dt).contiguous(memory_format=torch.channels_last)
         old_tf32 = torch.backends.cudnn.allow_tf32
         if precision == "fp32":
             torch.backends.cudnn.allow_tf32 = False
         try:
             if dt == torch.float32:
                 return self._plain_forward(t, x, by_scale)
-            # BN-folded bottlenecks through cuDNN's fused conv+bias(+add)+ReLU.  Checked ONCE per weight set against
-            # the plain module path; a mismatch (or any error of the fused calls) is raised, never papered over.
-            feats = _fused_trunk_forward(t, x, by_scale)
+            # Own implicit-GEMM convolutions, or BN-folded bottlenecks through cuDNN's fused conv+bias(+add)+ReLU.
+            # Checked ONCE per weight set against the plain module path; a mismatch (or any error of the fast path) is
+            # raised, never papered over.
+            if self._own is not None:
+                feats = self._own.features(x_in, self.act_scale)
+            else:
+                feats = _fused_trunk_forward(t, x, by_scale)
             if not self._verified:
                 ref = self._plain_forward(t, x, by_scale)
                 for k in ref:
@@ -210,7 +225,8 @@ class TrunkRunner:
                                            f"calibration max {self.calibration_max}) — pin TrunkRunner.act_scale_override")
                     err = float((a - r).abs().max() / r.abs().max().clamp_min(1e-30))
                     if err > 1e-2:
-                        raise RuntimeError(f"trunk stage {k}: fused cuDNN path differs from the module path by {err:.2e}")
+                        raise RuntimeError(f"trunk stage {k}: {'own convolution' if self._own is not None else 'fused cuDNN'} path "
+                                           f"differs from the module path by {err:.2e}")
                 self._verified = True
             return feats
         finally:

@@ -222,6 +222,43 @@ int duo_pool_to_slice(const void* in, int32_t in_kind, void* out, int64_t ld_out
 int duo_maxpool3x3s2(const void* in, int32_t kind, void* out, int32_t B, int32_t H, int32_t W, int32_t C,
                      duo_stream_t stream);
 
+/*
+ * Convolution of an NHWC 16-bit tensor as an implicit GEMM on tcgen05 / TMEM (no im2col matrix: the K loop walks the
+ * filter taps, each operand tile is one 4-D TMA box load that applies the stride and the zero padding):
+ *   out[b,ho,wo,n] = act( sum_{ky,kx,c} in[b, ho*s + ky - pad, wo*s + kx - pad, c] * weight[n, (ky,kx,c)] + bias[n]
+ *                         (+ residual[b,ho,wo,n]) ),   pad = ksize / 2,  act = ReLU if relu else identity.
+ * Replaces the cuDNN convolutions of the ResNet-50 trunk with BatchNorm folded into weight / bias
+ * (torchvision Bottleneck: conv1 1x1, conv2 3x3 stride s, conv3 1x1 + identity / downsample 1x1 stride s; the producer
+ * of the stage maps, model_wo_extra_params.py:214-224, model.py:213-223, resnet50ssl.py:35-45) and the 3x3 convolutions
+ * of the channel-token branch (projection_head.py:152-268).
+ * Cin % 64 == 0, Cout % 64 == 0, ksize 1 or 3, stride 1 or 2; in / weight fp16 (fp16 = 1) or bf16, out / residual fp16
+ * (out_fp16 = 1) or bf16 — fp16 trunk maps can feed a convolution whose un-normalised output needs bf16's range; all
+ * tensors 16-byte aligned.
+ */
+typedef struct duo_conv2d_args {
+  const void* in;       /* NHWC [B, H, W, Cin]                                              */
+  const void* weight;   /* [Cout, ksize*ksize*Cin], column order (ky, kx, c)                */
+  const float* bias;    /* [Cout] or NULL                                                   */
+  const void* residual; /* NHWC [B, Ho, Wo, Cout] added before the activation, or NULL      */
+  void* out;            /* NHWC [B, Ho, Wo, Cout], Ho = (H + 2*pad - ksize) / stride + 1    */
+  int32_t B, H, W, Cin, Cout;
+  int32_t ksize, stride, relu, fp16, out_fp16;
+} duo_conv2d_args;
+int duo_conv2d(const duo_conv2d_args* args, duo_stream_t stream);
+
+/*
+ * Trunk stem (torchvision ResNet conv1: 7x7, stride 2, padding 3, 3 input channels, + folded bn1 + ReLU;
+ * resnet50ssl.py:35-45 / model_wo_extra_params.py:214-224 child '0'..'2') on the same implicit-GEMM kernel.
+ * duo_stem_pack: fp32 image x[b,c,y,x] (element strides given: NCHW or channels-last) times `scale` ->
+ *   zero-padded NHWC8 tensor out [B, H, W + 8, 8] (pixel x at column x + 3, channels 3..7 zero), fp16 or bf16.
+ * duo_stem_conv7x7: packed -> out NHWC [B, H/2, W/2, Cout]; weight [Cout, 7 * 64] with column (ky, kx, c) at
+ *   ky*64 + kx*8 + c (kx < 7, c < 3; every other column zero).  H, W even, Cout % 64 == 0.
+ */
+int duo_stem_pack(const float* x, int64_t stride_b, int64_t stride_c, int64_t stride_h, int64_t stride_w, float scale,
+                  void* out, int32_t fp16, int32_t B, int32_t H, int32_t W, duo_stream_t stream);
+int duo_stem_conv7x7(const void* packed, const void* weight, const float* bias, void* out, int32_t B, int32_t H,
+                     int32_t W, int32_t Cout, int32_t relu, int32_t fp16, duo_stream_t stream);
+
 /* fp32 [rows, cols] (leading dim ld) -> bf16 / split bf16 (contiguous). */
 int duo_convert(const float* in, int64_t ld, void* out, int32_t out_kind, int64_t rows,
                 int32_t cols, duo_stream_t stream);

@@ -22,7 +22,7 @@ def test_c_abi_library_loads_and_exports_every_declared_symbol():
     lib = _lib.load()  # built by __graft_entry__.build(); fails loudly if missing
     for name in declared:
         assert hasattr(lib, name), f"{name} not exported"
-    assert lib.duo_abi_version() == _lib.ABI_VERSION == 3
+    assert lib.duo_abi_version() == _lib.ABI_VERSION == 4
     assert lib.duo_last_error() is not None
 
 
@@ -31,6 +31,32 @@ def test_gemm_args_struct_layout_matches_header():
     assert ctypes.sizeof(_lib.GemmArgs) == 160
     assert _lib.GemmArgs.xb_out.offset == 128 and _lib.GemmArgs.ln_stats.offset == 144 and _lib.GemmArgs.shift_stats.offset == 152
     assert _lib.GemmArgs.M.offset == 56 and _lib.GemmArgs.N.offset == 88
+
+
+def test_conv2d_args_struct_layout_matches_header():
+    # struct duo_conv2d_args: five pointers, then ten int32 (B H W Cin Cout ksize stride relu fp16 out_fp16)
+    assert ctypes.sizeof(_lib.Conv2dArgs) == 80
+    assert _lib.Conv2dArgs.out.offset == 32 and _lib.Conv2dArgs.B.offset == 40 and _lib.Conv2dArgs.out_fp16.offset == 76
+
+
+def test_own_trunk_eligibility():
+    """ResNet-50 (Bottlenecks, BatchNorm folded) runs on the own convolution kernels; r18 BasicBlocks and un-folded
+    trunks do not (they keep the cuDNN path)."""
+    import torchvision
+
+    from duoformer_tcga_b200 import token_builder, trunk_convs
+
+    r18 = torch.nn.Sequential(*list(torchvision.models.resnet18(weights=None).children())[:-2]).eval()
+    token_builder._fold_batchnorm_(r18)
+    assert not trunk_convs.eligible(r18, False)
+    r50 = torch.nn.Sequential(*list(torchvision.models.resnet50(weights=None).children())[:-2]).eval()
+    assert not trunk_convs.eligible(r50, False)  # BatchNorm not folded yet
+    token_builder._fold_batchnorm_(r50)
+    assert trunk_convs.eligible(r50, False)
+    own = trunk_convs.OwnTrunk(r50, False, torch.float16)  # packing works on the host
+    assert own.stem_w.shape == (64, 448) and len(own.layers) == 4 and [len(l) for l in own.layers] == [3, 4, 6, 3]
+    assert own.layers[1][0].ds is not None and own.layers[1][0].c2.stride == 2 and own.layers[1][1].ds is None
+    assert own.layers[0][0].c2.weight.shape == (64, 9 * 64)
 
 
 def test_ops_refuse_cpu_tensors():
