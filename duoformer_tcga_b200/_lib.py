@@ -94,6 +94,11 @@ class Conv2dArgs(Structure):
         ("relu", c_int32),
         ("fp16", c_int32),
         ("out_fp16", c_int32),
+        ("in2", c_void_p),
+        ("H2", c_int32),
+        ("W2", c_int32),
+        ("Cin2", c_int32),
+        ("stride2", c_int32),
     ]
 
 

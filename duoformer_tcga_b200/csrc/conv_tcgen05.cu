@@ -16,9 +16,13 @@
 // rows x 64 channels per warp and writes them with 4-D TMA box stores (the box clips batch rows past B).
 //
 // The 7 x 7 / stride 2 stem (3 input channels) runs on the same kernel: duo_stem_pack writes the image as a zero-padded
-// NHWC8 tensor [B, H, W + 8, 8] (3 pad pixels left, 5 right, channels 3..7 zero) and the input tensor map describes
-// OVERLAPPING windows — dim0 = 64 elements (8 pixels x 8 channels), dim1 = output column with a 2-pixel (32 B) stride —
-// so one filter row is one 64-wide K block (7 real taps x 3 real channels, the rest meets zero weights): K = 7 * 64.
+// ROW-PAIR tensor [B, H + 8, W + 8, 8] (3 pad pixels left / top, 5 right / bottom; element (R, X, 0..3) = channels of
+// padded pixel (R, X), element (R, X, 4..7) = channels of padded pixel (R + 1, X); channel 3 zero) and the input tensor
+// map describes OVERLAPPING windows — dim0 = 64 elements (8 pixels x 2 rows x 4 channels, 128 contiguous bytes), dim1 =
+// output column with a 2-pixel (32 B) stride, dim2 = padded image row (element stride 2), dim3 = batch — so TWO filter
+// rows are one 64-wide K block: K = 4 * 64 for 7 x 7 x 3 = 147 real taps (the 8th filter row / column and the 4th
+// channel meet zero weights).  (A 5-D map with the row pair as its own dimension and a 64-byte inner box was tried
+// first: cuTensorMapEncodeTiled accepts it, the loads return garbage.)
 //
 // Structure as in gemm_tcgen05.cu: persistent CTAs, N fastest; warps 0..3 epilogue (one TMEM lane quarter each),
 // warp 4 TMA producer, warp 5 MMA issuer; kStages-deep operand ring, two TMEM accumulator buffers.
@@ -35,47 +39,76 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kUmmaK = 16;
-constexpr int kThreads = 192;
-constexpr uint32_t kStagingBytesPerWarp = 2 * 32 * 128;  // two 32-row x 128 B buffers
+constexpr int kEpiWarps = 8;                    // two groups of four: group e owns accumulator buffer e (every other tile)
+constexpr int kThreads = 32 * (kEpiWarps + 2);  // + TMA producer warp + MMA issuer warp
+// Per epilogue warp a ring of kSlots staging slots (32 pixel rows x 64 channels, 4 KB, SWIZZLE_128B).  Without a residual
+// a slot is filled and TMA-stored; with one, the residual chunk is TMA-LOADED into the slot kSlots - 1 chunks ahead
+// (also across tile boundaries, so the reads overlap the MMAs of the tile), updated in place and stored — the residual
+// never travels through per-thread global loads (first version: 64 B per thread and row, 2.9 TB/s).
+constexpr int kSlots = 3;
+constexpr uint32_t kSlotBytes = 32 * 128;
+constexpr uint32_t kStagingBytesPerWarp = kSlots * kSlotBytes;
 
 template <int BLOCK_N>
 struct ConvCfg {
-  static constexpr int kStages = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8);
+  static constexpr int kStages = BLOCK_N == 128 ? 4 : 5;
   static constexpr uint32_t kABytes = kBlockM * kBlockK * 2;
   static constexpr uint32_t kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
   static constexpr uint32_t kTmemCols = 2 * BLOCK_N;
-  static constexpr uint32_t kStagingBytes = 4 * kStagingBytesPerWarp;
-  static constexpr uint32_t kBarrierBytes = (2 * kStages + 4) * 8 + 8;
+  static constexpr uint32_t kStagingBytes = kEpiWarps * kStagingBytesPerWarp;
+  static constexpr uint32_t kBarrierBytes = (2 * kStages + 4 + kEpiWarps * kSlots) * 8 + 8;
   static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kStagingBytes + kBarrierBytes + 1024;
   static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
 };
 
+// x / d for x * d < 2^40 (tile counts): one 32 x 32 -> 64 bit multiply and a shift instead of an integer division
+struct FastDiv {
+  uint64_t m;  // ceil(2^40 / d)
+  uint32_t d;
+  __host__ void init(uint32_t div) {
+    d = div;
+    m = ((uint64_t(1) << 40) + div - 1) / div;
+  }
+  // floor(x / d) = (x * m) >> 40, taken as the high half of (x << 24) * m
+  __device__ __forceinline__ uint32_t div(uint32_t x) const {
+    return static_cast<uint32_t>(__umul64hi(static_cast<uint64_t>(x) << 24, m));
+  }
+};
+
 struct ConvParams {
   const float* bias;
-  const void* residual;  // NHWC [B, Ho, Wo, Cout], same 16-bit type as out, or NULL
   int32_t B, Ho, Wo, Cout;
   int32_t cin_blocks;        // K blocks per filter tap
   int32_t taps_x, taps_y;    // filter window walked by the K loop
+  int32_t tap_step_h;        // input rows per filter-row step of the K loop (1; 2 for the stem's row-pair K blocks)
   int32_t mul_w, mul_h;      // input coordinate of tap (kx, ky) for output (w, h): w * mul_w + kx + off_w
   int32_t off_w, off_h;
+  int32_t cin2_blocks, mul2; // fused projection shortcut: K blocks of a 1x1 / stride mul2 convolution of tmap_in2, appended
   int32_t bw_log2, bh_log2;  // M tile = 2^bw_log2 x 2^bh_log2 x (128 >> (bw_log2 + bh_log2)) output pixels (w, h, batch)
-  int32_t tiles_w, tiles_h;
   int32_t num_m_blocks, num_n_blocks;
+  FastDiv div_n, div_w, div_h;  // by num_n_blocks, tiles_w, tiles_h
   int32_t relu;
-  int32_t f16;      // element type of out / residual: 1 fp16, 0 bf16
-  int32_t in_f16;   // element type of in / weight (host side: tensor maps, instruction descriptor)
   uint32_t idesc_mask;
 };
 
-__device__ __forceinline__ void tile_origin(const ConvParams& p, int m_blk, int& w0, int& h0, int& b0) {
-  const int tw = m_blk % p.tiles_w;
-  const int t = m_blk / p.tiles_w;
-  const int th = t % p.tiles_h;
-  const int tb = t / p.tiles_h;
-  w0 = tw << p.bw_log2;
-  h0 = th << p.bh_log2;
-  b0 = tb * (kBlockM >> (p.bw_log2 + p.bh_log2));
+struct TileCoords {
+  int n0, w0, h0, b0;
+};
+template <int BLOCK_N>
+__device__ __forceinline__ TileCoords tile_coords(const ConvParams& p, uint32_t tile) {
+  const uint32_t m_blk = p.div_n.div(tile);
+  const uint32_t n_blk = tile - m_blk * p.div_n.d;
+  const uint32_t t1 = p.div_w.div(m_blk);
+  const uint32_t tw = m_blk - t1 * p.div_w.d;
+  const uint32_t tb = p.div_h.div(t1);
+  const uint32_t th = t1 - tb * p.div_h.d;
+  TileCoords c;
+  c.n0 = static_cast<int>(n_blk) * BLOCK_N;
+  c.w0 = static_cast<int>(tw) << p.bw_log2;
+  c.h0 = static_cast<int>(th) << p.bh_log2;
+  c.b0 = static_cast<int>(tb) * (kBlockM >> (p.bw_log2 + p.bh_log2));
+  return c;
 }
 
 __device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const void* tmap, uint32_t bar, int32_t c0, int32_t c1,
@@ -93,14 +126,26 @@ __device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t smem_src
                : "memory");
 }
 
-__device__ __forceinline__ void unpack16x2(uint32_t u, bool f16, float& a, float& b) {
-  if (f16) {
+template <bool F16>
+__device__ __forceinline__ uint64_t unpack16x2(uint32_t u) {  // two 16-bit values -> packed fp32 pair
+  if constexpr (F16) {
     const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&u));
-    a = t.x;
-    b = t.y;
+    return pack2(t.x, t.y);
   } else {
-    a = __uint_as_float(u << 16);
-    b = __uint_as_float(u & 0xffff0000u);
+    return pack2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+  }
+}
+// packed fp32 pair -> two 16-bit values, clamped from below at `lo` (0 for ReLU, -inf otherwise: one HMNMX2 either way)
+template <bool F16>
+__device__ __forceinline__ uint32_t pack16x2_max(uint64_t v, uint32_t lo) {
+  float a, b;
+  unpack2(v, a, b);
+  if constexpr (F16) {
+    const __half2 h = __hmax2(__floats2half2_rn(a, b), *reinterpret_cast<const __half2*>(&lo));
+    return *reinterpret_cast<const uint32_t*>(&h);
+  } else {
+    const __nv_bfloat162 h = __hmax2(__floats2bfloat162_rn(a, b), *reinterpret_cast<const __nv_bfloat162*>(&lo));
+    return *reinterpret_cast<const uint32_t*>(&h);
   }
 }
 __device__ __forceinline__ uint32_t pack16x2(float a, float b, bool f16) {
@@ -114,10 +159,11 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool F16OUT, bool HAS_RES>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_w,
-                    const __grid_constant__ CUtensorMap tmap_out, const ConvParams p) {
+                    const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
+                    const __grid_constant__ CUtensorMap tmap_in2, const ConvParams p) {
   using C = ConvCfg<BLOCK_N>;
   constexpr int kStages = C::kStages;
 
@@ -130,9 +176,10 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
   auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
   auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
   const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * kStages + 4);
+  auto res_bar = [&](int i) { return bar_base + 8u * (2 * kStages + 5 + i); };  // "residual chunk loaded", one per slot
   uint32_t* tmem_ptr_generic = reinterpret_cast<uint32_t*>(smem_raw + (tmem_ptr_smem - ptx::smem_u32(smem_raw)));
 
-  constexpr int kTmaWarp = 4, kMmaWarp = 5;
+  constexpr int kTmaWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;  // highest warp ids: never starved of issue slots
   const int warp_idx = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
 
@@ -140,6 +187,8 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
     ptx::prefetch_tmap(&tmap_in);
     ptx::prefetch_tmap(&tmap_w);
     ptx::prefetch_tmap(&tmap_out);
+    if constexpr (HAS_RES) ptx::prefetch_tmap(&tmap_res);
+    if (p.cin2_blocks > 0) ptx::prefetch_tmap(&tmap_in2);
 #pragma unroll
     for (int s = 0; s < kStages; ++s) {
       ptx::mbar_init(full_bar(s), 1);
@@ -148,8 +197,9 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
 #pragma unroll
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(tmem_full_bar(a), 1);
-      ptx::mbar_init(tmem_empty_bar(a), 4);  // one arrival per epilogue warp
+      ptx::mbar_init(tmem_empty_bar(a), 4);  // one arrival per epilogue warp of the buffer's group
     }
+    for (int i = 0; i < kEpiWarps * kSlots; ++i) ptx::mbar_init(res_bar(i), 1);
     ptx::fence_barrier_init();
   }
   if (warp_idx == kMmaWarp) ptx::tmem_alloc<C::kTmemCols>(tmem_ptr_smem);
@@ -158,37 +208,48 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_generic;
 
-  const int num_k_blocks = p.taps_x * p.taps_y * p.cin_blocks;
-  const int64_t num_tiles = static_cast<int64_t>(p.num_m_blocks) * p.num_n_blocks;
+  const int num_k_blocks = p.taps_x * p.taps_y * p.cin_blocks + p.cin2_blocks;
+  const uint32_t num_tiles = static_cast<uint32_t>(p.num_m_blocks) * static_cast<uint32_t>(p.num_n_blocks);
 
   if (warp_idx == kTmaWarp) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = static_cast<int>(tile / p.num_n_blocks);
-        const int n_blk = static_cast<int>(tile - static_cast<int64_t>(m_blk) * p.num_n_blocks);
-        int w0, h0, b0;
-        tile_origin(p, m_blk, w0, h0, b0);
-        const int cw = w0 * p.mul_w + p.off_w;
-        const int ch = h0 * p.mul_h + p.off_h;
+      auto next_stage = [&](uint32_t& sa, uint32_t& sb) {
+        ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+        sa = smem_base + stage * C::kStageBytes;
+        sb = sa + C::kABytes;
+        ptx::mbar_arrive_expect_tx(full_bar(stage), C::kStageBytes);
+      };
+      auto advance = [&]() {
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      };
+      for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const TileCoords tc = tile_coords<BLOCK_N>(p, tile);
+        const int cw = tc.w0 * p.mul_w + p.off_w;
+        const int ch = tc.h0 * p.mul_h + p.off_h;
         int kb = 0;
         for (int ky = 0; ky < p.taps_y; ++ky) {
           for (int kx = 0; kx < p.taps_x; ++kx) {
             for (int cb = 0; cb < p.cin_blocks; ++cb, ++kb) {
-              ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-              const uint32_t sa = smem_base + stage * C::kStageBytes;
-              const uint32_t sb = sa + C::kABytes;
-              ptx::mbar_arrive_expect_tx(full_bar(stage), C::kStageBytes);
-              tma_load_4d(sa, &tmap_in, full_bar(stage), cb * kBlockK, cw + kx, ch + ky, b0);
-              ptx::tma_load_2d(sb, &tmap_w, full_bar(stage), kb * kBlockK, n_blk * BLOCK_N);
-              if (++stage == kStages) {
-                stage = 0;
-                phase ^= 1u;
-              }
+              uint32_t sa, sb;
+              next_stage(sa, sb);
+              tma_load_4d(sa, &tmap_in, full_bar(stage), cb * kBlockK, cw + kx, ch + p.tap_step_h * ky, tc.b0);
+              ptx::tma_load_2d(sb, &tmap_w, full_bar(stage), kb * kBlockK, tc.n0);
+              advance();
             }
           }
+        }
+        for (int cb = 0; cb < p.cin2_blocks; ++cb, ++kb) {  // fused 1x1 projection shortcut of the block input
+          uint32_t sa, sb;
+          next_stage(sa, sb);
+          tma_load_4d(sa, &tmap_in2, full_bar(stage), cb * kBlockK, tc.w0 * p.mul2, tc.h0 * p.mul2, tc.b0);
+          ptx::tma_load_2d(sb, &tmap_w, full_bar(stage), kb * kBlockK, tc.n0);
+          advance();
         }
       }
     }
@@ -200,7 +261,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         ptx::mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
@@ -229,111 +290,110 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
       }
     }
   } else {
-    // ===================== epilogue warps (0..3) =====================
-    const int quarter = warp_idx & 3;
-    const uint32_t stg = staging_base + static_cast<uint32_t>(quarter) * kStagingBytesPerWarp;
+    // ===================== epilogue warps: group e = warp / 4 takes this CTA's tiles e, e + 2, ... =====================
+    const int quarter = warp_idx & 3;  // TMEM lane quarter
+    const int grp = warp_idx >> 2;     // accumulator buffer
+    const uint32_t ring = staging_base + static_cast<uint32_t>(warp_idx) * kStagingBytesPerWarp;
     const uint32_t my_row_off = static_cast<uint32_t>(lane) * 128u;
-    uint32_t stg_buf = 0;
-    int acc = 0;
+    const uint32_t sw = static_cast<uint32_t>(lane & 7);
     uint32_t acc_phase = 0;
-    const bool f16 = p.f16 != 0;
+    const uint32_t relu_lo = p.relu ? 0u : (F16OUT ? 0xFC00FC00u : 0xFF80FF80u);  // 0 or -inf, packed pair
     const int bwm = (1 << p.bw_log2) - 1, bhm = (1 << p.bh_log2) - 1;
-    const int wh_log2 = p.bw_log2 + p.bh_log2;
-    const int r = quarter * 32 + lane;  // this thread's pixel inside the tile box
-    const int r0 = quarter * 32;        // first pixel of this warp's slab (a sub-box of the tile box)
-    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = static_cast<int>(tile / p.num_n_blocks);
-      const int n_blk = static_cast<int>(tile - static_cast<int64_t>(m_blk) * p.num_n_blocks);
-      const int n0 = n_blk * BLOCK_N;
-      int w0, h0, b0;
-      tile_origin(p, m_blk, w0, h0, b0);
-      const int pw = w0 + (r & bwm), ph = h0 + ((r >> p.bw_log2) & bhm), pb = b0 + (r >> wh_log2);
-      const int sw0 = w0 + (r0 & bwm), sh0 = h0 + ((r0 >> p.bw_log2) & bhm), sb0 = b0 + (r0 >> wh_log2);
-      const bool valid = pb < p.B;
-      const uint16_t* res_row = nullptr;
-      if (p.residual != nullptr && valid)
-        res_row = reinterpret_cast<const uint16_t*>(p.residual) +
-                  ((static_cast<int64_t>(pb) * p.Ho + ph) * p.Wo + pw) * p.Cout + n0;
-      ptx::mbar_wait(tmem_full_bar(acc), acc_phase);
+    const int r0 = quarter * 32;  // first pixel of this warp's slab (a sub-box of the tile box)
+    const int dw = r0 & bwm, dh = (r0 >> p.bw_log2) & bhm, db = r0 >> (p.bw_log2 + p.bh_log2);
+    constexpr int kChunks = BLOCK_N / 64;
+    const uint32_t tile_first = blockIdx.x + static_cast<uint32_t>(grp) * gridDim.x;
+    const uint32_t tile_step = 2u * gridDim.x;
+    // residual prefetch cursor (lane 0): next chunk to load
+    uint32_t ld_tile = tile_first, ld_g = 0;
+    int ld_ci = 0;
+    TileCoords ld_tc = {0, 0, 0, 0};
+    auto issue_load = [&]() {  // lane 0 only
+      if (ld_tile >= num_tiles) return;
+      if (ld_ci == 0) ld_tc = tile_coords<BLOCK_N>(p, ld_tile);
+      const uint32_t s = ld_g % kSlots;
+      const uint32_t bar = res_bar(warp_idx * kSlots + static_cast<int>(s));
+      ptx::mbar_arrive_expect_tx(bar, kSlotBytes);
+      tma_load_4d(ring + s * kSlotBytes, &tmap_res, bar, ld_tc.n0 + ld_ci * 64, ld_tc.w0 + dw, ld_tc.h0 + dh, ld_tc.b0 + db);
+      ++ld_g;
+      if (++ld_ci == kChunks) {
+        ld_ci = 0;
+        ld_tile += tile_step;
+      }
+    };
+    if constexpr (HAS_RES) {
+      if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i + 1 < kSlots; ++i) issue_load();
+      }
+    }
+    uint32_t g = 0;
+    for (uint32_t tile = tile_first; tile < num_tiles; tile += tile_step) {
+      const TileCoords tc = tile_coords<BLOCK_N>(p, tile);
+      ptx::mbar_wait(tmem_full_bar(grp), acc_phase);
       ptx::tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
+      acc_phase ^= 1u;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(grp * BLOCK_N);
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 64) {
-        const uint32_t buf = stg + stg_buf * (32u * 128u) + my_row_off;
+      for (int ci = 0; ci < kChunks; ++ci, ++g) {
+        const int c = ci * 64;
+        const uint32_t s = g % kSlots;
+        const uint32_t buf = ring + s * kSlotBytes + my_row_off;
+        __syncwarp();  // lane 0 has seen the slot's previous store read out (wait_group.read below)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           uint32_t v[32];
           float4 bia[8];
-          uint4 res[4];
           ptx::tmem_ld_32x32(taddr + static_cast<uint32_t>(c + 32 * h), v);
           if (p.bias != nullptr) {
-            const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + c + 32 * h);
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + tc.n0 + c + 32 * h);
 #pragma unroll
             for (int j = 0; j < 8; ++j) bia[j] = __ldg(b4 + j);
           } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j) bia[j] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
-          if (res_row != nullptr) {
-            const uint4* r4 = reinterpret_cast<const uint4*>(res_row + c + 32 * h);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) res[j] = __ldg(r4 + j);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) res[j] = make_uint4(0u, 0u, 0u, 0u);  // +0.0 in either format
+          if constexpr (HAS_RES) {
+            if (h == 0) ptx::mbar_wait(res_bar(warp_idx * kSlots + static_cast<int>(s)), (g / kSlots) & 1u);
           }
           ptx::tmem_ld_wait();
-          if (h == 1 && c + 64 >= BLOCK_N) {  // accumulator fully read: hand the TMEM buffer back
+          if (h == 1 && ci == kChunks - 1) {  // accumulator fully read: hand the TMEM buffer back
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(tmem_empty_bar(acc));
+            if (lane == 0) ptx::mbar_arrive(tmem_empty_bar(grp));
           }
-          float f[32];
+          uint64_t t[16];  // packed fp32 pairs (FADD2)
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + bia[j].x;
-            f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bia[j].y;
-            f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bia[j].z;
-            f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bia[j].w;
+            t[2 * j + 0] = add2(pack2(__uint_as_float(v[4 * j + 0]), __uint_as_float(v[4 * j + 1])), pack2(bia[j].x, bia[j].y));
+            t[2 * j + 1] = add2(pack2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), pack2(bia[j].z, bia[j].w));
           }
-          if (p.residual != nullptr) {
+          if constexpr (HAS_RES) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint32_t u[4] = {res[j].x, res[j].y, res[j].z, res[j].w};
+            for (int j = 0; j < 4; ++j) {  // 16-byte chunk (4h + j) of this pixel row of the residual, XOR-swizzled
+              uint32_t u[4];
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3])
+                           : "r"(buf + ((static_cast<uint32_t>(4 * h + j) ^ sw) << 4))
+                           : "memory");
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                float a, b;
-                unpack16x2(u[i], f16, a, b);
-                f[8 * j + 2 * i] += a;
-                f[8 * j + 2 * i + 1] += b;
-              }
+              for (int i = 0; i < 4; ++i) t[4 * j + i] = add2(t[4 * j + i], unpack16x2<F16OUT>(u[i]));
             }
           }
-          if (p.relu) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-          }
-          if (h == 0) {
-            if (lane == 0) ptx::tma_store_wait_read<1>();  // buffer `stg_buf` no longer being read
-            __syncwarp();
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j)  // 16-byte chunk (4h + j) of this pixel row, XOR-swizzled
-            st_shared_v4(buf + (static_cast<uint32_t>((4 * h + j) ^ (lane & 7)) << 4),
-                         pack16x2(f[8 * j + 0], f[8 * j + 1], f16), pack16x2(f[8 * j + 2], f[8 * j + 3], f16),
-                         pack16x2(f[8 * j + 4], f[8 * j + 5], f16), pack16x2(f[8 * j + 6], f[8 * j + 7], f16));
+          for (int j = 0; j < 4; ++j)  // in place: the same 16-byte chunks this thread just read
+            st_shared_v4(buf + ((static_cast<uint32_t>(4 * h + j) ^ sw) << 4), pack16x2_max<F16OUT>(t[4 * j + 0], relu_lo),
+                         pack16x2_max<F16OUT>(t[4 * j + 1], relu_lo), pack16x2_max<F16OUT>(t[4 * j + 2], relu_lo),
+                         pack16x2_max<F16OUT>(t[4 * j + 3], relu_lo));
         }
         ptx::fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          tma_store_4d(&tmap_out, stg + stg_buf * (32u * 128u), n0 + c, sw0, sh0, sb0);
+          tma_store_4d(&tmap_out, ring + s * kSlotBytes, tc.n0 + c, tc.w0 + dw, tc.h0 + dh, tc.b0 + db);
           ptx::tma_store_commit();
+          ptx::tma_store_wait_read<1>();      // the previous chunk's store has left its slot ...
+          if constexpr (HAS_RES) issue_load();  // ... which is the one chunk g + kSlots - 1 uses
         }
-        stg_buf ^= 1u;
-      }
-      if (++acc == 2) {
-        acc = 0;
-        acc_phase ^= 1u;
       }
     }
     if (lane == 0) ptx::tma_store_wait<0>();
@@ -347,25 +407,32 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
   }
 }
 
-// Image -> zero-padded NHWC8 operand of the stem convolution: out[b, y, 3 + x, c] = scale * x[b, c, y, x] for c < 3,
-// zero elsewhere ([B, H, W + 8, 8]); any input strides (NCHW or channels-last), one 16-byte store per pixel.
+// Image -> zero-padded row-pair operand of the stem convolution ([B, H + 8, W + 8, 8]):
+//   out[b, R, X, c] = scale * x[b, c, R - 3, X - 3],  out[b, R, X, 4 + c] = scale * x[b, c, R - 2, X - 3]  for c < 3,
+// zero outside the image and for c = 3; any input strides (NCHW or channels-last), one 16-byte store per pixel.
 __global__ void stem_pack_kernel(const float* __restrict__ x, int64_t sb, int64_t sc, int64_t sh, int64_t sw, float scale,
                                  uint4* __restrict__ out, int B, int H, int W, int f16) {
-  const int Wp = W + 8;
-  const int64_t total = static_cast<int64_t>(B) * H * Wp;
+  const int Wp = W + 8, Hp = H + 8;
+  const int64_t total = static_cast<int64_t>(B) * Hp * Wp;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int xp = static_cast<int>(i % Wp);
+    const int xi = static_cast<int>(i % Wp) - 3;
     const int64_t t = i / Wp;
-    const int y = static_cast<int>(t % H);
-    const int64_t b = t / H;
+    const int yi = static_cast<int>(t % Hp) - 3;
+    const int64_t b = t / Hp;
     uint4 o = make_uint4(0u, 0u, 0u, 0u);
-    const int xi = xp - 3;
     if (xi >= 0 && xi < W) {
-      const float* s = x + b * sb + y * sh + xi * sw;
-      const float c0 = __ldg(s) * scale, c1 = __ldg(s + sc) * scale, c2 = __ldg(s + 2 * sc) * scale;
-      o.x = pack16x2(c0, c1, f16 != 0);
-      o.y = pack16x2(c2, 0.f, f16 != 0);
+      const float* s = x + b * sb + xi * sw;
+      if (yi >= 0 && yi < H) {
+        const float* r = s + yi * sh;
+        o.x = pack16x2(__ldg(r) * scale, __ldg(r + sc) * scale, f16 != 0);
+        o.y = pack16x2(__ldg(r + 2 * sc) * scale, 0.f, f16 != 0);
+      }
+      if (yi + 1 >= 0 && yi + 1 < H) {
+        const float* r = s + (yi + 1) * sh;
+        o.z = pack16x2(__ldg(r) * scale, __ldg(r + sc) * scale, f16 != 0);
+        o.w = pack16x2(__ldg(r + 2 * sc) * scale, 0.f, f16 != 0);
+      }
     }
     out[i] = o;
   }
@@ -391,10 +458,10 @@ PFN_encodeTiled encode_fn() {
 // Tensor maps are a pure function of this key; the trunk calls with the same ~110 descriptions every step.
 struct MapKey {
   const void* base;
-  uint64_t dims[4];
-  uint64_t strides[3];  // bytes, dims 1..3
-  uint32_t box[4];
-  uint32_t estr[4];
+  uint64_t dims[5];
+  uint64_t strides[4];  // bytes, dims 1..4
+  uint32_t box[5];
+  uint32_t estr[5];
   int32_t rank, f16;
 };
 constexpr int kMapCacheSize = 256;
@@ -418,22 +485,22 @@ int make_map(CUtensorMap* tm, const MapKey& k) {
     set_error("cuTensorMapEncodeTiled entry point not available");
     return DUO_ERR_CUDA;
   }
-  cuuint64_t gdim[4], gstr[3];
-  cuuint32_t box[4], estr[4];
-  for (int i = 0; i < 4; ++i) {
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t box[5], estr[5];
+  for (int i = 0; i < 5; ++i) {
     gdim[i] = k.dims[i];
     box[i] = k.box[i];
     estr[i] = k.estr[i];
   }
-  for (int i = 0; i < 3; ++i) gstr[i] = k.strides[i];
+  for (int i = 0; i < 4; ++i) gstr[i] = k.strides[i];
   CUresult r = fn(tm, k.f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
                   static_cast<cuuint32_t>(k.rank), const_cast<void*>(k.base), gdim, gstr, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed: CUresult %d (rank %d dims %llu %llu %llu %llu box %u %u %u %u estr %u %u %u %u)",
+    set_error("cuTensorMapEncodeTiled failed: CUresult %d (rank %d dims %llu %llu %llu %llu %llu box %u %u %u %u %u)",
               (int)r, k.rank, (unsigned long long)k.dims[0], (unsigned long long)k.dims[1], (unsigned long long)k.dims[2],
-              (unsigned long long)k.dims[3], k.box[0], k.box[1], k.box[2], k.box[3], k.estr[0], k.estr[1], k.estr[2], k.estr[3]);
+              (unsigned long long)k.dims[3], (unsigned long long)k.dims[4], k.box[0], k.box[1], k.box[2], k.box[3], k.box[4]);
     return DUO_ERR_CUDA;
   }
   const int slot = mc.used < kMapCacheSize ? mc.used++ : (mc.next = (mc.next + 1) % kMapCacheSize);
@@ -445,7 +512,7 @@ int make_map(CUtensorMap* tm, const MapKey& k) {
 MapKey zero_key() {
   MapKey k;
   memset(&k, 0, sizeof(k));
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < 5; ++i) {
     k.dims[i] = 1;
     k.box[i] = 1;
     k.estr[i] = 1;
@@ -459,43 +526,56 @@ int pow2_divisor_log2(int v, int cap_log2) {
   return l;
 }
 
-template <int BLOCK_N>
-int launch_conv(const CUtensorMap& ti, const CUtensorMap& tw, const CUtensorMap& to, const ConvParams& p, cudaStream_t st) {
+template <int BLOCK_N, bool F16OUT, bool HAS_RES>
+int launch_conv(const CUtensorMap& ti, const CUtensorMap& tw, const CUtensorMap& to, const CUtensorMap& tr,
+                const CUtensorMap& ti2, const ConvParams& p, cudaStream_t st) {
   using C = ConvCfg<BLOCK_N>;
   static uint64_t configured = 0;  // per device
-  auto kfn = conv_tcgen05_kernel<BLOCK_N>;
+  auto kfn = conv_tcgen05_kernel<BLOCK_N, F16OUT, HAS_RES>;
   if (first_use_on_device(configured))
     DUO_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(C::kSmemBytes)));
   const int64_t tiles = static_cast<int64_t>(p.num_m_blocks) * p.num_n_blocks;
   const int sms = device_sm_count();
   const int grid = static_cast<int>(tiles < sms ? tiles : sms);
-  kfn<<<grid, kThreads, C::kSmemBytes, st>>>(ti, tw, to, p);
+  kfn<<<grid, kThreads, C::kSmemBytes, st>>>(ti, tw, to, tr, ti2, p);
   DUO_LAUNCH_CHECK("conv_tcgen05_kernel");
   return DUO_OK;
 }
 
-// Shared tail of duo_conv2d / duo_stem_conv7x7: tile box, output / weight maps, launch.
-int run_conv(const CUtensorMap& tmap_in, ConvParams& p, const void* weight, int64_t k_total, void* out, int bw_log2,
-             int bh_log2, cudaStream_t st) {
+template <int BLOCK_N>
+int dispatch_conv(bool f16out, bool has_res, const CUtensorMap& ti, const CUtensorMap& tw, const CUtensorMap& to,
+                  const CUtensorMap& tr, const CUtensorMap& ti2, const ConvParams& p, cudaStream_t st) {
+  if (f16out) return has_res ? launch_conv<BLOCK_N, true, true>(ti, tw, to, tr, ti2, p, st)
+                             : launch_conv<BLOCK_N, true, false>(ti, tw, to, tr, ti2, p, st);
+  return has_res ? launch_conv<BLOCK_N, false, true>(ti, tw, to, tr, ti2, p, st)
+                 : launch_conv<BLOCK_N, false, false>(ti, tw, to, tr, ti2, p, st);
+}
+
+// Shared tail of duo_conv2d / duo_stem_conv7x7: tile box, output / weight / residual maps, launch.
+// `tmap_in2` is only read when p.cin2_blocks > 0.
+int run_conv(const CUtensorMap& tmap_in, const CUtensorMap& tmap_in2, ConvParams& p, const void* weight, int64_t k_total,
+             void* out, const void* residual, bool in_f16, bool out_f16, int bw_log2, int bh_log2, cudaStream_t st) {
   const int bb = kBlockM >> (bw_log2 + bh_log2);
   p.bw_log2 = bw_log2;
   p.bh_log2 = bh_log2;
-  p.tiles_w = p.Wo >> bw_log2;
-  p.tiles_h = p.Ho >> bh_log2;
-  const int64_t m_blocks = static_cast<int64_t>(p.tiles_w) * p.tiles_h * ((p.B + bb - 1) / bb);
-  DUO_CHECK_ARG(m_blocks < (int64_t(1) << 30), "duo_conv2d: too many tiles");
+  const int tiles_w = p.Wo >> bw_log2, tiles_h = p.Ho >> bh_log2;
+  const int64_t m_blocks = static_cast<int64_t>(tiles_w) * tiles_h * ((p.B + bb - 1) / bb);
   p.num_m_blocks = static_cast<int32_t>(m_blocks);
-  const int sms = device_sm_count();
-  int block_n = 64;
-  if (p.Cout % 256 == 0 && m_blocks * (p.Cout / 256) >= 2 * sms) block_n = 256;
-  else if (p.Cout % 128 == 0) block_n = 128;
+  const int block_n = p.Cout % 128 == 0 ? 128 : 64;
   p.num_n_blocks = p.Cout / block_n;
+  const int64_t tiles = m_blocks * p.num_n_blocks;
+  // FastDiv: x * d < 2^40 for every quotient taken (x <= tiles, d <= 2^15)
+  DUO_CHECK_ARG(tiles < (int64_t(1) << 24) && p.num_n_blocks < (1 << 15) && tiles_w < (1 << 15) && tiles_h < (1 << 15),
+                "duo_conv2d: too many tiles (%lld)", (long long)tiles);
+  p.div_n.init(static_cast<uint32_t>(p.num_n_blocks));
+  p.div_w.init(static_cast<uint32_t>(tiles_w));
+  p.div_h.init(static_cast<uint32_t>(tiles_h));
 
   CUtensorMap tw, to;
   MapKey kw = zero_key();
   kw.base = weight;
   kw.rank = 2;
-  kw.f16 = p.in_f16;
+  kw.f16 = in_f16;
   kw.dims[0] = static_cast<uint64_t>(k_total);
   kw.dims[1] = static_cast<uint64_t>(p.Cout);
   kw.strides[0] = static_cast<uint64_t>(k_total) * 2;
@@ -510,7 +590,7 @@ int run_conv(const CUtensorMap& tmap_in, ConvParams& p, const void* weight, int6
   MapKey ko = zero_key();
   ko.base = out;
   ko.rank = 4;
-  ko.f16 = p.f16;
+  ko.f16 = out_f16;
   ko.dims[0] = static_cast<uint64_t>(p.Cout);
   ko.dims[1] = static_cast<uint64_t>(p.Wo);
   ko.dims[2] = static_cast<uint64_t>(p.Ho);
@@ -524,11 +604,35 @@ int run_conv(const CUtensorMap& tmap_in, ConvParams& p, const void* weight, int6
   ko.box[3] = static_cast<uint32_t>(sb_n);
   rc = make_map(&to, ko);
   if (rc != DUO_OK) return rc;
-  switch (block_n) {
-    case 256: return launch_conv<256>(tmap_in, tw, to, p, st);
-    case 128: return launch_conv<128>(tmap_in, tw, to, p, st);
-    default: return launch_conv<64>(tmap_in, tw, to, p, st);
+  CUtensorMap tr = to;  // residual: the output's geometry on another base
+  if (residual != nullptr) {
+    ko.base = residual;
+    rc = make_map(&tr, ko);
+    if (rc != DUO_OK) return rc;
   }
+  if (block_n == 128) return dispatch_conv<128>(out_f16, residual != nullptr, tmap_in, tw, to, tr, tmap_in2, p, st);
+  return dispatch_conv<64>(out_f16, residual != nullptr, tmap_in, tw, to, tr, tmap_in2, p, st);
+}
+
+// Input map of an NHWC tensor read with convolution stride `stride` by tiles of (1 << bw_log2) x (1 << bh_log2) x bb pixels.
+int input_map(CUtensorMap* tm, const void* base, int B, int H, int W, int C, int stride, int bw_log2, int bh_log2, bool f16) {
+  MapKey ki = zero_key();
+  ki.base = base;
+  ki.rank = 4;
+  ki.f16 = f16;
+  ki.dims[0] = static_cast<uint64_t>(C);
+  ki.dims[1] = static_cast<uint64_t>(W);
+  ki.dims[2] = static_cast<uint64_t>(H);
+  ki.dims[3] = static_cast<uint64_t>(B);
+  ki.strides[0] = static_cast<uint64_t>(C) * 2;
+  ki.strides[1] = ki.strides[0] * W;
+  ki.strides[2] = ki.strides[1] * H;
+  ki.box[0] = kBlockK;
+  ki.box[1] = static_cast<uint32_t>((1 << bw_log2) * stride);
+  ki.box[2] = static_cast<uint32_t>((1 << bh_log2) * stride);
+  ki.box[3] = static_cast<uint32_t>(kBlockM >> (bw_log2 + bh_log2));
+  ki.estr[1] = ki.estr[2] = static_cast<uint32_t>(stride);
+  return make_map(tm, ki);
 }
 
 }  // namespace
@@ -544,51 +648,45 @@ extern "C" int duo_conv2d(const duo_conv2d_args* a, duo_stream_t stream) {
   DUO_CHECK_ARG(a->ksize == 1 || a->ksize == 3, "duo_conv2d: ksize=%d (1 or 3)", a->ksize);
   DUO_CHECK_ARG(a->stride == 1 || a->stride == 2, "duo_conv2d: stride=%d (1 or 2)", a->stride);
   DUO_CHECK_ARG(((reinterpret_cast<uintptr_t>(a->in) | reinterpret_cast<uintptr_t>(a->weight) |
-                  reinterpret_cast<uintptr_t>(a->out) | reinterpret_cast<uintptr_t>(a->residual)) & 15) == 0,
+                  reinterpret_cast<uintptr_t>(a->out) | reinterpret_cast<uintptr_t>(a->residual) |
+                  reinterpret_cast<uintptr_t>(a->in2)) & 15) == 0,
                 "duo_conv2d: tensors must be 16-byte aligned");
-  DUO_CHECK_ARG(a->out != a->in && a->out != a->residual, "duo_conv2d: out must not alias in / residual");
+  DUO_CHECK_ARG(a->out != a->in && a->out != a->residual && a->out != a->in2, "duo_conv2d: out must not alias an input");
   const int pad = a->ksize / 2;
   ConvParams p;
   memset(&p, 0, sizeof(p));
   p.bias = a->bias;
-  p.residual = a->residual;
   p.B = a->B;
   p.Ho = (a->H + 2 * pad - a->ksize) / a->stride + 1;
   p.Wo = (a->W + 2 * pad - a->ksize) / a->stride + 1;
   p.Cout = a->Cout;
   p.cin_blocks = a->Cin / 64;
   p.taps_x = p.taps_y = a->ksize;
+  p.tap_step_h = 1;
   p.mul_w = p.mul_h = a->stride;
   p.off_w = p.off_h = -pad;
   p.relu = a->relu;
-  p.f16 = a->out_fp16 ? 1 : 0;
-  p.in_f16 = a->fp16 ? 1 : 0;
   p.idesc_mask = a->fp16 ? ~((1u << 7) | (1u << 10)) : ~0u;  // a_format / b_format: 1 = BF16, 0 = F16
   // tile box: powers of two dividing the output map, w first (at most 16 wide), then h, the rest along the batch
   const int bw_log2 = pow2_divisor_log2(p.Wo, 4);
   const int bh_log2 = pow2_divisor_log2(p.Ho, 7 - bw_log2 < 4 ? 7 - bw_log2 : 4);
-  const int bb = kBlockM >> (bw_log2 + bh_log2);
-
-  CUtensorMap ti;
-  MapKey ki = zero_key();
-  ki.base = a->in;
-  ki.rank = 4;
-  ki.f16 = p.in_f16;
-  ki.dims[0] = static_cast<uint64_t>(a->Cin);
-  ki.dims[1] = static_cast<uint64_t>(a->W);
-  ki.dims[2] = static_cast<uint64_t>(a->H);
-  ki.dims[3] = static_cast<uint64_t>(a->B);
-  ki.strides[0] = static_cast<uint64_t>(a->Cin) * 2;
-  ki.strides[1] = ki.strides[0] * a->W;
-  ki.strides[2] = ki.strides[1] * a->H;
-  ki.box[0] = kBlockK;
-  ki.box[1] = static_cast<uint32_t>((1 << bw_log2) * a->stride);
-  ki.box[2] = static_cast<uint32_t>((1 << bh_log2) * a->stride);
-  ki.box[3] = static_cast<uint32_t>(bb);
-  ki.estr[1] = ki.estr[2] = static_cast<uint32_t>(a->stride);
-  int rc = make_map(&ti, ki);
+  CUtensorMap ti, ti2;
+  int rc = input_map(&ti, a->in, a->B, a->H, a->W, a->Cin, a->stride, bw_log2, bh_log2, a->fp16 != 0);
   if (rc != DUO_OK) return rc;
-  return run_conv(ti, p, a->weight, static_cast<int64_t>(a->ksize) * a->ksize * a->Cin, a->out, bw_log2, bh_log2,
+  ti2 = ti;
+  int64_t k_total = static_cast<int64_t>(a->ksize) * a->ksize * a->Cin;
+  if (a->in2 != nullptr) {  // fused 1x1 projection shortcut
+    DUO_CHECK_ARG(a->Cin2 > 0 && a->Cin2 % 64 == 0 && (a->stride2 == 1 || a->stride2 == 2),
+                  "duo_conv2d: in2 needs Cin2 %% 64 == 0 and stride2 1 or 2 (Cin2=%d stride2=%d)", a->Cin2, a->stride2);
+    DUO_CHECK_ARG((a->H2 - 1) / a->stride2 + 1 == p.Ho && (a->W2 - 1) / a->stride2 + 1 == p.Wo,
+                  "duo_conv2d: in2 [%d x %d] / stride %d does not produce the output map %d x %d", a->H2, a->W2, a->stride2, p.Ho, p.Wo);
+    p.cin2_blocks = a->Cin2 / 64;
+    p.mul2 = a->stride2;
+    rc = input_map(&ti2, a->in2, a->B, a->H2, a->W2, a->Cin2, a->stride2, bw_log2, bh_log2, a->fp16 != 0);
+    if (rc != DUO_OK) return rc;
+    k_total += a->Cin2;
+  }
+  return run_conv(ti, ti2, p, a->weight, k_total, a->out, a->residual, a->fp16 != 0, a->out_fp16 != 0, bw_log2, bh_log2,
                   reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -598,7 +696,7 @@ extern "C" int duo_stem_pack(const float* x, int64_t stride_b, int64_t stride_c,
   using namespace duo;
   DUO_CHECK_ARG(x && out && B > 0 && H > 0 && W > 0, "duo_stem_pack: bad arguments");
   DUO_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15) == 0, "duo_stem_pack: out must be 16-byte aligned");
-  const int64_t total = static_cast<int64_t>(B) * H * (W + 8);
+  const int64_t total = static_cast<int64_t>(B) * (H + 8) * (W + 8);
   const int threads = 256;
   const int64_t want = (total + threads - 1) / threads;
   const int64_t cap = static_cast<int64_t>(device_sm_count()) * 16;
@@ -626,30 +724,30 @@ extern "C" int duo_stem_conv7x7(const void* packed, const void* weight, const fl
   p.Cout = Cout;
   p.cin_blocks = 1;
   p.taps_x = 1;
-  p.taps_y = 7;
-  p.mul_w = 1;  // the output-column stride (2 pixels) is the tensor map's dim-1 stride
+  p.taps_y = 4;  // K blocks: filter rows (0,1), (2,3), (4,5), (6, zero)
+  p.tap_step_h = 2;
+  p.mul_w = 1;   // the output-column stride (2 pixels) is the tensor map's dim-1 stride
   p.mul_h = 2;
-  p.off_w = 0;  // the 3 pad pixels are physically present in the packed tensor
-  p.off_h = -3;
+  p.off_w = 0;   // the pad pixels / rows are physically present in the packed tensor
+  p.off_h = 0;
   p.relu = relu;
-  p.f16 = p.in_f16 = fp16 ? 1 : 0;
   p.idesc_mask = fp16 ? ~((1u << 7) | (1u << 10)) : ~0u;
   const int bw_log2 = pow2_divisor_log2(p.Wo, 4);
   const int bh_log2 = pow2_divisor_log2(p.Ho, 7 - bw_log2 < 4 ? 7 - bw_log2 : 4);
   const int bb = kBlockM >> (bw_log2 + bh_log2);
-  const int Wp = W + 8;
+  const uint64_t row_pitch = static_cast<uint64_t>(W + 8) * 16;  // bytes of one packed image row
   CUtensorMap ti;
   MapKey ki = zero_key();
   ki.base = packed;
   ki.rank = 4;
-  ki.f16 = p.f16;
-  ki.dims[0] = 64;                               // 8 pixels x 8 channels of one filter row's window
+  ki.f16 = fp16 ? 1 : 0;
+  ki.dims[0] = 64;                               // 8 pixels x (2 rows x 4 channels): 128 contiguous bytes
   ki.dims[1] = static_cast<uint64_t>(p.Wo);      // output column: windows 2 pixels (32 B) apart, overlapping
-  ki.dims[2] = static_cast<uint64_t>(H);
+  ki.dims[2] = static_cast<uint64_t>(H + 8);     // padded image row
   ki.dims[3] = static_cast<uint64_t>(B);
   ki.strides[0] = 32;
-  ki.strides[1] = static_cast<uint64_t>(Wp) * 16;
-  ki.strides[2] = ki.strides[1] * H;
+  ki.strides[1] = row_pitch;
+  ki.strides[2] = row_pitch * (H + 8);
   ki.box[0] = 64;
   ki.box[1] = 1u << bw_log2;
   ki.box[2] = static_cast<uint32_t>(2 << bh_log2);
@@ -657,5 +755,6 @@ extern "C" int duo_stem_conv7x7(const void* packed, const void* weight, const fl
   ki.estr[2] = 2;
   int rc = make_map(&ti, ki);
   if (rc != DUO_OK) return rc;
-  return run_conv(ti, p, weight, 7 * 64, out, bw_log2, bh_log2, reinterpret_cast<cudaStream_t>(stream));
+  return run_conv(ti, ti, p, weight, 4 * 64, out, nullptr, fp16 != 0, fp16 != 0, bw_log2, bh_log2,
+                  reinterpret_cast<cudaStream_t>(stream));
 }

@@ -346,15 +346,20 @@ def maxpool3x3s2(x: torch.Tensor) -> torch.Tensor:
 @_on_operand_device
 def conv2d(x_nhwc: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], ksize: int, stride: int,
            relu: bool, residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-           out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+           out_dtype: Optional[torch.dtype] = None, in2: Optional[torch.Tensor] = None, stride2: int = 1) -> torch.Tensor:
     """Implicit-GEMM convolution (tcgen05, TMA box loads; include/duoformer_sm100.h duo_conv2d).
     x_nhwc [B,H,W,Cin] fp16 / bf16 contiguous; weight [Cout, ksize*ksize*Cin] in (ky, kx, c) column order, same dtype;
     bias fp32 [Cout] or None; residual / out NHWC [B,Ho,Wo,Cout] fp16 / bf16 (out_dtype, default = the input's);
-    padding ksize // 2."""
+    padding ksize // 2.  in2 [B,H2,W2,Cin2] (+ stride2): fused 1x1 projection shortcut of another tensor, its weights are
+    the last Cin2 columns of `weight` ([Cout, ksize*ksize*Cin + Cin2])."""
     assert x_nhwc.dim() == 4 and x_nhwc.is_contiguous() and x_nhwc.dtype in (torch.float16, torch.bfloat16)
     B, H, W, Cin = x_nhwc.shape
     Cout = weight.shape[0]
-    assert weight.dtype == x_nhwc.dtype and weight.is_contiguous() and weight.shape == (Cout, ksize * ksize * Cin)
+    Cin2 = 0
+    if in2 is not None:
+        assert in2.dim() == 4 and in2.is_contiguous() and in2.dtype == x_nhwc.dtype and in2.shape[0] == B
+        Cin2 = in2.shape[3]
+    assert weight.dtype == x_nhwc.dtype and weight.is_contiguous() and weight.shape == (Cout, ksize * ksize * Cin + Cin2)
     pad = ksize // 2
     Ho, Wo = (H + 2 * pad - ksize) // stride + 1, (W + 2 * pad - ksize) // stride + 1
     if out is None:
@@ -369,21 +374,26 @@ def conv2d(x_nhwc: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tens
     a.B, a.H, a.W, a.Cin, a.Cout = B, H, W, Cin, Cout
     a.ksize, a.stride, a.relu, a.fp16 = ksize, stride, 1 if relu else 0, 1 if x_nhwc.dtype == torch.float16 else 0
     a.out_fp16 = 1 if out.dtype == torch.float16 else 0
+    if in2 is not None:
+        a.in2, a.H2, a.W2, a.Cin2, a.stride2 = _ptr(in2), in2.shape[1], in2.shape[2], Cin2, stride2
     e0 = _prof_begin()
     _lib.check(_lib.load().duo_conv2d(ctypes.byref(a), _stream()), "duo_conv2d")
     if e0 is not None:
         rows = B * Ho * Wo
         nbytes = x_nhwc.numel() * 2 + weight.numel() * 2 + rows * Cout * 2 * (2 if residual is not None else 1)
-        _prof_end(e0, "conv", 2.0 * rows * Cout * weight.shape[1], nbytes, f"conv{ksize}x{ksize}s{stride}:{Cin}->{Cout}@{Ho}")
+        nbytes += 0 if in2 is None else in2.numel() * 2 // (stride2 * stride2)
+        tag = f"conv{ksize}x{ksize}s{stride}:{Cin}->{Cout}@{Ho}" + ("+res" if residual is not None else "") + (f"+ds{Cin2}" if in2 is not None else "")
+        _prof_end(e0, "conv", 2.0 * rows * Cout * weight.shape[1], nbytes, tag)
     return out
 
 
 @_on_operand_device
 def stem_pack(x: torch.Tensor, scale: float, dtype: torch.dtype) -> torch.Tensor:
-    """fp32 image [B,3,H,W] (any strides) * scale -> zero-padded NHWC8 [B, H, W + 8, 8] (duo_stem_pack)."""
+    """fp32 image [B,3,H,W] (any strides) * scale -> zero-padded row-pair tensor [B, H + 8, W + 8, 8]: channels 0..3 =
+    pixel (R - 3, X - 3), channels 4..7 = pixel (R - 2, X - 3) (duo_stem_pack)."""
     assert x.dim() == 4 and x.shape[1] == 3 and x.dtype == torch.float32 and dtype in (torch.float16, torch.bfloat16)
     B, _, H, W = x.shape
-    out = torch.empty(B, H, W + 8, 8, dtype=dtype, device=x.device)
+    out = torch.empty(B, H + 8, W + 8, 8, dtype=dtype, device=x.device)
     _lib.check(_lib.load().duo_stem_pack(_ptr(x), x.stride(0), x.stride(1), x.stride(2), x.stride(3), float(scale), _ptr(out),
                                          1 if dtype == torch.float16 else 0, B, H, W, _stream()), "duo_stem_pack")
     return out
@@ -391,12 +401,12 @@ def stem_pack(x: torch.Tensor, scale: float, dtype: torch.dtype) -> torch.Tensor
 
 @_on_operand_device
 def stem_conv7x7(packed: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], relu: bool = True) -> torch.Tensor:
-    """7x7 / stride 2 / padding 3 stem convolution of a stem_pack()ed image; weight [Cout, 7*64] (ky, kx(8), c(8))."""
+    """7x7 / stride 2 / padding 3 stem convolution of a stem_pack()ed image; weight [Cout, 256] (pack_stem_weight)."""
     assert packed.dim() == 4 and packed.is_contiguous() and packed.shape[3] == 8
-    B, H, Wp, _ = packed.shape
-    W = Wp - 8
+    B, Hp, Wp, _ = packed.shape
+    H, W = Hp - 8, Wp - 8
     Cout = weight.shape[0]
-    assert weight.shape == (Cout, 448) and weight.is_contiguous() and weight.dtype == packed.dtype
+    assert weight.shape == (Cout, 256) and weight.is_contiguous() and weight.dtype == packed.dtype
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() == Cout and bias.is_contiguous()
     out = torch.empty(B, H // 2, W // 2, Cout, dtype=packed.dtype, device=packed.device)
@@ -405,8 +415,18 @@ def stem_conv7x7(packed: torch.Tensor, weight: torch.Tensor, bias: Optional[torc
                                             1 if packed.dtype == torch.float16 else 0, _stream()), "duo_stem_conv7x7")
     if e0 is not None:
         rows = B * (H // 2) * (W // 2)
-        _prof_end(e0, "conv", 2.0 * rows * Cout * 448, packed.numel() * 2 + rows * Cout * 2, f"stem7x7:{Cout}@{H // 2}")
+        _prof_end(e0, "conv", 2.0 * rows * Cout * 256, packed.numel() * 2 + rows * Cout * 2, f"stem7x7:{Cout}@{H // 2}")
     return out
+
+
+def pack_stem_weight(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """[Cout, 3, 7, 7] -> 16-bit [Cout, 256]: tap (ky, kx, c) at column (ky // 2) * 64 + kx * 8 + (ky % 2) * 4 + c
+    (filter rows and columns padded to 8, channels to 4 with zeros) — the K layout of duo_stem_conv7x7."""
+    w = w.detach().float()
+    full = torch.zeros(w.shape[0], 8, 8, 4, dtype=torch.float32, device=w.device)  # (ky, kx, c)
+    full[:, :7, :7, :3] = w.permute(0, 2, 3, 1)
+    packed = full.view(w.shape[0], 4, 2, 8, 4).permute(0, 1, 3, 2, 4)  # (ky / 2, kx, ky % 2, c)
+    return packed.reshape(w.shape[0], 256).to(dtype).contiguous()
 
 
 def launch_count() -> int:

@@ -6,10 +6,12 @@ MaxPool2d(3, 2, 1), four stages of Bottlenecks).  Built from the BN-folded fp32 
 _fold_batchnorm_): every convolution becomes one implicit-GEMM launch with bias / residual add / ReLU in its epilogue,
 activations stay NHWC 16-bit (fp16 by default) from the packed image to the four taps:
 
-  stem        ops.stem_pack (image -> padded NHWC8, the fp16 range-guard factor folded in) + ops.stem_conv7x7 + ReLU
+  stem        ops.stem_pack (image -> padded row-pair tensor, the fp16 range-guard factor folded in) + ops.stem_conv7x7 + ReLU
   max-pool    ops.maxpool3x3s2
-  Bottleneck  conv1 1x1 + ReLU;  conv2 3x3 stride s + ReLU;  [downsample 1x1 stride s, bias moved into conv3's];
-              conv3 1x1 + bias + identity + ReLU
+  Bottleneck  conv1 1x1 + ReLU;  conv2 3x3 stride s + ReLU;  conv3 1x1 + bias + identity + ReLU (the identity tile is
+              TMA-loaded into the epilogue's staging slot), or — first block of a stage — conv3 with the downsample
+              1x1 / stride s convolution of the block input FUSED: its K blocks are appended to conv3's K loop (second
+              input tensor map, concatenated weights, summed biases), so the shortcut tensor is never written.
 """
 from __future__ import annotations
 
@@ -32,37 +34,47 @@ def _plain_conv(conv, ksize: int, strides=(1, 2)) -> bool:
             and conv.in_channels % 64 == 0 and conv.out_channels % 64 == 0 and conv.padding_mode == "zeros")
 
 
-class _Conv:
-    """One packed convolution: weight [Cout, k*k*Cin] in (ky, kx, c) column order, 16-bit; bias fp32 or None."""
+def _gemm_weight(conv: nn.Conv2d) -> torch.Tensor:
+    """[Cout, Cin, k, k] -> fp32 [Cout, k*k*Cin] in (ky, kx, c) column order."""
+    w = conv.weight.detach().float()
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)
 
-    def __init__(self, conv: nn.Conv2d, dtype: torch.dtype, bias: Optional[torch.Tensor]):
-        w = conv.weight.detach().float()
+
+class _Conv:
+    """One packed convolution: weight [Cout, k*k*Cin (+ Cin2)] 16-bit, bias fp32 or None; `shortcut` = a 1x1 convolution
+    of a second tensor fused into the K loop (the Bottleneck's downsample)."""
+
+    def __init__(self, conv: nn.Conv2d, dtype: torch.dtype, bias: Optional[torch.Tensor], shortcut: Optional[nn.Conv2d] = None):
         self.ksize = int(conv.kernel_size[0])
         self.stride = int(_pair(conv.stride)[0])
-        self.weight = w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(dtype).contiguous()
+        w = _gemm_weight(conv)
+        self.stride2 = 1
+        if shortcut is not None:
+            w = torch.cat([w, _gemm_weight(shortcut)], dim=1)
+            self.stride2 = int(_pair(shortcut.stride)[0])
+        self.weight = w.to(dtype).contiguous()
         self.bias = None if bias is None else bias.detach().float().contiguous()
 
-    def __call__(self, x: torch.Tensor, relu: bool, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
-        return ops.conv2d(x, self.weight, self.bias, self.ksize, self.stride, relu, residual)
+    def __call__(self, x: torch.Tensor, relu: bool, residual: Optional[torch.Tensor] = None,
+                 in2: Optional[torch.Tensor] = None) -> torch.Tensor:
+        return ops.conv2d(x, self.weight, self.bias, self.ksize, self.stride, relu, residual, in2=in2, stride2=self.stride2)
 
 
 class _Bottleneck:
     def __init__(self, blk: nn.Module, dtype: torch.dtype):
         self.c1 = _Conv(blk.conv1, dtype, blk.conv1.bias)
         self.c2 = _Conv(blk.conv2, dtype, blk.conv2.bias)
-        bias3 = blk.conv3.bias.detach().float()
-        self.ds = None
-        if blk.downsample is not None:
-            conv = blk.downsample[0]
-            self.ds = _Conv(conv, dtype, None)  # its bias joins conv3's: relu(conv3(.) + b3 + conv_ds(x) + b_ds)
-            bias3 = bias3 + conv.bias.detach().float()
-        self.c3 = _Conv(blk.conv3, dtype, bias3)
+        self.fused_shortcut = blk.downsample is not None
+        if self.fused_shortcut:  # relu(conv3(.) + b3 + conv_ds(x) + b_ds): one accumulator, one bias
+            ds = blk.downsample[0]
+            self.c3 = _Conv(blk.conv3, dtype, blk.conv3.bias.detach().float() + ds.bias.detach().float(), shortcut=ds)
+        else:
+            self.c3 = _Conv(blk.conv3, dtype, blk.conv3.bias)
 
     def __call__(self, x: torch.Tensor) -> torch.Tensor:
         o = self.c1(x, True)
         o = self.c2(o, True)
-        identity = x if self.ds is None else self.ds(x, False)
-        return self.c3(o, True, identity)
+        return self.c3(o, True, in2=x) if self.fused_shortcut else self.c3(o, True, residual=x)
 
 
 def _parts(trunk: nn.Module, by_scale: bool):
@@ -112,10 +124,7 @@ class OwnTrunk:
         assert dtype in (torch.float16, torch.bfloat16)
         stem, _, layers = _parts(folded, by_scale)
         self.dtype = dtype
-        w = stem.weight.detach().float()  # [Cout, 3, 7, 7]
-        packed = torch.zeros(w.shape[0], 7, 8, 8, dtype=torch.float32, device=w.device)  # (ky, kx padded to 8, c padded to 8)
-        packed[:, :, :7, :3] = w.permute(0, 2, 3, 1)
-        self.stem_w = packed.reshape(w.shape[0], 448).to(dtype).contiguous()
+        self.stem_w = ops.pack_stem_weight(stem.weight, dtype)
         self.stem_b = stem.bias.detach().float().contiguous()
         self.layers: List[List[_Bottleneck]] = [[_Bottleneck(blk, dtype) for blk in layer] for layer in layers]
 

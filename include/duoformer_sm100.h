@@ -243,6 +243,11 @@ typedef struct duo_conv2d_args {
   void* out;            /* NHWC [B, Ho, Wo, Cout], Ho = (H + 2*pad - ksize) / stride + 1    */
   int32_t B, H, W, Cin, Cout;
   int32_t ksize, stride, relu, fp16, out_fp16;
+  /* optional fused projection shortcut (torchvision Bottleneck.downsample: 1x1 convolution of the BLOCK INPUT with
+   * stride stride2, summed into conv3's output): in2 NHWC [B, H2, W2, Cin2], same type as in; its weights are the LAST
+   * Cin2 columns of `weight` ([Cout, ksize*ksize*Cin + Cin2]); (H2 - 1) / stride2 + 1 must equal Ho.  NULL: none. */
+  const void* in2;
+  int32_t H2, W2, Cin2, stride2;
 } duo_conv2d_args;
 int duo_conv2d(const duo_conv2d_args* args, duo_stream_t stream);
 
@@ -250,9 +255,12 @@ int duo_conv2d(const duo_conv2d_args* args, duo_stream_t stream);
  * Trunk stem (torchvision ResNet conv1: 7x7, stride 2, padding 3, 3 input channels, + folded bn1 + ReLU;
  * resnet50ssl.py:35-45 / model_wo_extra_params.py:214-224 child '0'..'2') on the same implicit-GEMM kernel.
  * duo_stem_pack: fp32 image x[b,c,y,x] (element strides given: NCHW or channels-last) times `scale` ->
- *   zero-padded NHWC8 tensor out [B, H, W + 8, 8] (pixel x at column x + 3, channels 3..7 zero), fp16 or bf16.
- * duo_stem_conv7x7: packed -> out NHWC [B, H/2, W/2, Cout]; weight [Cout, 7 * 64] with column (ky, kx, c) at
- *   ky*64 + kx*8 + c (kx < 7, c < 3; every other column zero).  H, W even, Cout % 64 == 0.
+ *   zero-padded row-pair tensor out [B, H + 8, W + 8, 8], fp16 or bf16: out[b,R,X,c] = pixel (R - 3, X - 3),
+ *   out[b,R,X,4 + c] = pixel (R - 2, X - 3) for c < 3, zero outside the image and for c = 3.
+ * duo_stem_conv7x7: packed -> out NHWC [B, H/2, W/2, Cout]; weight [Cout, 4 * 64] with the coefficient of filter tap
+ *   (ky, kx, c) in column (ky / 2) * 64 + kx * 8 + (ky % 2) * 4 + c (ky, kx < 7, c < 3; every other column zero): one
+ *   64-wide K block = 8 pixels x two filter rows x 4 channels = 128 contiguous bytes of the packed tensor, loaded by ONE
+ *   TMA box of overlapping windows.  H, W even, Cout % 64 == 0.
  */
 int duo_stem_pack(const float* x, int64_t stride_b, int64_t stride_c, int64_t stride_h, int64_t stride_w, float scale,
                   void* out, int32_t fp16, int32_t B, int32_t H, int32_t W, duo_stream_t stream);

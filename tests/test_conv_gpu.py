@@ -67,6 +67,23 @@ def test_conv2d_vs_torch(B, H, Cin, Cout, k, stride, res, dtype):
     assert relerr(out, (ref - bias[None, :, None, None]).permute(0, 2, 3, 1)) < tol
 
 
+@pytest.mark.parametrize("B,H,Cmid,Cin2,Cout,stride2", [(4, 56, 64, 64, 256, 1), (5, 28, 128, 256, 512, 2), (3, 7, 512, 1024, 2048, 2),
+                                                       (2, 14, 256, 512, 1024, 2)])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_conv2d_fused_projection_shortcut(B, H, Cmid, Cin2, Cout, stride2, dtype):
+    """conv3 (1x1) + downsample (1x1, stride s) of the block input in one K loop == the sum of the two convolutions."""
+    o = _gen((B, H, H, Cmid), 1).to(dtype)
+    x = _gen((B, H * stride2, H * stride2, Cin2), 2).to(dtype)
+    w3 = _gen((Cout, Cmid, 1, 1), 3, (1.0 / Cmid) ** 0.5).to(dtype)
+    wd = _gen((Cout, Cin2, 1, 1), 4, (1.0 / Cin2) ** 0.5).to(dtype)
+    bias = _gen((Cout,), 5)
+    ref = F.conv2d(o.float().permute(0, 3, 1, 2), w3.float(), bias) + F.conv2d(x.float().permute(0, 3, 1, 2), wd.float(), None, stride=stride2)
+    ref = ref.clamp_min(0).permute(0, 2, 3, 1)
+    w = torch.cat([w3.reshape(Cout, Cmid), wd.reshape(Cout, Cin2)], dim=1).contiguous()
+    out = ops.conv2d(o, w, bias, 1, 1, True, in2=x, stride2=stride2)
+    assert relerr(out, ref) < (2e-3 if dtype == torch.float16 else 1e-2)
+
+
 def test_conv2d_fp16_operands_bf16_output():
     x = _gen((4, 28, 28, 128), 1, 30.0).to(torch.float16)
     w = _gen((256, 128, 3, 3), 2, 1.0).to(torch.float16)  # sums far beyond the fp16 maximum
@@ -96,15 +113,14 @@ def test_stem_vs_torch(B, H, W, dtype):
     bias = _gen((64,), 3)
     scale = 0.5
     packed = ops.stem_pack(x, scale, dtype)
-    assert packed.shape == (B, H, W + 8, 8)
-    want = torch.zeros(B, H, W + 8, 8, device="cuda")
-    want[:, :, 3:3 + W, :3] = (x * scale).permute(0, 2, 3, 1)
+    assert packed.shape == (B, H + 8, W + 8, 8)
+    want = torch.zeros(B, H + 8, W + 8, 8, device="cuda")
+    want[:, 3:3 + H, 3:3 + W, :3] = (x * scale).permute(0, 2, 3, 1)    # padded pixel (R, X)
+    want[:, 2:2 + H, 3:3 + W, 4:7] = (x * scale).permute(0, 2, 3, 1)   # padded pixel (R + 1, X)
     assert torch.equal(packed.float(), want.to(dtype).float())
     # channels-last input gives the same packed tensor
     assert torch.equal(ops.stem_pack(x.contiguous(memory_format=torch.channels_last), scale, dtype), packed)
-    wk = torch.zeros(64, 7, 8, 8, device="cuda")
-    wk[:, :, :7, :3] = w.float().permute(0, 2, 3, 1)
-    out = ops.stem_conv7x7(packed, wk.reshape(64, 448).to(dtype).contiguous(), bias, relu=True)
+    out = ops.stem_conv7x7(packed, ops.pack_stem_weight(w, dtype), bias, relu=True)
     ref = F.conv2d((x * scale).to(dtype).float(), w.float(), bias, stride=2, padding=3).clamp_min(0).permute(0, 2, 3, 1)
     assert out.shape == ref.shape
     assert relerr(out, ref) < (2e-3 if dtype == torch.float16 else 1e-2)
@@ -140,9 +156,10 @@ def test_own_trunk_matches_module_path(size, B):
     lib.backend = "cudnn"
     f_lib = lib.features(trunk, x, "bf16", False)
     assert lib._own is None
-    for k in range(4):
+    assert own.act_scale == lib.act_scale
+    for k in range(4):  # the maps come multiplied by the fp16 range-guard factor
         assert f_own[k].shape == ref[k].shape and f_own[k].dtype == torch.float16
-        e_own, e_lib = relerr(f_own[k], ref[k]), relerr(f_lib[k], ref[k])
+        e_own, e_lib = relerr(f_own[k].float() / own.act_scale, ref[k]), relerr(f_lib[k].float() / lib.act_scale, ref[k])
         assert e_own < 5e-3, (k, e_own)
         assert e_own < 2 * e_lib + 1e-3, (k, e_own, e_lib)
     # second call: the verified fast path alone

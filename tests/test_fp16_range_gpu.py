@@ -99,19 +99,27 @@ def test_unguarded_fp16_trunk_would_overflow():
         model(x.cuda())
 
 
-def test_fused_trunk_mismatch_raises(monkeypatch):
-    """The fused cuDNN conv+bias(+add)+ReLU path is verified once per weight set against the module path; a mismatch
-    is an error — there is no silent fallback."""
+@pytest.mark.parametrize("backend", ["own", "cudnn"])
+def test_fused_trunk_mismatch_raises(monkeypatch, backend):
+    """The fast trunk path (own implicit-GEMM convolutions, or cuDNN's fused conv+bias(+add)+ReLU calls) is verified once
+    per weight set against the module path; a mismatch is an error — there is no silent fallback."""
     from duoformer_tcga_b200 import token_builder as tb
+    from duoformer_tcga_b200 import trunk_convs
 
     case, sd, model = _model()
-    real = tb._fused_trunk_forward
+    model._trunk_runner.backend = backend
 
-    def skewed(t, x, by_scale):
-        f = real(t, x, by_scale)
-        f[2] = f[2] * 1.05
-        return f
+    def skew(real):
+        def skewed(*args, **kwargs):
+            f = real(*args, **kwargs)
+            f[2] = f[2] * 1.05
+            return f
+        return skewed
 
-    monkeypatch.setattr(tb, "_fused_trunk_forward", skewed)
+    if backend == "own":
+        monkeypatch.setattr(trunk_convs.OwnTrunk, "features", skew(trunk_convs.OwnTrunk.features))
+    else:
+        monkeypatch.setattr(tb, "_fused_trunk_forward", skew(tb._fused_trunk_forward))
     with torch.no_grad(), pytest.raises(RuntimeError, match="differs from the module path"):
         model(synth.synth_images(2, seed=34).cuda())
+

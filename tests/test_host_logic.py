@@ -34,9 +34,10 @@ def test_gemm_args_struct_layout_matches_header():
 
 
 def test_conv2d_args_struct_layout_matches_header():
-    # struct duo_conv2d_args: five pointers, then ten int32 (B H W Cin Cout ksize stride relu fp16 out_fp16)
-    assert ctypes.sizeof(_lib.Conv2dArgs) == 80
+    # struct duo_conv2d_args: five pointers, ten int32 (B H W Cin Cout ksize stride relu fp16 out_fp16), in2, four int32
+    assert ctypes.sizeof(_lib.Conv2dArgs) == 104
     assert _lib.Conv2dArgs.out.offset == 32 and _lib.Conv2dArgs.B.offset == 40 and _lib.Conv2dArgs.out_fp16.offset == 76
+    assert _lib.Conv2dArgs.in2.offset == 80 and _lib.Conv2dArgs.stride2.offset == 100
 
 
 def test_own_trunk_eligibility():
@@ -54,8 +55,9 @@ def test_own_trunk_eligibility():
     token_builder._fold_batchnorm_(r50)
     assert trunk_convs.eligible(r50, False)
     own = trunk_convs.OwnTrunk(r50, False, torch.float16)  # packing works on the host
-    assert own.stem_w.shape == (64, 448) and len(own.layers) == 4 and [len(l) for l in own.layers] == [3, 4, 6, 3]
-    assert own.layers[1][0].ds is not None and own.layers[1][0].c2.stride == 2 and own.layers[1][1].ds is None
+    assert own.stem_w.shape == (64, 256) and len(own.layers) == 4 and [len(l) for l in own.layers] == [3, 4, 6, 3]
+    assert own.layers[1][0].fused_shortcut and own.layers[1][0].c2.stride == 2 and not own.layers[1][1].fused_shortcut
+    assert own.layers[1][0].c3.weight.shape == (512, 128 + 256) and own.layers[1][0].c3.stride2 == 2
     assert own.layers[0][0].c2.weight.shape == (64, 9 * 64)
 
 
