@@ -324,7 +324,7 @@ def main():
                        "per_gpu_batch": B, "global_batch": global_batch,
                        "parallelism": f"dp{world} (batch-sharded, NCCL all-gather of logits)" if world > 1 else "single GPU",
                        "precision": "bf16 operands / fp32 accumulate, fp32 residual stream (scale blocks, 98% of FLOPs); "
-                                    "fp16 cuDNN trunk and fp16 token-builder GEMM; patch blocks as 3-pass split-bf16 GEMMs "
+                                    "fp16 ResNet trunk on the own implicit-GEMM convolution kernel (conv_tcgen05) and fp16 token-builder GEMM; patch blocks as 3-pass split-bf16 GEMMs "
                                     "(DESIGN.md precision policy)",
                        "l2": "no flush needed: per-step working set (3.3 GB fp32 tokens + 8 GB activations) >> 126 MB L2"},
             "gpu_launches": int(launches),
@@ -348,6 +348,13 @@ def main():
                              "how": "algorithmic bytes / CUDA-event duration of every LayerNorm and attention launch of the profiled pass",
                              "kernels": hbm},
         }
+        cv = agg.get("conv")
+        if cv is not None and cv["ms"] > 0:  # the trunk's convolutions (own implicit-GEMM kernel), profiled pass
+            line["trunk_convs"] = {"kernel": "conv_tcgen05_kernel", "launches_per_step": cv["n"] / prof_steps,
+                                   "ms_per_step": cv["ms"] / prof_steps, "tflops": cv["flops"] / cv["ms"] / 1e9,
+                                   "algorithmic_gbs": cv["bytes"] / cv["ms"] / 1e6,
+                                   "how": "CUDA events around every duo_conv2d / duo_stem_conv7x7 launch of the profiled pass; "
+                                          "FLOPs = 2 * pixels * Cout * K as executed (the stem's K is padded 147 -> 256)"}
         if library_bar is not None:
             line["library_bar"] = library_bar
         if world == 1 and not args.no_cpu_baseline:
