@@ -2,24 +2,28 @@
 // group and head_dim 64 — the S = 86 case of the 4-scale model (scale_attention.py:28-45,
 // multiscale_attn.py:149-166: softmax(q k^T * scale) v inside every (patch, head)).
 //
-// One persistent CTA of four warps walks (group, head) problems; two CTAs share an SM.
-//   warp 3   : lane 0 issues TMA loads (Q, K, V head slices, one box of S rows x 128 B each,
-//              double-buffered) and all tcgen05.mma; the whole warp transposes V into the K-major
-//              V^T operand (ldmatrix.trans -> st.shared) while the scores are being computed.
+// One persistent CTA of four warps walks (group, head) problems; THREE CTAs share an SM (74 KB of shared memory and
+// 128 TMEM columns each: a problem is a ~3 000-cycle dependent chain — MMA, TMEM round trips, a MUFU-bound softmax,
+// barriers — so the kernel lives on problems in flight; with two CTAs per SM it ran at 0.94 of the HBM peak alone at
+// burst clocks but 0.60 inside the power-capped step at ~1.05 GHz).
+//   warp 3   : lane 0 issues TMA loads (Q, K, V head slices, one box of S rows x 128 B each; the next problem's loads
+//              start as soon as Q K^T has completed and V is transposed) and all tcgen05.mma; the whole warp
+//              transposes V into the K-major V^T operand (ldmatrix.trans -> st.shared) while the scores are computed.
 //   warps 0-2: thread = query row.  scores from TMEM (tcgen05.ld) -> softmax in registers (no
 //              shuffles) -> P (bf16) into shared memory -> after the second MMA, O from TMEM,
 //              scaled by 1/sum, transposed through the warp's (dead) P rows and stored as full
 //              128-byte lines.
-// Loads run two problems ahead: a buffer is refilled as soon as its Q/K have been multiplied and
-// its V transposed.
+// (Round 1 / early round 2: two CTAs per SM with double-buffered Q | K | V, S and O in separate TMEM columns.)
 // (Measured and dropped in round 2: two threads per query row — eight warps per CTA splitting the score / output
 // columns, a named barrier per row quarter for the maximum, a helper warp for half of the V transpose: 0.303 ms per 64
 // images against 0.270 alone, 22.4 against 17.8 ms per step.)
 //   MMA 1    : S[128 x 96] = Q[128 x 64] K^T          4 x UMMA 128x96x16, accumulator columns [0, 96)
-//   MMA 2    : O[128 x 64] = P[128 x 96] V^T^T        ceil(S/16) x UMMA 128x64x16, columns [128, 192)
-// Rows >= S of the M = 128 operands are whatever follows them in shared memory: they only feed
-// accumulator rows that are never read.  Key padding (S..95): P columns are written as zeros and
-// the V padding rows are zeroed once (TMA boxes never touch them), so no NaN can enter a real row.
+//   MMA 2    : O[128 x 64] = P[128 x 96] V^T^T        ceil(S/16) x UMMA 128x64x16, columns [0, 64): O ALIASES S (every
+//              score has been read when P is complete; the next problem's MMA 1 waits until O has been read: `o_read`)
+// Q and K tiles sit 88 rows apart (S <= 88: the model's 86; otherwise 96): rows >= S of the M = 128 / N = 96 operands are
+// whatever follows them in shared memory (K rows for Q, V rows for K): they only feed accumulator rows that are never read
+// and score columns that are masked.  Key padding (S..95): P columns are written as zeros and the V padding rows are
+// zeroed once (TMA boxes never touch them), so no NaN can enter a real row.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -30,14 +34,15 @@ namespace {
 
 constexpr int kDh = 64;
 constexpr int kKeysPad = 96;
-constexpr uint32_t kTile = kKeysPad * 128;       // one Q / K / V head slice: 96 rows x 128 B
-constexpr uint32_t kBuf = 3 * kTile;             // Q | K | V
+constexpr uint32_t kTile = kKeysPad * 128;       // a 96-row tile: V, and each half of P
 constexpr uint32_t kVtBlock = kDh * 128;         // V^T: 64 rows x (64 keys) per block
 constexpr uint32_t kPBytes = 2 * kTile;          // P: keys 0..63 | keys 64..95, 96 rows x 128 B each
-constexpr uint32_t kSmemData = 2 * kBuf + kPBytes + 2 * kVtBlock;
-constexpr uint32_t kSmemBytes = kSmemData + 64;  // 112 KB + barriers: two CTAs per SM (no alignment slack to spare)
-constexpr uint32_t kTmemCols = 256;
-constexpr uint32_t kColS = 0, kColO = 128;
+// Q | K | V with Q and K `qk_rows` rows apart (a multiple of 8: 1024-byte aligned swizzle atoms)
+__host__ __device__ constexpr uint32_t qk_pitch(int S) { return static_cast<uint32_t>(S <= 88 ? 88 : 96) * 128u; }
+__host__ __device__ constexpr uint32_t smem_data(int S) { return 2 * qk_pitch(S) + kTile + kPBytes + 2 * kVtBlock; }
+__host__ __device__ constexpr uint32_t smem_bytes(int S) { return smem_data(S) + 64; }  // S <= 88: 74 KB + barriers, three CTAs per SM
+constexpr uint32_t kTmemCols = 128;
+constexpr uint32_t kColS = 0, kColO = 0;
 
 __device__ __forceinline__ void ldmatrix_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
@@ -47,17 +52,19 @@ __device__ __forceinline__ void ldmatrix_x4_t(uint32_t addr, uint32_t& r0, uint3
 
 // S_CT > 0: S known at compile time (the model's 86); 0: runtime S.
 template <int S_CT>
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(128, 3)
 scale_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __restrict__ out,
                           int S_rt, int H, int64_t problems, float scale_log2e) {
   const int S = S_CT > 0 ? S_CT : S_rt;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = ptx::smem_u32(smem_raw);
   if ((base & 1023u) != 0) __trap();  // the 128-byte swizzle patterns of TMA and UMMA assume 1024-byte aligned tiles
-  const uint32_t p_base = base + 2 * kBuf;
+  const uint32_t kQK = qk_pitch(S);
+  const uint32_t k_tile = base + kQK, v_tile = base + 2 * kQK;
+  const uint32_t p_base = v_tile + kTile;
   const uint32_t vt_base = p_base + kPBytes;
-  const uint32_t bar_base = base + kSmemData;
-  const uint32_t full_bar0 = bar_base, s_full = bar_base + 16, p_ready = bar_base + 24, o_full = bar_base + 32;
+  const uint32_t bar_base = base + smem_data(S);
+  const uint32_t full_bar0 = bar_base, o_read = bar_base + 8, s_full = bar_base + 16, p_ready = bar_base + 24, o_full = bar_base + 32;
   const uint32_t tmem_slot = bar_base + 40;
   uint32_t* tmem_slot_generic = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
 
@@ -67,18 +74,16 @@ scale_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfl
   const uint32_t load_bytes = 3u * static_cast<uint32_t>(S) * 128u;
   const int nk = (S + 15) >> 4;  // 16-key steps of the second MMA
 
-  // V padding rows of both buffers: zero once
-  for (int i = threadIdx.x; i < 2 * (kKeysPad - S) * 8; i += 128) {
-    const int b = i / ((kKeysPad - S) * 8);
-    const int j = i - b * (kKeysPad - S) * 8;
-    const uint32_t dst = base + b * kBuf + 2 * kTile + static_cast<uint32_t>((S + (j >> 3)) * 128 + ((j & 7) << 4));
+  // V padding rows: zero once
+  for (int j = threadIdx.x; j < (kKeysPad - S) * 8; j += 128) {
+    const uint32_t dst = v_tile + static_cast<uint32_t>((S + (j >> 3)) * 128 + ((j & 7) << 4));
     asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0u) : "memory");
   }
   if (warp == 3) {
     if (lane == 0) {
       ptx::prefetch_tmap(&tmap_qkv);
       ptx::mbar_init(full_bar0, 1);
-      ptx::mbar_init(full_bar0 + 8, 1);
+      ptx::mbar_init(o_read, 3);   // one arrival per softmax warp: O (= the S columns) has been read
       ptx::mbar_init(s_full, 1);
       ptx::mbar_init(p_ready, 3);  // one arrival per softmax warp
       ptx::mbar_init(o_full, 1);
@@ -93,16 +98,14 @@ scale_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfl
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_generic;
 
-  auto issue_loads = [&](int b, int64_t prob) {  // warp 3, lane 0
+  auto issue_loads = [&](int64_t prob) {  // warp 3, lane 0
     const int64_t g = prob / H;
     const int h = static_cast<int>(prob - g * H);
-    const uint32_t dst = base + b * kBuf;
-    const uint32_t bar = full_bar0 + 8u * b;
     const int32_t row = static_cast<int32_t>(g * S);
-    ptx::mbar_arrive_expect_tx(bar, load_bytes);
-    ptx::tma_load_2d(dst, &tmap_qkv, bar, h * kDh, row);
-    ptx::tma_load_2d(dst + kTile, &tmap_qkv, bar, D + h * kDh, row);
-    ptx::tma_load_2d(dst + 2 * kTile, &tmap_qkv, bar, 2 * D + h * kDh, row);
+    ptx::mbar_arrive_expect_tx(full_bar0, load_bytes);
+    ptx::tma_load_2d(base, &tmap_qkv, full_bar0, h * kDh, row);
+    ptx::tma_load_2d(k_tile, &tmap_qkv, full_bar0, D + h * kDh, row);
+    ptx::tma_load_2d(v_tile, &tmap_qkv, full_bar0, 2 * D + h * kDh, row);
   };
 
   const int64_t first = blockIdx.x;
@@ -112,21 +115,16 @@ scale_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfl
     // ===================== control warp: TMA, MMA issue, V transpose =====================
     constexpr uint32_t idesc_s = ptx::make_idesc_bf16(128, kKeysPad);
     constexpr uint32_t idesc_o = ptx::make_idesc_bf16(128, kDh);
-    if (lane == 0) {
-      if (first < problems) issue_loads(0, first);
-      if (first + stride < problems) issue_loads(1, first + stride);
-    }
-    uint32_t full_phase = 0;  // bit b = parity to wait for on buffer b
+    if (lane == 0 && first < problems) issue_loads(first);
     int it = 0;
     for (int64_t prob = first; prob < problems; prob += stride, ++it) {
-      const int b = it & 1;
-      const uint32_t buf = base + b * kBuf;
-      ptx::mbar_wait(full_bar0 + 8u * b, (full_phase >> b) & 1u);
-      full_phase ^= (1u << b);
+      ptx::mbar_wait(full_bar0, static_cast<uint32_t>(it & 1));
+      // the previous problem's O sits in the score columns: wait until the softmax warps have read it
+      if (it > 0) ptx::mbar_wait(o_read, static_cast<uint32_t>((it - 1) & 1));
       if (lane == 0) {
         ptx::tc_fence_after();
-        const uint64_t dq = ptx::make_smem_desc_sw128(buf);
-        const uint64_t dk = ptx::make_smem_desc_sw128(buf + kTile);
+        const uint64_t dq = ptx::make_smem_desc_sw128(base);
+        const uint64_t dk = ptx::make_smem_desc_sw128(k_tile);
 #pragma unroll
         for (int k = 0; k < kDh / 16; ++k)
           ptx::umma_bf16(tmem_base + kColS, dq + static_cast<uint64_t>(2 * k), dk + static_cast<uint64_t>(2 * k),
@@ -137,7 +135,6 @@ scale_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfl
       if (it > 0) ptx::mbar_wait(o_full, static_cast<uint32_t>((it - 1) & 1));
       // ---- V[key][d] -> V^T[d][key] (K-major, 128B swizzle, two blocks of 64 keys) ----
       {
-        const uint32_t v_tile = buf + 2 * kTile;
 #pragma unroll 2
         for (int kb = 0; kb < kKeysPad / 8; ++kb) {
           const int key = 8 * kb + (lane & 7);
@@ -160,10 +157,10 @@ scale_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfl
       ptx::fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
-        // this buffer is free once Q K^T has completed (V is already transposed): refill it two problems ahead
-        if (prob + 2 * stride < problems) {
+        // Q | K | V are free once Q K^T has completed (V is already transposed): fetch the next problem
+        if (prob + stride < problems) {
           ptx::mbar_wait(s_full, static_cast<uint32_t>(it & 1));
-          issue_loads(b, prob + 2 * stride);
+          issue_loads(prob + stride);
         }
         ptx::mbar_wait(p_ready, static_cast<uint32_t>(it & 1));
         ptx::tc_fence_after();
@@ -242,6 +239,8 @@ scale_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfl
       ptx::tmem_ld_32x32(taddr + kColO + 32, v1);
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(o_read);  // the score columns may be overwritten by the next problem's Q K^T
       {
         // O row -> this thread's (dead) P row, then the warp stores four complete 128-byte rows per instruction
         float sum_a, sum_b;
@@ -327,19 +326,22 @@ int launch_scale_attention_tc(const void* qkv, void* out, int64_t groups, int S,
   static uint64_t configured = 0;  // per device
   if (first_use_on_device(configured)) {
     DUO_CUDA(cudaFuncSetAttribute(scale_attention_tc_kernel<86>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(kSmemBytes)));
+                                  static_cast<int>(smem_bytes(86))));
     DUO_CUDA(cudaFuncSetAttribute(scale_attention_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(kSmemBytes)));
+                                  static_cast<int>(smem_bytes(96))));
+    // the three-CTAs-per-SM design needs the whole 228 KB carve-out
+    DUO_CUDA(cudaFuncSetAttribute(scale_attention_tc_kernel<86>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    DUO_CUDA(cudaFuncSetAttribute(scale_attention_tc_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   }
   const int64_t problems = groups * H;
-  const int64_t max_ctas = 2LL * device_sm_count();
+  const int64_t max_ctas = 3LL * device_sm_count();
   const unsigned grid = static_cast<unsigned>(problems < max_ctas ? problems : max_ctas);
   if (S == 86)
-    scale_attention_tc_kernel<86><<<grid, 128, kSmemBytes, st>>>(tm, reinterpret_cast<__nv_bfloat16*>(out), S, H, problems,
-                                                                 scale * 1.4426950408889634f);
+    scale_attention_tc_kernel<86><<<grid, 128, smem_bytes(86), st>>>(tm, reinterpret_cast<__nv_bfloat16*>(out), S, H, problems,
+                                                                     scale * 1.4426950408889634f);
   else
-    scale_attention_tc_kernel<0><<<grid, 128, kSmemBytes, st>>>(tm, reinterpret_cast<__nv_bfloat16*>(out), S, H, problems,
-                                                                scale * 1.4426950408889634f);
+    scale_attention_tc_kernel<0><<<grid, 128, smem_bytes(S), st>>>(tm, reinterpret_cast<__nv_bfloat16*>(out), S, H, problems,
+                                                                   scale * 1.4426950408889634f);
   DUO_LAUNCH_CHECK("scale_attention_tc_kernel");
   return DUO_OK;
 }

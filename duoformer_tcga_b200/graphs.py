@@ -58,7 +58,7 @@ class GraphedForward:
         # pin what the graph addresses: workspace buffers, packed operands, the trunk copy, token row maps
         self._pins = [ws.buf for ws in self._workspaces]
         for m in list(model.modules()) + [getattr(model, n, None) for n in ("_trunk_runner", "_token_builder", "_channel_branch")]:
-            for attr in ("_packed", "_trunk", "_maps"):
+            for attr in ("_packed", "_trunk", "_own", "_maps"):
                 v = getattr(m, attr, None)
                 if v is not None:
                     self._pins.append(v)
