@@ -464,21 +464,34 @@ struct MapKey {
   uint32_t estr[5];
   int32_t rank, f16;
 };
-constexpr int kMapCacheSize = 256;
+// Open-addressing hash table (linear probing, FNV-1a over the key bytes): a trunk pass looks up ~200 maps, a linear scan
+// of the cache would put ~10^4 key comparisons on every forward's launch path.
+constexpr int kMapCacheSize = 512;  // slots (power of two); the table is flushed when 3/4 full
 struct MapCache {
   MapKey key[kMapCacheSize];
   CUtensorMap map[kMapCacheSize];
-  int used = 0, next = 0;
+  bool used[kMapCacheSize];
+  int count = 0;
+  MapCache() { memset(used, 0, sizeof(used)); }
 };
 thread_local MapCache g_map_cache;
 
+uint32_t key_hash(const MapKey& k) {
+  const unsigned char* b = reinterpret_cast<const unsigned char*>(&k);
+  uint64_t h = 1469598103934665603ull;
+  for (size_t i = 0; i < sizeof(MapKey); ++i) h = (h ^ b[i]) * 1099511628211ull;
+  return static_cast<uint32_t>(h ^ (h >> 32));
+}
+
 int make_map(CUtensorMap* tm, const MapKey& k) {
   MapCache& mc = g_map_cache;
-  for (int i = 0; i < mc.used; ++i) {
-    if (memcmp(&mc.key[i], &k, sizeof(MapKey)) == 0) {
-      *tm = mc.map[i];
+  uint32_t slot = key_hash(k) & (kMapCacheSize - 1);
+  while (mc.used[slot]) {
+    if (memcmp(&mc.key[slot], &k, sizeof(MapKey)) == 0) {
+      *tm = mc.map[slot];
       return DUO_OK;
     }
+    slot = (slot + 1) & (kMapCacheSize - 1);
   }
   PFN_encodeTiled fn = encode_fn();
   if (fn == nullptr) {
@@ -503,9 +516,15 @@ int make_map(CUtensorMap* tm, const MapKey& k) {
               (unsigned long long)k.dims[3], (unsigned long long)k.dims[4], k.box[0], k.box[1], k.box[2], k.box[3], k.box[4]);
     return DUO_ERR_CUDA;
   }
-  const int slot = mc.used < kMapCacheSize ? mc.used++ : (mc.next = (mc.next + 1) % kMapCacheSize);
+  if (mc.count >= kMapCacheSize * 3 / 4) {  // activation buffers moved too often: start over
+    memset(mc.used, 0, sizeof(mc.used));
+    mc.count = 0;
+    slot = key_hash(k) & (kMapCacheSize - 1);
+  }
+  mc.used[slot] = true;
   mc.key[slot] = k;
   mc.map[slot] = *tm;
+  ++mc.count;
   return DUO_OK;
 }
 
