@@ -401,7 +401,10 @@ int launch_fma(const void* qkv, void* out, int64_t groups, int S, int H, float s
   if (S >= 32 && q_rows > 1) {
     // cooperative CTA per problem: one K/V copy shared by four warps, kQB queries per warp pass
     constexpr int WPR = ElemTraits<Tin>::kWordsPerRow;
-    const int warps = 4;
+#ifndef DUO_FMA_QB_WARPS
+#define DUO_FMA_QB_WARPS 8  // warps sharing one staged K / V copy (4: latency-bound at S = 145, 0.87 ms per block of config 4)
+#endif
+    const int warps = DUO_FMA_QB_WARPS;
     const size_t smem =
         (static_cast<size_t>((S * WPR + S * (WPR + 1) + 3) & ~3) + warps * (kQB * 64 + kQB * KPL * 32)) * 4;
     if (smem > 220 * 1024 || problems >= (int64_t(1) << 31)) {
