@@ -311,9 +311,12 @@ def region_attention(
     out_f32: bool,
     cls_only: bool = False,
     scratch: Optional[PatchScratch] = None,
+    skip_proj: bool = False,
 ) -> torch.Tensor:
     """One patch ("region") attention block without residual / norm / MLP:
     Z <- proj(softmax(q k^T * scale) v)   (scale_attention.py:195-209, multiscale_attn.py:205-219).
+    skip_proj: return the attention output (the kind proj would consume) — the caller has composed this block's proj
+    with the next block's qkv into one linear map (MultiscaleFormer.fuse_patch_linears).
 
     precision "bf16":  Z bf16 [B*N, D], everything bf16.
               "fp32":  Z split [B*N, 2D]; 3-pass split GEMMs; attention in split precision on tcgen05 (N <= 64:
@@ -356,6 +359,8 @@ def region_attention(
         else:
             AO = buf("ao", (rows, kd_ao * D), torch.bfloat16)
             ops.group_attention(QKV, AO, N, num_heads, scale)
+    if skip_proj:
+        return AO
     proj_split = 1 if fp32 else (2 if precision == "mixed" else 0)
     if out_f32:
         out = buf("f32", (rows, D), torch.float32)

@@ -58,16 +58,16 @@ class GraphedForward:
         # pin what the graph addresses: workspace buffers, packed operands, the trunk copy, token row maps
         self._pins = [ws.buf for ws in self._workspaces]
         for m in list(model.modules()) + [getattr(model, n, None) for n in ("_trunk_runner", "_token_builder", "_channel_branch")]:
-            for attr in ("_packed", "_trunk", "_own", "_maps"):
+            for attr in ("_packed", "_trunk", "_own", "_maps", "_patch_cache"):
                 v = getattr(m, attr, None)
                 if v is not None:
-                    self._pins.append(v)
+                    self._pins.append(getattr(v, "_packed", v) if attr == "_patch_cache" else v)
         self._signature = self._model_signature()
 
     def _model_signature(self):
         vt = getattr(self.model, "vision_transformer", self.model)
         return engine.param_signature(self.model, f"{getattr(vt, 'precision', '')}|{getattr(vt, 'patch_precision', '')}|"
-                                                  f"{getattr(vt, 'dead_work_elimination', '')}|{engine.FORWARD_LN_STATS}")
+                                                  f"{getattr(vt, 'dead_work_elimination', '')}|{getattr(vt, 'fuse_patch_linears', '')}|{engine.FORWARD_LN_STATS}")
 
     @torch.no_grad()
     def __call__(self, x: torch.Tensor) -> torch.Tensor:

@@ -169,6 +169,13 @@ class MultiscaleFormer(nn.Module):
         # `precision`; "fp32" runs them as 3-pass split GEMMs so that their bf16 rounding does not
         # compound through the stack (no residual stream to absorb it).
         self.patch_precision: Optional[str] = "fp32"
+        # PatchBlock is proj(attention(qkv(x))) with NO residual / norm / activation (scale_attention.py:234-236), so block
+        # i's proj and block i + 1's qkv are two adjacent linear maps: they are composed once per weight set
+        # (W = W_qkv W_proj in fp64, b = W_qkv b_proj + b_qkv) and the 11 intermediate proj GEMMs of the patch stage
+        # (and the re-rounding of their outputs) disappear.  Split-precision patch stage only (the default).  Nothing for
+        # the 4-scale step (the patch stage is 1.5 % of it), 5 % for the 2-scale model where it is a fifth of the forward.
+        self.fuse_patch_linears = True
+        self._patch_cache = engine.PackCache()
         self._capture: Optional[Dict[str, torch.Tensor]] = None
         self._ws: Optional[engine.Workspace] = None
 
@@ -222,14 +229,23 @@ class MultiscaleFormer(nn.Module):
             cap["patch_in"] = engine.unsplit(Z, prec).view(B, N, D)
         nblk = len(self.blocks)
         cls_only = False
+        fuse = self.fuse_patch_linears and prec == "fp32" and nblk >= 2
+        packs = self._patch_packs(fuse) if fuse else None
         for i, blk in enumerate(self.blocks):
             last = i == nblk - 1
             cls_only = last and self.dead_work_elimination
-            Z = engine.region_attention(Z, blk.pack("bf16" if prec == "bf16" else "fp32"), N, self.num_heads, blk.attn.scale, prec, out_f32=last,
-                                        cls_only=cls_only, scratch=scratch)
+            pk = packs[i] if fuse else blk.pack("bf16" if prec == "bf16" else "fp32")
+            Z = engine.region_attention(Z, pk, N, self.num_heads, blk.attn.scale, prec, out_f32=last,
+                                        cls_only=cls_only, scratch=scratch, skip_proj=fuse and not last)
             if cap is not None:
                 if cls_only:
                     cap[f"patch_block_{i}_cls"] = Z.view(B, D).clone()
+                elif fuse and not last:
+                    # the block output x_i = proj_i(attention output) is not part of the fused data flow: computed for the
+                    # probe only, from the attention output the next block's composed weights consume
+                    xi = torch.empty(B * N, D, dtype=torch.float32, device=X.device)
+                    ops.gemm(Z, pk["proj"][0], pk["proj"][1], xi, ops.EPI_F32, split3=1)
+                    cap[f"patch_block_{i}"] = xi.view(B, N, D)
                 else:
                     cap[f"patch_block_{i}"] = engine.unsplit(Z, prec).view(B, N, D).clone()
         if nblk == 0:
@@ -240,6 +256,25 @@ class MultiscaleFormer(nn.Module):
         # head on the CLS row; fc_norm is computed-and-discarded in the reference (:341-344)
         ops.head(Zf, D if cls_only else N * D, engine._f32(self.head.weight), engine._f32(self.head.bias), logits)
         return logits
+
+    def _patch_packs(self, fuse: bool):
+        """Split-precision operands of the patch blocks; with `fuse`, block i >= 1 carries qkv_i composed with proj_{i-1}."""
+        def build():
+            out = []
+            for i, blk in enumerate(self.blocks):
+                Wq = blk.attn.qkv.weight.detach().double()
+                bq = blk.attn.qkv.bias.detach().double() if blk.attn.qkv.bias is not None else torch.zeros(Wq.shape[0], dtype=torch.float64, device=Wq.device)
+                if fuse and i > 0:
+                    prev = self.blocks[i - 1].attn.proj
+                    Wp = prev.weight.detach().double()
+                    if prev.bias is not None:
+                        bq = Wq @ prev.bias.detach().double() + bq
+                    Wq = Wq @ Wp
+                out.append({"qkv": engine.pack_linear(Wq.float(), bq.float(), "fp32"),
+                            "proj": engine.pack_linear(blk.attn.proj.weight, blk.attn.proj.bias, "fp32")})
+            return out
+
+        return self._patch_cache.packed(build, self.blocks, f"fp32-fuse{int(fuse)}")
 
     @torch.no_grad()
     def forward(self, x: torch.Tensor) -> torch.Tensor:

@@ -203,6 +203,28 @@ def test_statistics_forwarding_on_off_agree(name, batch):
     assert torch.equal(y_on.reshape(-1, 10).argmax(-1), yo.reshape(-1, 10).argmax(-1))
 
 
+@pytest.mark.parametrize("name", ["wo4_d12", "wo2_d12"])
+def test_composed_patch_linears_on_off_agree(name):
+    """proj_i and qkv_{i+1} of the residual-free patch blocks composed into one linear map (fuse_patch_linears) against
+    the block-by-block sequence: same logits up to the split-bf16 rounding of the eleven skipped intermediates."""
+    g = load_golden(name)
+    case = g["case"]
+    model = build_product(case)
+    sd = synth.synth_state_dict(model.state_dict(), seed=g["weight_seed"])
+    model.load_state_dict(sd)
+    model = model.cuda().eval()
+    x = synth.synth_images(4, seed=77).cuda()
+    vt = model.vision_transformer
+    assert vt.fuse_patch_linears
+    with torch.no_grad():
+        y_fused = model(x).float()
+        vt.fuse_patch_linears = False
+        y_seq = model(x).float()
+        vt.fuse_patch_linears = True
+    assert relerr(y_fused, y_seq) < 2e-4, relerr(y_fused, y_seq)
+    assert torch.equal(y_fused.argmax(-1), y_seq.argmax(-1))
+
+
 def test_scale_block_module_updates_every_row():
     """ScaleBlock.forward on its own (the reference's module API, scale_attention.py:90-93) updates ALL S rows of
     every patch — the dead-row elimination belongs to the whole-model callers only."""
