@@ -7,8 +7,10 @@
 // of the QKV GEMM), and both products run as three bf16 UMMAs accumulated in TMEM,
 //     S = Qh Kh^T + Qh Kl^T + Ql Kh^T            O = Ph Vh + Ph Vl + Pl Vh,
 // which reproduces the fp32 result to ~2^-16.  Same structure as scale_attention_tc.cu: one persistent
-// CTA of four warps walks (image, head) problems; warp 3 issues TMA (six head slices per problem, two
-// problems ahead) and the MMAs and transposes Vh, warp 2 transposes Vl, warps 0-1 own one query row
+// CTA of four warps walks (image, head) problems, TWO CTAs per SM (96 KB each: the kernel is a latency chain per
+// problem, round 1 ran one CTA per SM with double-buffered operands); warp 3 issues TMA (six head slices per problem;
+// the next problem's loads start once Q K^T has completed and both V halves are transposed) and the MMAs and
+// transposes Vh, warp 2 transposes Vl, warps 0-1 own one query row
 // per thread: scores from TMEM, softmax in registers, P split into hi | lo in shared memory, O from
 // TMEM scaled by 1 / sum and written as a hi | lo pair for the split proj GEMM.
 // Rows >= N of the M = 128 operands are whatever follows in shared memory (they feed accumulator
@@ -26,7 +28,7 @@ constexpr int kKeys = 64;                         // padded group size
 constexpr uint32_t kTile = kKeys * 128;           // one head slice: 64 rows x 128 B = 8 KB
 constexpr uint32_t kBuf = 6 * kTile;              // Qh Ql Kh Kl Vh Vl
 constexpr uint32_t kPTile = 128 * 128;            // P hi / lo: M = 128 rows x 64 keys
-constexpr uint32_t kSmemData = 2 * kBuf + 2 * kPTile + 2 * kTile;  // + V^T hi, lo
+constexpr uint32_t kSmemData = kBuf + 2 * kPTile + 2 * kTile;  // Q K V (hi, lo) | P hi, lo | V^T hi, lo = 96 KB
 constexpr uint32_t kSmemBytes = kSmemData + 64;
 constexpr uint32_t kTmemCols = 256;
 constexpr uint32_t kColS = 0, kColO = 128;
@@ -57,13 +59,13 @@ __device__ __forceinline__ void transpose_v(uint32_t v_tile, uint32_t vt_tile, i
   }
 }
 
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(128, 2)
 patch_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __restrict__ out,
                           int N, int H, int64_t problems, float scale_log2e) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = ptx::smem_u32(smem_raw);
   if ((base & 1023u) != 0) __trap();
-  const uint32_t p_base = base + 2 * kBuf;          // P hi, P lo
+  const uint32_t p_base = base + kBuf;              // P hi, P lo
   const uint32_t vt_base = p_base + 2 * kPTile;     // V^T hi, V^T lo
   const uint32_t bar_base = base + kSmemData;
   const uint32_t full_bar0 = bar_base, s_full = bar_base + 16, p_ready = bar_base + 24, o_full = bar_base + 32;
@@ -77,18 +79,17 @@ patch_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfl
   const uint32_t load_bytes = 6u * static_cast<uint32_t>(N) * 128u;
   const int nk = (N + 15) >> 4;
 
-  // V padding rows (hi and lo, both buffers): zero once
-  for (int i = threadIdx.x; i < 4 * (kKeys - N) * 8; i += 128) {
-    const int t = i / ((kKeys - N) * 8);  // buffer * 2 + (hi / lo)
+  // V padding rows (hi and lo): zero once
+  for (int i = threadIdx.x; i < 2 * (kKeys - N) * 8; i += 128) {
+    const int t = i / ((kKeys - N) * 8);  // hi / lo
     const int j = i - t * (kKeys - N) * 8;
-    const uint32_t dst = base + (t >> 1) * kBuf + (4 + (t & 1)) * kTile + static_cast<uint32_t>((N + (j >> 3)) * 128 + ((j & 7) << 4));
+    const uint32_t dst = base + (4 + t) * kTile + static_cast<uint32_t>((N + (j >> 3)) * 128 + ((j & 7) << 4));
     asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0u) : "memory");
   }
   if (warp == 3) {
     if (lane == 0) {
       ptx::prefetch_tmap(&tmap_qkv);
       ptx::mbar_init(full_bar0, 1);
-      ptx::mbar_init(full_bar0 + 8, 1);
       ptx::mbar_init(s_full, 1);
       ptx::mbar_init(p_ready, 2);   // one arrival per softmax warp
       ptx::mbar_init(o_full, 1);
@@ -105,11 +106,11 @@ patch_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfl
   const uint32_t tmem_base = *tmem_slot_generic;
 
   // qkv row = [hi: q k v | lo: q k v], each 3 * D wide
-  auto issue_loads = [&](int b, int64_t prob) {  // warp 3, lane 0
+  auto issue_loads = [&](int64_t prob) {  // warp 3, lane 0
     const int64_t g = prob / H;
     const int h = static_cast<int>(prob - g * H);
-    const uint32_t dst = base + b * kBuf;
-    const uint32_t bar = full_bar0 + 8u * b;
+    const uint32_t dst = base;
+    const uint32_t bar = full_bar0;
     const int32_t row = static_cast<int32_t>(g * N);
     ptx::mbar_arrive_expect_tx(bar, load_bytes);
 #pragma unroll
@@ -125,17 +126,11 @@ patch_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfl
 
   if (warp == 3) {
     // ===================== control warp: TMA, MMA issue, V^T hi =====================
-    if (lane == 0) {
-      if (first < problems) issue_loads(0, first);
-      if (first + stride < problems) issue_loads(1, first + stride);
-    }
-    uint32_t full_phase = 0;
+    if (lane == 0 && first < problems) issue_loads(first);
     int it = 0;
     for (int64_t prob = first; prob < problems; prob += stride, ++it) {
-      const int b = it & 1;
-      const uint32_t buf = base + b * kBuf;
-      ptx::mbar_wait(full_bar0 + 8u * b, (full_phase >> b) & 1u);
-      full_phase ^= (1u << b);
+      const uint32_t buf = base;
+      ptx::mbar_wait(full_bar0, static_cast<uint32_t>(it & 1));
       if (lane == 0) {
         ptx::tc_fence_after();
         const uint64_t dqh = ptx::make_smem_desc_sw128(buf), dql = ptx::make_smem_desc_sw128(buf + kTile);
@@ -160,9 +155,9 @@ patch_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfl
       __syncwarp();
       if (lane == 0) {
         ptx::mbar_wait(vt_ready, static_cast<uint32_t>(it & 1));  // V^T lo (warp 2)
-        if (prob + 2 * stride < problems) {
+        if (prob + stride < problems) {
           ptx::mbar_wait(s_full, static_cast<uint32_t>(it & 1));  // Q / K consumed, both V halves transposed
-          issue_loads(b, prob + 2 * stride);
+          issue_loads(prob + stride);
         }
         ptx::mbar_wait(p_ready, static_cast<uint32_t>(it & 1));
         ptx::tc_fence_after();
@@ -185,14 +180,11 @@ patch_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfl
     }
   } else if (warp == 2) {
     // ===================== helper warp: V^T lo =====================
-    uint32_t full_phase = 0;
     int it = 0;
     for (int64_t prob = first; prob < problems; prob += stride, ++it) {
-      const int b = it & 1;
-      ptx::mbar_wait(full_bar0 + 8u * b, (full_phase >> b) & 1u);
-      full_phase ^= (1u << b);
+      ptx::mbar_wait(full_bar0, static_cast<uint32_t>(it & 1));
       if (it > 0) ptx::mbar_wait(o_full, static_cast<uint32_t>((it - 1) & 1));
-      transpose_v(base + b * kBuf + 5 * kTile, vt_base + kTile, lane);
+      transpose_v(base + 5 * kTile, vt_base + kTile, lane);
       ptx::fence_proxy_async();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(vt_ready);
@@ -325,7 +317,7 @@ int launch_patch_attention_tc(const void* qkv, void* out, int64_t groups, int N,
     DUO_CUDA(cudaFuncSetAttribute(patch_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(kSmemBytes)));
   const int64_t problems = groups * H;
-  const int64_t max_ctas = device_sm_count();
+  const int64_t max_ctas = 2LL * device_sm_count();
   const unsigned grid = static_cast<unsigned>(problems < max_ctas ? problems : max_ctas);
   patch_attention_tc_kernel<<<grid, 128, kSmemBytes, st>>>(tm, reinterpret_cast<__nv_bfloat16*>(out), N, H, problems,
                                                            scale * 1.4426950408889634f);
