@@ -45,13 +45,16 @@ constexpr int kThreads = 32 * (kEpiWarps + 2);  // + TMA producer warp + MMA iss
 // a slot is filled and TMA-stored; with one, the residual chunk is TMA-LOADED into the slot kSlots - 1 chunks ahead
 // (also across tile boundaries, so the reads overlap the MMAs of the tile), updated in place and stored — the residual
 // never travels through per-thread global loads (first version: 64 B per thread and row, 2.9 TB/s).
-constexpr int kSlots = 3;
 constexpr uint32_t kSlotBytes = 32 * 128;
-constexpr uint32_t kStagingBytesPerWarp = kSlots * kSlotBytes;
 
 template <int BLOCK_N>
 struct ConvCfg {
-  static constexpr int kStages = BLOCK_N == 128 ? 4 : 5;
+  // 128 x 256 tiles (Cout % 256 == 0 and at least two waves of them): a third less L2 -> SM operand traffic per FLOP than
+  // 128 x 128 — the 128-wide tiles of layers 3 - 4 sit at ~830 TFLOP/s = ~13 TB/s of operand traffic, the L2 limit; the
+  // 48 KB stages leave room for three of them and two staging slots per warp.
+  static constexpr int kStages = BLOCK_N == 256 ? 3 : (BLOCK_N == 128 ? 4 : 5);
+  static constexpr int kSlots = BLOCK_N == 256 ? 2 : 3;
+  static constexpr uint32_t kStagingBytesPerWarp = kSlots * kSlotBytes;
   static constexpr uint32_t kABytes = kBlockM * kBlockK * 2;
   static constexpr uint32_t kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
@@ -166,6 +169,8 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
                     const __grid_constant__ CUtensorMap tmap_in2, const ConvParams p) {
   using C = ConvCfg<BLOCK_N>;
   constexpr int kStages = C::kStages;
+  constexpr int kSlots = C::kSlots;
+  constexpr uint32_t kStagingBytesPerWarp = C::kStagingBytesPerWarp;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -580,7 +585,11 @@ int run_conv(const CUtensorMap& tmap_in, const CUtensorMap& tmap_in2, ConvParams
   const int tiles_w = p.Wo >> bw_log2, tiles_h = p.Ho >> bh_log2;
   const int64_t m_blocks = static_cast<int64_t>(tiles_w) * tiles_h * ((p.B + bb - 1) / bb);
   p.num_m_blocks = static_cast<int32_t>(m_blocks);
-  const int block_n = p.Cout % 128 == 0 ? 128 : 64;
+  int block_n = p.Cout % 128 == 0 ? 128 : 64;
+  // (with a residual the two staging slots per warp of the 256-wide variant prefetch too little: 0.241 -> 0.257 ms on
+  // layer 2's conv3; those keep 128-wide tiles and three slots)
+  if (residual == nullptr && p.Cout % 256 == 0 && m_blocks * (p.Cout / 256) >= 2 * static_cast<int64_t>(device_sm_count()))
+    block_n = 256;
   p.num_n_blocks = p.Cout / block_n;
   const int64_t tiles = m_blocks * p.num_n_blocks;
   // FastDiv: x * d < 2^40 for every quotient taken (x <= tiles, d <= 2^15)
@@ -629,6 +638,7 @@ int run_conv(const CUtensorMap& tmap_in, const CUtensorMap& tmap_in2, ConvParams
     rc = make_map(&tr, ko);
     if (rc != DUO_OK) return rc;
   }
+  if (block_n == 256) return dispatch_conv<256>(out_f16, residual != nullptr, tmap_in, tw, to, tr, tmap_in2, p, st);
   if (block_n == 128) return dispatch_conv<128>(out_f16, residual != nullptr, tmap_in, tw, to, tr, tmap_in2, p, st);
   return dispatch_conv<64>(out_f16, residual != nullptr, tmap_in, tw, to, tr, tmap_in2, p, st);
 }

@@ -42,6 +42,8 @@ CASES = [
     (2, 24, 512, 512, 3, 2, False),    # 384 x 384 input: layer4 stride 2
     (3, 7, 3840, 768, 3, 1, False),    # channel-token branch, first 3x3
     (2, 10, 64, 128, 3, 1, True),      # map size with a single factor of two
+    (200, 14, 256, 256, 3, 1, False),  # enough tiles for the 128 x 256 tile variant (layer 3 at batch >= 200)
+    (200, 14, 256, 512, 1, 1, True),   # same size with a residual (keeps 128 x 128 tiles)
 ]
 
 
