@@ -86,6 +86,20 @@ def test_conv2d_fused_projection_shortcut(B, H, Cmid, Cin2, Cout, stride2, dtype
     assert relerr(out, ref) < (2e-3 if dtype == torch.float16 else 1e-2)
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,stride", [(2, 12, 20, 64, 64, 3, 1), (3, 9, 15, 64, 128, 3, 2), (1, 5, 24, 128, 64, 1, 1),
+                                                     (2, 16, 6, 64, 64, 3, 2), (1, 1, 1, 64, 64, 3, 1)])
+def test_conv2d_non_square_maps(B, H, W, Cin, Cout, k, stride):
+    """Rectangular and odd-sized maps: the tile box takes whatever powers of two divide the OUTPUT width / height (down to
+    1 x 1 x 128 pixels), the rest comes from the batch."""
+    x = _gen((B, H, W, Cin), 1).half()
+    w = _gen((Cout, Cin, k, k), 2, (2.0 / (Cin * k * k)) ** 0.5).half()
+    bias = _gen((Cout,), 3)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, stride=stride, padding=k // 2).clamp_min(0).permute(0, 2, 3, 1)
+    out = ops.conv2d(x, w.permute(0, 2, 3, 1).reshape(Cout, -1).contiguous(), bias, k, stride, True)
+    assert out.shape == ref.shape
+    assert relerr(out, ref) < 2e-3
+
+
 def test_conv2d_fp16_operands_bf16_output():
     x = _gen((4, 28, 28, 128), 1, 30.0).to(torch.float16)
     w = _gen((256, 128, 3, 3), 2, 1.0).to(torch.float16)  # sums far beyond the fp16 maximum
