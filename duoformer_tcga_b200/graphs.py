@@ -2,7 +2,7 @@
 
 At batch 2 a DuoFormer forward is ~130 kernel launches of a few microseconds each: the GPU waits
 for Python.  Every launch of this package is capture-safe (enqueue-only, no host syncs, TMA
-descriptors passed by value), so the forward — cuDNN trunk included — can be captured once per
+descriptors passed by value), so the forward — the trunk's convolution launches included — can be captured once per
 input shape and replayed with a single `cudaGraphLaunch`.
 
 A captured graph bakes in device ADDRESSES.  Everything it reads or writes is therefore owned (or pinned) by the

@@ -91,8 +91,8 @@ class MyModel(nn.Module):
 
     @torch.no_grad()
     def channel_branch(self, feats) -> torch.Tensor:
-        """[B, P, D] fp32 channel token (model.py:279-289).  bf16 mode: im2col + tcgen05 GEMMs
-        (channel_branch.py); fp32 mode: the fp32 cuDNN modules with TF32 off."""
+        """[B, P, D] fp32 channel token (model.py:279-289).  bf16 mode: implicit-GEMM convolutions on
+        tcgen05 (channel_branch.py); fp32 mode: the fp32 cuDNN modules with TF32 off."""
         if self.precision == "bf16":
             if self._channel_branch is None:
                 self._channel_branch = ChannelBranch(self.chann_proj1, self.chann_proj2, self.chann_proj_all)

@@ -3,8 +3,8 @@
 Drop-in for models/model_wo_extra_params.py:29-302 of the reference: same constructor
 signature (plus the additive keyword `pretrained`, which build_model_no_extra_params already
 passes, `__init__.py:53,69`, App. A D2/D3), same attribute names = same state_dict keys.
-Forward: torch/cuDNN ResNet trunk -> fused projection/token-builder kernel -> MultiscaleFormer
-kernels.  CUDA + eval only; there is no CPU fallback.
+Forward: ResNet trunk on the package's implicit-GEMM convolution kernel (trunk_convs.py; fp32 mode: cuDNN fp32) -> fused
+projection/token-builder kernel -> MultiscaleFormer kernels.  CUDA + eval only; there is no CPU fallback.
 """
 from __future__ import annotations
 
@@ -123,7 +123,7 @@ class MyModel_no_extra_params(nn.Module):
     @torch.no_grad()
     def channel_branch(self, feats) -> torch.Tensor:
         """Channel token [B, P, D] fp32 from the four stage maps (model_wo_extra_params.py:236-248).
-        bf16 mode: im2col + tcgen05 GEMMs (channel_branch.py); fp32 mode: fp32 cuDNN modules."""
+        bf16 mode: implicit-GEMM convolutions on tcgen05 (channel_branch.py); fp32 mode: fp32 cuDNN modules."""
         if self.precision == "bf16":
             if self._channel_branch is None:
                 self._channel_branch = ChannelBranch(self.chann_proj1, self.chann_proj2, self.chann_proj_all)

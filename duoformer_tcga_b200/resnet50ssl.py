@@ -1,8 +1,8 @@
 """ResNet-50 trunks that return the four stage feature maps (producer of the token builder).
 
 Mirrors models/resnet50ssl.py of the reference (ResNetTrunk :12-27, ResNetTrunkByScale :30-45,
-resnet50FeatureExtractor :60-79).  The convolutional trunk itself stays on torch / cuDNN
-(input producer of the hot path).  Weight download (Lunit TCGA SSL
+resnet50FeatureExtractor :60-79).  These classes only hold the parameters (state_dict schema); the forward of the
+bf16 path runs the BN-folded trunk on the package's own convolution kernel (trunk_convs.py, csrc/conv_tcgen05.cu).  Weight download (Lunit TCGA SSL
 checkpoints, :48-57) needs network access and is only attempted when `pretrained=True`; a
 local file of the reference's name is used when present.
 """
