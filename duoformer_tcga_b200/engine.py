@@ -182,7 +182,16 @@ def _scale_chunk(X, g0, ng, buf, blocks, num_heads, scale, eps, precision, captu
     def run_block(i: int, blk: Dict, have_ln1: bool) -> bool:
         """One scale block; have_ln1: Ha / ST hold this block's forwarded norm1 input.  Returns the same for the next."""
         last = i == L - 1
-        if have_ln1:
+        if have_ln1 and live_only_last and last:
+            # Last scale block: keys and values for every token, but only the s = 0 QUERY of each patch is ever used
+            # (below) — the q third of the projection runs on those rows alone (A, output and statistics are the strided
+            # s = 0 views; the statistics are gathered densely first: the kernel indexes them by row)
+            w, b = blk["qkv_ln"]
+            st = STS[st_cur[0]]
+            ops.gemm(Ha, w[D:], b[D:], QKV[:, D:], ops.EPI_BF16, ln_stats=st, ln_eps=eps)
+            st0 = st.view(ng, S, D // STAT_COLS, 2)[:, 0].contiguous()
+            ops.gemm(Ha.view(ng, S, D)[:, 0, :], w[:D], b[:D], QKV.view(ng, S, 3 * D)[:, 0, :D], ops.EPI_BF16, ln_stats=st0, ln_eps=eps)
+        elif have_ln1:
             w, b = blk["qkv_ln"]
             ops.gemm(Ha, w, b, QKV, ops.EPI_BF16, ln_stats=STS[st_cur[0]], ln_eps=eps)
         else:

@@ -197,7 +197,9 @@ def test_statistics_forwarding_on_off_agree(name, batch):
             engine.FORWARD_LN_STATS = True
         yo = oracle_forward(case, x, sd)
     depth = case["depth"]
-    assert n_off - n_on == 2 * depth - (2 if model.vision_transformer.dead_work_elimination else 1), (n_on, n_off)
+    # (with the dead rows of the last block skipped, the forwarding path runs that block's q projection as an extra
+    # launch on the live rows)
+    assert n_off - n_on == 2 * depth - (3 if model.vision_transformer.dead_work_elimination else 1), (n_on, n_off)
     assert relerr(y_on, y_off) < 1.5e-2  # two valid bf16 rounding sequences, each within ~8e-3 of the reference
     assert relerr(y_on, yo) < 2e-2 and relerr(y_off, yo) < 2e-2
     assert torch.equal(y_on.reshape(-1, 10).argmax(-1), yo.reshape(-1, 10).argmax(-1))
