@@ -61,6 +61,24 @@ def test_own_trunk_eligibility():
     assert own.layers[0][0].c2.weight.shape == (64, 9 * 64)
 
 
+def test_conv_tile_coordinates_multiply_shift_is_exact():
+    """csrc/conv_tcgen05.cu takes tile coordinates with floor(x / d) = ((x << 24) * ceil(2^40 / d)) >> 64 instead of integer
+    divisions; exact for x < 2^24 tiles and d < 2^15 (the host refuses larger problems).  Restated here on Python integers."""
+    import random
+
+    def fast_div(x, d):
+        return ((x << 24) * (((1 << 40) + d - 1) // d)) >> 64
+
+    rnd = random.Random(0)
+    for _ in range(200000):
+        d, x = rnd.randint(1, (1 << 15) - 1), rnd.randint(0, (1 << 24) - 1)
+        assert fast_div(x, d) == x // d, (x, d)
+    for d in (1, 2, 3, 7, 49, 98, 392, 6272, 25088, 32767):
+        for x in list(range(0, 300)) + [(1 << 24) - 1, d * 511 - 1, d * 511]:
+            if x < (1 << 24):
+                assert fast_div(x, d) == x // d, (x, d)
+
+
 def test_ops_refuse_cpu_tensors():
     a = torch.zeros(128, 64, dtype=torch.bfloat16)
     w = torch.zeros(128, 64, dtype=torch.bfloat16)
